@@ -1,0 +1,388 @@
+#!/usr/bin/env python
+"""Benchmark of the video-to-voxel hot path (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+Workload (config.workload): BASELINE config 2 — the train_v2v_e2vid_10k data
+path: WebVid-shaped synthetic clips uint8 [121,480,640], num_bins=5,
+frames_per_bin=1, thresholds / noise parameters sampled per clip by the
+reference's law (data/v2v_datasets.py:368-386) with the shipped ranges
+(config/train_v2v_e2vid_10k.yaml:72-75), noise generated in-kernel (Philox).
+A step = one pass of the fused kernel over one batch of clips per GPU.
+
+* value      : whole-job Mpix-frames/s (pixel-intervals/s / 1e6), inputs resident in HBM, CUDA-event timed.
+* e2e        : same metric through the host-buffer API (pinned uint8 frames in, float32 voxels back in
+               pinned host memory; H2D + kernel + D2H inside the timed region).
+* roofline   : algorithmic bytes (1 B in + 4 B out per pixel-interval, +1 B/pixel for frame 0) / launch time
+               against the measured HBM copy bandwidth in MEASURED_PEAKS.json.
+* cpu_baseline: the NumPy oracle port of the reference's ESIM core timed on this host's cores.
+
+Under torchrun (N>1) every rank simulates its own clips (clip-sharded, weak scaling, no data-path
+collective); one NCCL all-reduce of the event-count statistics closes the timed region.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N_FRAMES, H, W, BINS, FPB = 121, 480, 640, 5, 1
+TRAIN_CFG = dict(num_bins=BINS, frames_per_bin=FPB, threshold_range=[0.05, 2], max_thres_pos_neg_gap=1.5,
+                 base_noise_std_range=[0, 0.1], hot_pixel_fraction_range=[0, 0.001], hot_pixel_std_range=[0, 10])
+PIX_INTERVALS_PER_CLIP = (N_FRAMES - 1) * H * W
+ALGO_BYTES_PER_CLIP = H * W * (N_FRAMES * 1 + (N_FRAMES - 1) // FPB * 4)       # 184.6 MB
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def ncu_traffic():
+    """dram bytes per launch of the dominant kernel from the committed ncu capture (profiles/), else None."""
+    p = os.path.join(ROOT, "profiles", "esim_traffic.json")
+    if os.path.exists(p):
+        try:
+            return json.load(open(p))
+        except Exception:
+            return None
+    return None
+
+
+# ----------------------------------------------------------------------------------------------
+# CPU baseline: NumPy port of the reference's ESIM core (oracle/), one clip per worker process
+# ----------------------------------------------------------------------------------------------
+
+def _cpu_clip_job(args):
+    seed, n_frames, h, w = args
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import v2v_oracle as orc
+    g = np.random.Generator(np.random.PCG64(seed))
+    base = g.integers(0, 256, size=(h, w)).astype(np.int16)
+    steps = g.integers(-6, 7, size=(n_frames, h, w), dtype=np.int16)
+    steps[0] = 0
+    vid = np.clip(base[None] + np.cumsum(steps, axis=0, dtype=np.int16), 0, 255).astype(np.uint8)
+    rs = np.random.RandomState(seed)
+    p = orc.sample_esim_params(rs, TRAIN_CFG["threshold_range"], TRAIN_CFG["max_thres_pos_neg_gap"],
+                               TRAIN_CFG["base_noise_std_range"], TRAIN_CFG["hot_pixel_fraction_range"],
+                               TRAIN_CFG["hot_pixel_std_range"])
+    t0 = time.perf_counter()
+    # the timed part is what the reference's imgs_to_voxels does: draws + simulation + binning + float32 cast
+    u0, hot, gs = orc.esim_draw_randomness(n_frames, h, w, p["hot_pixel_fraction"], p["hot_pixel_std"], rs)
+    iv = orc.esim_video_to_voxel(vid, p["pos_thres"], p["neg_thres"], p["base_noise_std"], u0, hot, gs, False)
+    vox = orc.bin_accumulate(iv, BINS, FPB).astype(np.float32)
+    dt = time.perf_counter() - t0
+    return dt, float(np.abs(vox).sum())
+
+
+def cpu_reference_run(n_frames, clips, procs):
+    """Simulate `clips` clips of [n_frames,H,W] on `procs` processes; returns wall seconds."""
+    import multiprocessing as mp
+    jobs = [(1000 + i, n_frames, H, W) for i in range(clips)]
+    t0 = time.perf_counter()
+    if procs == 1:
+        res = [_cpu_clip_job(j) for j in jobs]
+    else:
+        with mp.get_context("spawn").Pool(procs) as pool:
+            pool.map(_cpu_clip_job, [(0, 2, 8, 8)] * procs)        # warm the workers (imports) outside the timing
+            t0 = time.perf_counter()
+            res = pool.map(_cpu_clip_job, jobs)
+    wall = time.perf_counter() - t0
+    return wall, res
+
+
+def cpu_baseline(cores):
+    n_frames = 41                                                   # bounded sample: 1/3-length clips
+    wall, _ = cpu_reference_run(n_frames, cores, cores)
+    pix = cores * (n_frames - 1) * H * W
+    return {"value": pix / wall / 1e6, "unit": "Mpix-frames/s", "cores": cores, "kind": "port",
+            "sample": f"{cores} clips uint8 [{n_frames},{H},{W}] (1/3-length config-2 clips), one per process, "
+                      f"NumPy oracle port of data/v2v_core_esim.py incl. MT19937 noise draws, binning, float32 cast",
+            "clips_per_s_equiv": pix / wall / PIX_INTERVALS_PER_CLIP, "wall_s": wall}
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    n_frames = 41
+    times = []
+    import multiprocessing as mp
+    jobs_per_step = cores
+    with mp.get_context("spawn").Pool(cores) as pool:
+        pool.map(_cpu_clip_job, [(0, 2, 8, 8)] * cores)
+        for s in range(args.warmup + args.steps):
+            jobs = [(5000 + s * jobs_per_step + i, n_frames, H, W) for i in range(jobs_per_step)]
+            t0 = time.perf_counter()
+            pool.map(_cpu_clip_job, jobs)
+            if s >= args.warmup:
+                times.append(time.perf_counter() - t0)
+    total = sum(times)
+    pix = args.steps * jobs_per_step * (n_frames - 1) * H * W
+    val = pix / total / 1e6
+    line = {
+        "impl": "reference", "metric": "video_to_voxel_throughput", "value": val, "unit": "Mpix-frames/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "clips_per_s": pix / total / PIX_INTERVALS_PER_CLIP,
+        "config": workload_config(jobs_per_step, f"step = {jobs_per_step} clips of [{n_frames},{H},{W}] on {cores} host processes"),
+        "cpu_baseline": {"value": val, "unit": "Mpix-frames/s", "cores": cores, "kind": "port",
+                         "sample": f"{args.steps} steps x {jobs_per_step} clips uint8 [{n_frames},{H},{W}], NumPy oracle "
+                                   "port of the reference ESIM path (the reference is pure Python/NumPy; nothing to compile)"},
+        "e2e": {"value": val, "unit": "Mpix-frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def workload_config(clips_per_step, note=""):
+    return {"workload": "BASELINE config 2: train_v2v_e2vid_10k data path, synthetic WebVid-shaped clips uint8 "
+                        f"[{N_FRAMES},{H},{W}], num_bins={BINS}, frames_per_bin={FPB}, per-clip thresholds U[0.05,2]x gap U[1,1.5], "
+                        "base_noise_std U[0,0.1], hot_pixel_fraction U[0,0.001], hot_pixel_std U[0,10], in-kernel Philox noise",
+            "clips_per_step_per_gpu": clips_per_step, "frames": N_FRAMES, "height": H, "width": W, "num_bins": BINS,
+            "l2": "inputs+outputs per step exceed the 126 MB L2 (no flush needed)", "note": note}
+
+
+# ----------------------------------------------------------------------------------------------
+# clocks sampler
+# ----------------------------------------------------------------------------------------------
+
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.rows.append((time.perf_counter(), ln.strip()))
+
+    def stop(self, t0, t1):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], None, set()
+        for t, ln in self.rows:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                mx = float(f[1])
+                if t0 - 0.05 <= t <= t1 + 0.05:
+                    sm.append(float(f[0]))
+                    for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
+                        if v.lower().startswith("active"):
+                            reasons.add(name)
+            except ValueError:
+                continue
+        if not sm:      # timed region shorter than one sample: take every sample we have
+            sm = [float(ln.split(",")[0]) for _, ln in self.rows if ln and ln.split(",")[0].strip().replace(".", "").isdigit()]
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------------------------
+# our arm
+# ----------------------------------------------------------------------------------------------
+
+def make_clips(torch, dev, clips, seed):
+    """Temporally correlated random-walk clips generated on the device (SURVEY §8(d) synthetic input)."""
+    g = torch.Generator(device=dev)
+    g.manual_seed(seed)
+    out = torch.empty((clips, N_FRAMES, H, W), dtype=torch.uint8, device=dev)
+    for b in range(clips):
+        base = torch.randint(0, 256, (H, W), generator=g, device=dev, dtype=torch.int16)
+        steps = torch.randint(-6, 7, (N_FRAMES, H, W), generator=g, device=dev, dtype=torch.int16)
+        steps[0] = 0
+        out[b] = (base[None] + torch.cumsum(steps, dim=0)).clamp_(0, 255).to(torch.uint8)
+    return out
+
+
+def run_ours(args):
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    cores = os.cpu_count() or 1
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cpu = cpu_baseline(cores)                                  # before CUDA is initialised in this process
+
+    import torch
+    import v2v_b200 as v2v
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+    B = args.clips
+    vz = v2v.V2VVoxelizer(TRAIN_CFG, device=dev)
+    rs = np.random.RandomState(1234 + rank)
+    params = vz.sample_batch_params(B, rs=rs)
+    frames = make_clips(torch, dev, B, 100 + rank)
+    T = (N_FRAMES - 1) // (BINS * FPB)
+    out = torch.empty((B, T, BINS, H, W), dtype=torch.float32, device=dev)
+    col = lambda k: torch.tensor([p[k] for p in params], dtype=torch.float64, device=dev)
+    pos, neg, std, frac, hstd = (col(k) for k in ("pos_thres", "neg_thres", "base_noise_std", "hot_pixel_fraction", "hot_pixel_std"))
+    stats_total = torch.zeros(2, dtype=torch.int64, device=dev)
+
+    def step(i):
+        o = v2v.frames_to_voxel(frames, pos, neg, num_bins=BINS, frames_per_bin=FPB, noise="philox", base_noise_std=std,
+                                hot_pixel_fraction=frac, hot_pixel_std=hstd, seed=args.seed, clip_index_base=(i * world + rank) * B,
+                                with_stats=True, out=out)
+        return o
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    for i in range(args.warmup):
+        step(i)
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.25)
+    launches0 = v2v.launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    t_wall0 = time.perf_counter()
+    ev0.record()
+    for i in range(args.steps):
+        o = step(args.warmup + i)
+        stats_total += o.stats.sum(dim=0)
+    if dist is not None:
+        dist.all_reduce(stats_total)                               # the only collective: event-count statistics
+    ev1.record()
+    barrier()
+    t_wall1 = time.perf_counter()
+    launches = v2v.launch_count() - launches0
+    ms = ev0.elapsed_time(ev1)
+    if dist is not None:
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    clocks = sampler.stop(t_wall0, t_wall1) if rank == 0 else None
+
+    # kernel-only duration for the roofline: per-launch CUDA events on the launching stream
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    barrier()
+    for i, (a, b) in enumerate(evs):
+        a.record()
+        v2v.frames_to_voxel(frames, pos, neg, num_bins=BINS, frames_per_bin=FPB, noise="philox", base_noise_std=std,
+                            hot_pixel_fraction=frac, hot_pixel_std=hstd, seed=args.seed, clip_index_base=i * B, out=out)
+        b.record()
+    torch.cuda.synchronize(dev)
+    launch_ms = float(np.mean([a.elapsed_time(b) for a, b in evs]))
+
+    # noise-free variant (explains how much of the time is the in-kernel generator)
+    evs2 = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(max(3, args.steps // 2))]
+    for a, b in evs2:
+        a.record()
+        v2v.frames_to_voxel(frames, pos, neg, num_bins=BINS, frames_per_bin=FPB, noise="none", out=out)
+        b.record()
+    torch.cuda.synchronize(dev)
+    clean_ms = float(np.mean([a.elapsed_time(b) for a, b in evs2]))
+
+    # ---- e2e: pinned host frames -> H2D -> kernel -> D2H float32 voxels in pinned host memory ----
+    e2e = None
+    if not args.no_e2e:
+        Be = min(B, args.e2e_clips)
+        host_in = torch.empty((Be, N_FRAMES, H, W), dtype=torch.uint8).pin_memory()
+        host_in.copy_(frames[:Be].cpu())
+        host_out = torch.empty((Be, T, BINS, H, W), dtype=torch.float32).pin_memory()
+        pipe = v2v.HostPipeline(vz, dev, clips_per_chunk=args.e2e_chunk, seed=args.seed)
+        ksteps = max(2, min(args.steps, 5))
+        pipe.run(host_in, params[:Be], host_out)                   # warm-up (allocates staging buffers)
+        barrier()
+        t0 = time.perf_counter()
+        for i in range(ksteps):
+            pipe.run(host_in, params[:Be], host_out)
+        torch.cuda.synchronize(dev)
+        t_e2e = time.perf_counter() - t0
+        if dist is not None:
+            t = torch.tensor([t_e2e], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            t_e2e = float(t.item())
+        e2e = {"value": world * ksteps * Be * PIX_INTERVALS_PER_CLIP / t_e2e / 1e6, "unit": "Mpix-frames/s",
+               "h2d_bytes_per_step": int(host_in.numel()), "d2h_bytes_per_step": int(host_out.numel() * 4),
+               "clips_per_s": world * ksteps * Be / t_e2e, "steps": ksteps, "clips_per_step_per_gpu": Be,
+               "api": "v2v_b200.HostPipeline.run(pinned uint8 frames, params, pinned float32 out): chunked H2D / kernel / D2H on 3 streams"}
+
+    if rank == 0:
+        peak, peak_src = measured_peak()
+        total_pix = world * args.steps * B * PIX_INTERVALS_PER_CLIP
+        achieved = B * ALGO_BYTES_PER_CLIP / (launch_ms * 1e-3) / 1e9
+        tr = ncu_traffic()
+        line = {
+            "metric": "video_to_voxel_throughput", "value": total_pix / (ms * 1e-3) / 1e6, "unit": "Mpix-frames/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic", "config": workload_config(B),
+            "clips_per_s": world * args.steps * B / (ms * 1e-3),
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": (tr or {}).get("dram_bytes_per_launch"), "peak_source": peak_src,
+                         "kernel": "esim_kernel<P=4,PHILOX>", "algorithmic_bytes_per_launch": B * ALGO_BYTES_PER_CLIP,
+                         "launch_ms": launch_ms, "frac_of_8TBs_nominal": achieved / 8000.0,
+                         "noise_free_launch_ms": clean_ms,
+                         "noise_free_frac": B * ALGO_BYTES_PER_CLIP / (clean_ms * 1e-3) / 1e9 / peak},
+            "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+            "event_stats": {"positive": int(stats_total[0]), "negative": int(stats_total[1])},
+        }
+        print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--clips", type=int, default=16, help="clips per step per GPU")
+    ap.add_argument("--seed", type=int, default=2026)
+    ap.add_argument("--e2e-clips", type=int, default=16)
+    ap.add_argument("--e2e-chunk", type=int, default=2)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

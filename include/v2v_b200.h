@@ -1,0 +1,212 @@
+/*
+ * v2v_b200.h — C ABI of the B200-native video-to-voxel hot path.
+ *
+ * This is the drop-in boundary: plain pointers and sizes, no C++/torch types.
+ * Every compute entry point is stream-ordered and non-blocking, allocates
+ * nothing, keeps no global mutable state, and returns 0 on success or a
+ * negative V2V_ERR_* code (never throws across the ABI).  All data pointers are
+ * DEVICE pointers unless a name ends in `_host`; the caller owns every buffer
+ * and keeps it alive until the stream has passed the call.  `stream` is a
+ * `cudaStream_t` passed as `void*` (NULL = legacy default stream).
+ *
+ * The reference (HYLZ-2019/V2V) has no FFI: its seams are Python call
+ * signatures.  Each entry point cites the reference function(s) it replaces
+ * (paths relative to the reference checkout); INTEGRATION.md shows the ctypes
+ * binding a maintainer adds on the reference side.
+ */
+#ifndef V2V_B200_H_
+#define V2V_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define V2V_ABI_VERSION 1
+
+/* ---- error codes ------------------------------------------------------- */
+#define V2V_OK 0
+#define V2V_ERR_INVALID_ARG (-1)   /* null pointer / non-positive size / bad enum  */
+#define V2V_ERR_SHAPE (-2)         /* (N-1) % (num_bins*frames_per_bin) != 0, ...  */
+#define V2V_ERR_ALIGNMENT (-3)     /* pointer not aligned for its element type     */
+#define V2V_ERR_CUDA (-4)          /* a CUDA runtime call failed (see last_error)  */
+#define V2V_ERR_UNSUPPORTED (-5)   /* combination not implemented                  */
+#define V2V_ERR_NO_DEVICE (-6)     /* no sm_100 device                             */
+
+/* ---- queries ----------------------------------------------------------- */
+int v2v_abi_version(void);
+/* Thread-local description of the last error returned on this thread. */
+const char* v2v_last_error(void);
+/* Compute capability / SM count of `device`; V2V_ERR_NO_DEVICE without a GPU. */
+int v2v_device_info(int device, int* cc_major, int* cc_minor, int* sm_count);
+/* Number of kernels this library has launched in this process (all threads). */
+long long v2v_launch_count(void);
+
+/* ======================================================================= *
+ * 1. ESIM-style frames -> voxel
+ *    replaces  EventEmulator.video_to_voxel      data/v2v_core_esim.py:26-69
+ *              reverse_gamma_correction + log    data/v2v_core_esim.py:3-4,34 (as the 256-entry LUT)
+ *              bin accumulation                  data/v2v_datasets.py:365-366,399-400
+ *              float32 packing of events/frame   data/v2v_datasets.py:328-356
+ * ======================================================================= */
+
+enum v2v_noise_mode {
+  V2V_NOISE_NONE = 0,     /* no base noise, hot noise only if `hot_noise` given        */
+  V2V_NOISE_EXPLICIT = 1, /* caller passes the reference's random fields (bit parity)  */
+  V2V_NOISE_PHILOX = 2    /* counter-based in-kernel generator (throughput mode)       */
+};
+
+enum v2v_threshold_mode {
+  V2V_THRES_PER_CLIP = 0, /* pos_thres/neg_thres are [B]      (the ESIM core)          */
+  V2V_THRES_PER_PIXEL = 1 /* pos_thres/neg_thres are [B,H,W]  (per-pixel maps)         */
+};
+
+typedef struct v2v_esim_desc {
+  /* shapes */
+  int32_t B, N, H, W;            /* clips, frames per clip (>=2), height, width         */
+  int32_t num_bins;              /* voxel channels                                      */
+  int32_t frames_per_bin;        /* consecutive intervals summed per bin (>=1)          */
+  int32_t noise_mode;            /* enum v2v_noise_mode                                 */
+  int32_t put_noise_external;    /* data/v2v_core_esim.py:46,62                         */
+  int32_t threshold_mode;        /* enum v2v_threshold_mode                             */
+  int32_t frame_out_mode;        /* 0: none; 1: frames (t+1)*bins*fpb, t<T; 2: frames t*bins*fpb, t<=T */
+  /* inputs */
+  const uint8_t* frames;         /* [B,N,H,W] uint8, contiguous                         */
+  const double* lut;             /* [256] float64: log(0.001 + gamma^-1(v)) built on the host */
+  const double* pos_thres;       /* [B] or [B,H,W], > 0                                  */
+  const double* neg_thres;       /* [B] or [B,H,W], > 0                                  */
+  const double* base_noise_std;  /* [B]; may be NULL for V2V_NOISE_NONE                 */
+  /* explicit random fields (V2V_NOISE_EXPLICIT; any may be NULL = absent) */
+  const double* u0;              /* [B,H,W] uniform [0,1): potential0 = u0*(pos+neg)-neg */
+  const double* hot_noise;       /* [B,H,W] masked+scaled hot-pixel noise               */
+  const double* base_gauss;      /* [B,N-1,H,W] standard normal per interval            */
+  /* Philox parameters (V2V_NOISE_PHILOX) */
+  const double* hot_pixel_fraction; /* [B]                                              */
+  const double* hot_pixel_std;      /* [B]                                              */
+  uint64_t seed;                 /* key; clip b uses counter word b + clip_index_base   */
+  uint64_t clip_index_base;      /* global index of clip 0 (so shards draw distinct streams) */
+  /* optional carried state: overrides u0 / Philox initial potential when given */
+  const double* potential_in;    /* [B,H,W] or NULL                                     */
+  double* potential_out;         /* [B,H,W] or NULL: potential after the last interval  */
+  /* outputs */
+  float* voxel;                  /* [B,T,num_bins,Hp,Wp] float32, T=(N-1)/(bins*fpb)    */
+  int64_t voxel_row_stride;      /* elements between rows   (0 -> W)                    */
+  int64_t voxel_plane_stride;    /* elements between planes (0 -> H*W); pads are NOT written */
+  float* frame_out;              /* [B,T or T+1,1,H,W] float32 = frame/255, or NULL     */
+  long long* stats;              /* [B,2] int64 += {positive events, negative events}, or NULL */
+} v2v_esim_desc;
+
+int v2v_esim_frames_to_voxel(const v2v_esim_desc* desc, void* stream);
+
+/* ======================================================================= *
+ * 2. v2e-style frames -> voxel
+ *    replaces  video_to_voxel / EventEmulator.generate_events
+ *                                              data/v2v_core_v2e.py:401-581
+ *              lin_log (as a 256-entry float32 LUT)   data/v2v_core_v2e.py:108-137
+ *              low_pass_filter :139-182, subtract_leak_current :192-211,
+ *              compute_event_map :42-62, generate_shot_noise :65-105
+ * ======================================================================= */
+
+typedef struct v2v_v2e_desc {
+  int32_t B, N, H, W;
+  int32_t num_bins, frames_per_bin; /* num_bins*frames_per_bin must divide N-1; use 1,1 for raw intervals */
+  int32_t noise_mode;            /* EXPLICIT: leak_randn / shot tensors given; PHILOX: generated; NONE: leak jitter & shot off */
+  int32_t state_f32;             /* 1: base/diff kept in float32 (reference when cutoff_hz<=0 and leak_rate_hz<=0) */
+  double fps;                    /* frame k is at t=k/fps                                */
+  double cutoff_hz, leak_rate_hz, shot_noise_rate_hz, leak_jitter_fraction;
+  const uint8_t* frames;         /* [B,N,H,W]                                            */
+  const float* lut;              /* [256] float32(log(v/255+0.01)) built on the host     */
+  const double* pos_thres;       /* [B,H,W] per-pixel ON thresholds  (>=0.01)            */
+  const double* neg_thres;       /* [B,H,W] per-pixel OFF thresholds (>=0.01)            */
+  const float* noise_rate;       /* [B,H,W] float32 leak-rate multipliers; NULL if leak_rate_hz<=0 */
+  const double* leak_randn;      /* [B,N-1,H,W] (EXPLICIT, leak_rate_hz>0)               */
+  const int32_t* pos_shot;       /* [B,N-1,H,W] Poisson draws (EXPLICIT, shot>0)         */
+  const int32_t* neg_shot;       /* [B,N-1,H,W]                                          */
+  const double* shot_pos_scale;  /* [B,N-1] PHILOX shot noise: (rate/2*dt)/mean(pos_factor) per frame, from v2v_v2e_shot_scales */
+  const double* shot_neg_scale;  /* [B,N-1]                                              */
+  double pos_thres_nominal, neg_thres_nominal; /* data/v2v_core_v2e.py:297-298           */
+  uint64_t seed, clip_index_base;
+  float* voxel;                  /* [B,T,num_bins,H,W] float32                           */
+  long long* stats;              /* [B,2] or NULL                                        */
+} v2v_v2e_desc;
+
+int v2v_v2e_frames_to_voxel(const v2v_v2e_desc* desc, void* stream);
+
+/* Per-frame shot-noise normalisers (the full-frame means of generate_shot_noise,
+ * data/v2v_core_v2e.py:90-96): scales[b,k-1] = (rate/2*dt_k)/mean_pixels(inten_factor*nominal/thres). */
+int v2v_v2e_shot_scales(const v2v_v2e_desc* desc, double* shot_pos_scale, double* shot_neg_scale, void* stream);
+
+/* ======================================================================= *
+ * 3. Event stream -> voxel (segmented by windows)
+ *    replaces  TestH5Dataset.make_voxel          data/testh5.py:60-90
+ *              events_to_voxel_torch             utils/event_utils.py:466-507
+ *              events_to_neg_pos_voxel_torch     utils/event_utils.py:509-541
+ * ======================================================================= */
+
+enum v2v_dtype {
+  V2V_U8 = 0, V2V_I8 = 1, V2V_U16 = 2, V2V_I16 = 3, V2V_I32 = 4, V2V_I64 = 5, V2V_F32 = 6, V2V_F64 = 7
+};
+
+enum v2v_scatter_mode {
+  V2V_SCATTER_H5_DISCRETE = 0,   /* data/testh5.py:70-73  (µs timestamps, integer bins)   */
+  V2V_SCATTER_H5_INTERP = 1,     /* data/testh5.py:74-80  (µs timestamps, 2-tap in time)  */
+  V2V_SCATTER_TORCH_DISCRETE = 2,/* utils/event_utils.py:501-505 (float32 arithmetic)      */
+  V2V_SCATTER_TORCH_BILINEAR = 3 /* utils/event_utils.py:490-500                           */
+};
+
+enum v2v_polarity_mode {
+  V2V_POL_SIGNED = 0,  /* weight = p (torch modes) or 2p-1 (h5 modes, p in {0,1})          */
+  V2V_POL_POS_ONLY = 1,/* weight = 1[p>0]   (events_to_neg_pos_voxel_torch, pos half)      */
+  V2V_POL_NEG_ONLY = 2 /* weight = 1[p<=0]                                                */
+};
+
+typedef struct v2v_scatter_desc {
+  int64_t num_events;
+  int32_t num_windows;           /* Wn                                                    */
+  int32_t num_bins, H, W;
+  int32_t mode;                  /* enum v2v_scatter_mode                                 */
+  int32_t polarity_mode;         /* enum v2v_polarity_mode                                */
+  int32_t xs_dtype, ys_dtype;    /* U16 / I16 / I32 / I64 / F32                           */
+  int32_t ts_dtype;              /* F64 / F32 (seconds)                                   */
+  int32_t ps_dtype;              /* U8 / I8 / F32                                         */
+  int32_t out_dtype;             /* F32 or F64                                            */
+  const void* xs;
+  const void* ys;
+  const void* ts;
+  const void* ps;
+  const int64_t* window_offsets; /* [Wn+1] ascending event offsets; window w = [off[w], off[w+1]) */
+  void* voxel;                   /* [Wn,num_bins,H,W]; fully written (zeros where no event) */
+  long long* dropped;            /* [1] += events skipped (out-of-sensor / out-of-range bin), or NULL */
+} v2v_scatter_desc;
+
+int v2v_events_to_voxel(const v2v_scatter_desc* desc, void* stream);
+
+/* ======================================================================= *
+ * 4. Event stream -> image
+ *    replaces  events_to_image_torch / interpolate_to_image
+ *                                              utils/event_utils.py:330-376,176-184
+ *              events_to_image (bincount)      utils/event_utils.py:155-174
+ *              per-pixel event-count map       scripts/testset_evcnt_maps.py:19-25
+ * ======================================================================= */
+typedef struct v2v_image_desc {
+  int64_t num_events;
+  int32_t H, W;                  /* sensor size                                           */
+  int32_t bilinear;              /* 0 nearest (truncate), 1 spatial 4-tap                 */
+  int32_t padding;               /* bilinear: output is [H+1,W+1]                         */
+  int32_t clip_out_of_range;     /* bilinear: mask events at/after the last row/column    */
+  int32_t xs_dtype, ys_dtype, ps_dtype; /* ps may be NULL: weight 1 (count map)          */
+  int32_t out_dtype;             /* F32, F64 or I64 (count map)                           */
+  const void* xs;
+  const void* ys;
+  const void* ps;
+  void* image;                   /* [Ho,Wo]; fully written                                */
+  long long* dropped;
+} v2v_image_desc;
+
+int v2v_events_to_image(const v2v_image_desc* desc, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* V2V_B200_H_ */

@@ -1,0 +1,266 @@
+"""GPU parity of the ESIM frame->voxel kernel against the reference's golden outputs and the CPU oracle.
+
+Bar: crossing counts bit-exact; voxels bit-exact as float32 (integer valued) and within 1e-5 relative
+in the external-noise mode (float64 sums rounded to float32).
+"""
+import numpy as np
+import pytest
+import torch
+
+import v2v_oracle as orc
+from conftest import golden, synth_video
+
+pytestmark = pytest.mark.gpu
+
+
+def run_explicit(v2v, dev, video, pos, neg, std, u0, hot, g, external, lut, bins=1, fpb=1, **kw):
+    fr = torch.from_numpy(video).to(dev)
+    return v2v.frames_to_voxel(fr, pos, neg, num_bins=bins, frames_per_bin=fpb, noise="explicit",
+                               base_noise_std=std, put_noise_external=external, u0=u0[None], hot_noise=hot[None],
+                               base_gauss=g[None], lut=lut, **kw)
+
+
+@pytest.mark.parametrize("name", golden("esim").names("esim_"))
+def test_golden_core(cuda_device, name):
+    import v2v_b200 as v2v
+    c = golden("esim").case(name)
+    o = run_explicit(v2v, cuda_device, c["video"], float(c["pos"]), float(c["neg"]), float(c["base_noise_std"]),
+                     c["u0"], c["hot"], c["g"], bool(c["external"]), c["lut"], with_stats=True)
+    got = o.voxel[0, :, 0].cpu().numpy()
+    ref = c["ref"]
+    if bool(c["external"]):
+        assert np.allclose(got, ref, rtol=1e-5, atol=1e-6)
+        assert np.array_equal(got, ref.astype(np.float32))       # in fact the float32 rounding of the reference
+    else:
+        assert np.array_equal(got.astype(np.float64), ref)       # bit-exact counts
+        st = o.stats[0].cpu().numpy()
+        assert st[0] == int(np.maximum(ref, 0).sum()) and st[1] == int(np.maximum(-ref, 0).sum())
+
+
+@pytest.mark.parametrize("name", golden("esim").names("esimds_"))
+def test_golden_dataset_level(cuda_device, name):
+    import v2v_b200 as v2v
+    c = golden("esim").case(name)
+    o = run_explicit(v2v, cuda_device, c["video"], float(c["p_pos_thres"]), float(c["p_neg_thres"]),
+                     float(c["p_base_noise_std"]), c["u0"], c["hot"], c["g"], bool(c["external"]), c["lut"],
+                     bins=int(c["bins"]), fpb=int(c["fpb"]))
+    got = o.voxel[0].cpu().numpy()
+    assert got.shape == c["ref"].shape
+    assert np.allclose(got, c["ref"], rtol=1e-5, atol=1e-6)
+    if not bool(c["external"]):
+        assert np.array_equal(got.astype(np.float64), c["ref"])
+
+
+@pytest.mark.parametrize("name", golden("esim").names("esim_"))
+def test_event_emulator_numpy_rng_is_reference(cuda_device, name):
+    """Reference signature + same np.random.seed -> the reference's output (replayed MT19937 stream)."""
+    import v2v_b200 as v2v
+    c = golden("esim").case(name)
+    np.random.seed(int(c["seed"]))
+    em = v2v.EventEmulator(pos_thres=float(c["pos"]), neg_thres=float(c["neg"]), base_noise_std=float(c["base_noise_std"]),
+                           hot_pixel_fraction=float(c["hot_pixel_fraction"]), hot_pixel_std=float(c["hot_pixel_std"]),
+                           put_noise_external=bool(c["external"]), rng="numpy")
+    got = em.video_to_voxel(c["video"], lut=c["lut"])
+    assert got.dtype == np.float64 and got.shape == c["ref"].shape
+    assert np.allclose(got, c["ref"], rtol=1e-5, atol=1e-6)
+    if not bool(c["external"]):
+        assert np.array_equal(got, c["ref"])
+
+
+@pytest.mark.parametrize("name", golden("esim").names("esimds_"))
+def test_imgs_to_voxels_mixin(cuda_device, name):
+    import v2v_b200 as v2v
+    c = golden("esim").case(name)
+    cfg = {str(k): eval(str(v)) for k, v in zip(c["cfg_keys"], c["cfg_vals"])}
+    vz = v2v.V2VVoxelizer(cfg, rng="numpy")
+    fixed = (None, None) if float(c["fixed_pos"]) < 0 else (float(c["fixed_pos"]), float(c["fixed_neg"]))
+    import v2v_b200.esim as E
+    old = E.esim_log_lut
+    E._lut_cache.clear()
+    E.esim_log_lut = lambda: c["lut"]            # replay the LUT the fixture was generated with
+    try:
+        np.random.seed(int(c["seed"]))
+        params, vox = vz.imgs_to_voxels(c["video"], int(c["bins"]), int(c["fpb"]), 24, fixed[0], fixed[1])
+    finally:
+        E.esim_log_lut = old
+        E._lut_cache.clear()
+    for k in ("pos_thres", "neg_thres", "base_noise_std", "hot_pixel_fraction", "hot_pixel_std"):
+        assert params[k] == float(c[f"p_{k}"])
+    assert np.allclose(vox, c["ref"], rtol=1e-5, atol=1e-6)
+
+
+@pytest.mark.parametrize("shape,kind,pos,neg", [
+    ((41, 256, 256), "walk", 0.2, 0.2),        # BASELINE config 1 shape through the binned path
+    ((40, 256, 256), "iid", 0.2, 0.2),         # config 1 raw core, stress content
+    ((11, 96, 160), "iid", 0.05, 0.0625),      # smallest shipped thresholds, many multi-count crossings
+    ((11, 480, 640), "walk", 0.7, 1.05),       # config 2 frame size (vectorised path)
+    ((6, 33, 17), "iid", 0.31, 0.2),           # ragged plane: HW % 4 != 0 (scalar path)
+])
+def test_oracle_parity_sizes(cuda_device, shape, kind, pos, neg):
+    import v2v_b200 as v2v
+    n, h, w = shape
+    vid = synth_video(kind, n, h, w, 42)
+    g = np.random.Generator(np.random.PCG64(7))
+    u0, hot = g.random((h, w)), np.where(g.random((h, w)) < 0.01, g.standard_normal((h, w)) * 3.0, 0.0)
+    gs = g.standard_normal((n - 1, h, w))
+    lut = orc.esim_log_lut()
+    for ext in (False, True):
+        ref = orc.esim_video_to_voxel(vid, pos, neg, 0.04, u0, hot, gs, ext, lut=lut)
+        o = run_explicit(v2v, cuda_device, vid, pos, neg, 0.04, u0, hot, gs, ext, lut, return_potential=True)
+        got = o.voxel[0, :, 0].cpu().numpy()
+        if ext:
+            assert np.array_equal(got, ref.astype(np.float32))
+        else:
+            assert np.array_equal(got.astype(np.float64), ref)
+
+
+def test_near_multiple_thresholds(cuda_device):
+    """Adversarial floor-division cases: potentials that are k*thr +- a few ulp."""
+    import v2v_b200 as v2v
+    lut = orc.esim_log_lut()
+    h, w = 64, 64
+    g = np.random.Generator(np.random.PCG64(11))
+    vid = np.zeros((2, h, w), dtype=np.uint8)
+    vid[0] = g.integers(0, 256, (h, w))
+    vid[1] = g.integers(0, 256, (h, w))
+    for thr in (0.05, 0.1, 0.2, 0.3, 1.0 / 3.0, 0.7):
+        d = lut[vid[1]] - lut[vid[0]]
+        k = g.integers(1, 40, (h, w)) * np.sign(g.standard_normal((h, w)))
+        target = k * thr
+        for _ in range(int(g.integers(0, 4))):
+            target = np.nextafter(target, np.inf if g.random() < 0.5 else -np.inf)
+        pot0 = target - d                       # potential lands (almost) on a multiple of the threshold
+        ref, _ = orc.esim_video_to_voxel(vid, thr, thr, 0.0, np.zeros((h, w)), np.zeros((h, w)), np.zeros((1, h, w)),
+                                         False, lut, return_state=True), None
+        # feed pot0 through potential_in (u0 path would re-derive it)
+        fr = torch.from_numpy(vid).to(cuda_device)
+        o = v2v.frames_to_voxel(fr, thr, thr, num_bins=1, potential_in=pot0[None], return_potential=True, lut=lut)
+        got = o.voxel[0, 0, 0].cpu().numpy().astype(np.float64)
+        pot = pot0 + d
+        pe = np.where(pot >= thr, np.floor_divide(pot, thr), 0)
+        ne = np.where(pot <= -thr, np.floor_divide(-pot, thr), 0)
+        assert np.array_equal(got, pe - ne)
+        exp_pot = pot - pe * thr
+        exp_pot = exp_pot + ne * thr
+        assert np.array_equal(o.potential[0].cpu().numpy(), exp_pot)
+
+
+def test_batched_per_clip_and_per_pixel_thresholds(cuda_device):
+    import v2v_b200 as v2v
+    lut = orc.esim_log_lut()
+    B, n, h, w = 3, 11, 40, 64
+    vids = np.stack([synth_video("walk", n, h, w, 60 + b) for b in range(B)])
+    g = np.random.Generator(np.random.PCG64(5))
+    u0 = g.random((B, h, w))
+    pos = np.array([0.1, 0.25, 0.8])
+    neg = np.array([0.15, 0.2, 0.6])
+    fr = torch.from_numpy(vids).to(cuda_device)
+    o = v2v.frames_to_voxel(fr, pos, neg, num_bins=5, u0=u0, lut=lut, with_stats=True)
+    z, zg = np.zeros((h, w)), np.zeros((n - 1, h, w))
+    for b in range(B):
+        ref = orc.bin_accumulate(orc.esim_video_to_voxel(vids[b], pos[b], neg[b], 0.0, u0[b], z, zg, False, lut), 5, 1)
+        assert np.array_equal(o.voxel[b].cpu().numpy().astype(np.float64), ref)
+    # per-pixel maps: each pixel must behave like a clip with that scalar threshold
+    pmap = g.uniform(0.05, 1.0, (B, h, w))
+    nmap = g.uniform(0.05, 1.0, (B, h, w))
+    o2 = v2v.frames_to_voxel(fr, pmap, nmap, num_bins=5, u0=u0, lut=lut)
+    got = o2.voxel.cpu().numpy()
+    ys, xs = g.integers(0, h, 12), g.integers(0, w, 12)
+    for y, x in zip(ys, xs):
+        for b in range(B):
+            ref = orc.esim_video_to_voxel(vids[b][:, y:y + 1, x:x + 1], pmap[b, y, x], nmap[b, y, x], 0.0,
+                                          u0[b][y:y + 1, x:x + 1], np.zeros((1, 1)), np.zeros((n - 1, 1, 1)), False, lut)
+            assert np.array_equal(got[b, :, :, y, x].reshape(-1).astype(np.float64), ref.reshape(-1))
+
+
+def test_frame_out_padding_and_chunking(cuda_device):
+    import v2v_b200 as v2v
+    lut = orc.esim_log_lut()
+    n, h, w = 21, 36, 40                      # 36 is not a multiple of 16 -> padded rows
+    vid = synth_video("walk", n, h, w, 9)
+    u0 = np.random.Generator(np.random.PCG64(2)).random((h, w))
+    fr = torch.from_numpy(vid).to(cuda_device)
+    base = v2v.frames_to_voxel(fr, 0.2, 0.3, num_bins=5, frames_per_bin=2, u0=u0[None], lut=lut, return_potential=True)
+    for mode, add in (("frames", False), ("frames+first", True)):
+        o = v2v.frames_to_voxel(fr, 0.2, 0.3, num_bins=5, frames_per_bin=2, u0=u0[None], lut=lut, frame_out=mode,
+                                pad_multiple=16)
+        assert o.padded.shape[-2:] == (48, 48)
+        assert torch.equal(o.voxel, base.voxel)
+        assert float(o.padded[..., h:, :].abs().sum()) == 0 and float(o.padded[..., :, w:].abs().sum()) == 0
+        ref = orc.pack_frames(vid[..., None], 10, 2, add)
+        assert np.array_equal(o.frames[0].cpu().numpy(), ref)
+    # chunked clip: carrying the potential across calls equals one long call
+    a = v2v.frames_to_voxel(fr[:11], 0.2, 0.3, num_bins=5, frames_per_bin=2, u0=u0[None], lut=lut, return_potential=True)
+    b = v2v.frames_to_voxel(fr[10:], 0.2, 0.3, num_bins=5, frames_per_bin=2, potential_in=a.potential, lut=lut,
+                            return_potential=True)
+    assert torch.equal(torch.cat([a.voxel, b.voxel], dim=1), base.voxel)
+    assert torch.equal(b.potential, base.potential)
+
+
+def test_philox_statistics_and_determinism(cuda_device):
+    import v2v_b200 as v2v
+    n, h, w = 41, 128, 128
+    vid = np.full((n, h, w), 128, dtype=np.uint8)            # static scene: every event is noise
+    fr = torch.from_numpy(vid).to(cuda_device)
+    kw = dict(num_bins=1, noise="philox", base_noise_std=0.05, hot_pixel_fraction=0.01, hot_pixel_std=5.0,
+              return_potential=True, with_stats=True)
+    a = v2v.frames_to_voxel(fr, 0.2, 0.2, seed=123, **kw)
+    b = v2v.frames_to_voxel(fr, 0.2, 0.2, seed=123, **kw)
+    c = v2v.frames_to_voxel(fr, 0.2, 0.2, seed=124, **kw)
+    assert torch.equal(a.voxel, b.voxel) and not torch.equal(a.voxel, c.voxel)
+    # potential stays inside (-neg, pos) and initial potential is uniform: compare event rate with the oracle
+    g = np.random.Generator(np.random.PCG64(0))
+    u0, m = g.random((h, w)), g.random((h, w)) < 0.01
+    hot = np.where(m, 5.0 * g.standard_normal((h, w)), 0.0)
+    ref = orc.esim_video_to_voxel(vid, 0.2, 0.2, 0.05, u0, hot, g.standard_normal((n - 1, h, w)), False)
+    rate_ref = np.abs(ref).sum() / ref.size
+    rate = float(a.voxel.abs().sum()) / a.voxel.numel()
+    assert abs(rate - rate_ref) / rate_ref < 0.15
+    pot = a.potential.cpu().numpy()
+    assert pot.max() < 0.2 and pot.min() > -0.2
+    st = a.stats.cpu().numpy()[0]
+    assert st[0] == int(a.voxel.clamp(min=0).sum()) and st[1] == int((-a.voxel).clamp(min=0).sum())
+    # clip streams are distinct: same seed, shifted clip index
+    d = v2v.frames_to_voxel(fr, 0.2, 0.2, seed=123, clip_index_base=1, **kw)
+    assert not torch.equal(a.voxel, d.voxel)
+
+
+def test_full_size_properties(cuda_device):
+    """BASELINE config 2 size (121x480x640): size-independent properties instead of a full oracle run."""
+    import v2v_b200 as v2v
+    lut = orc.esim_log_lut()
+    n, h, w = 121, 480, 640
+    vid = synth_video("walk", n, h, w, 3)
+    fr = torch.from_numpy(vid).to(cuda_device)
+    pos, neg = 0.23, 0.31
+    g = np.random.Generator(np.random.PCG64(4))
+    u0 = g.random((h, w))
+    o = v2v.frames_to_voxel(fr, pos, neg, num_bins=5, u0=u0[None], lut=lut, return_potential=True, with_stats=True)
+    vox = o.voxel[0].to(torch.float64)
+    # conservation: potential_end + pos*P - neg*N == potential_0 + L_end - L_0 (up to accumulated rounding)
+    pe = vox.clamp(min=0).sum(dim=(0, 1)).cpu().numpy()
+    ne = (-vox).clamp(min=0).sum(dim=(0, 1)).cpu().numpy()
+    pot0 = u0 * (pos + neg) - neg
+    lhs = o.potential[0].cpu().numpy() + pe * pos - ne * neg
+    # intervals with both polarities summed inside one bin cannot occur with fpb=1, so pe/ne are exact
+    assert np.allclose(lhs, pot0 + lut[vid[-1]] - lut[vid[0]], atol=1e-9)
+    assert float(o.potential.max()) < pos and float(o.potential.min()) > -neg
+    st = o.stats.cpu().numpy()[0]
+    assert st[0] == int(pe.sum()) and st[1] == int(ne.sum())
+    # a strip of the full-size result against the oracle
+    sl = slice(200, 204)
+    ref = orc.bin_accumulate(orc.esim_video_to_voxel(vid[:, sl], pos, neg, 0.0, u0[sl], np.zeros((4, w)),
+                                                     np.zeros((n - 1, 4, w)), False, lut), 5, 1)
+    assert np.array_equal(o.voxel[0, :, :, sl].cpu().numpy().astype(np.float64), ref)
+
+
+def test_errors(cuda_device):
+    import v2v_b200 as v2v
+    fr = torch.zeros((1, 7, 8, 8), dtype=torch.uint8, device=cuda_device)
+    with pytest.raises(AssertionError):
+        v2v.frames_to_voxel(fr, 0.2, 0.2, num_bins=5)             # (N-1) % 5 != 0, data/v2v_datasets.py:365
+    with pytest.raises(v2v.V2VError):
+        v2v.frames_to_voxel(fr.cpu(), 0.2, 0.2, num_bins=1)       # no CPU fallback
+    out = v2v.frames_to_voxel(torch.zeros((1, 1, 8, 8), dtype=torch.uint8, device=cuda_device), 0.2, 0.2, num_bins=5)
+    assert out.voxel.shape == (1, 0, 5, 8, 8)                     # single frame: no intervals
+    assert v2v.EventEmulator(rng="numpy").video_to_voxel(np.zeros((1, 4, 4), np.uint8)).shape == (0, 4, 4)

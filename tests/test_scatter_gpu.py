@@ -1,0 +1,134 @@
+"""GPU parity of the event-stream scatter kernels (golden vectors of the reference + CPU oracle)."""
+import numpy as np
+import pytest
+import torch
+
+import v2v_oracle as orc
+from conftest import golden
+
+pytestmark = pytest.mark.gpu
+
+TOL = dict(rtol=1e-5, atol=1e-5)     # |a-b| <= 1e-5*max(1,|b|), BASELINE north_star
+
+
+@pytest.mark.parametrize("name", golden("scatter").names("scat_mv_"))
+def test_make_voxel_golden(cuda_device, name):
+    import v2v_b200 as v2v
+    c = golden("scatter").case(name)
+    got = v2v.make_voxel([c["ts"], c["xs"], c["ys"], c["ps"]], int(c["bins"]), int(c["H"]), int(c["W"]), bool(c["interp"]))
+    assert got.dtype == np.float64 and got.shape == c["ref"].shape
+    if bool(c["interp"]):
+        assert np.allclose(got, c["ref"], **TOL)
+        assert np.max(np.abs(got - c["ref"])) < 1e-6
+    else:
+        assert np.array_equal(got, c["ref"])         # integer counts: exact
+
+
+@pytest.mark.parametrize("name", golden("scatter").names("scat_tv_"))
+def test_events_to_voxel_torch_golden(cuda_device, name):
+    import v2v_b200 as v2v
+    c = golden("scatter").case(name)
+    hw = (int(c["H"]), int(c["W"]))
+    args = [torch.from_numpy(c[k]) for k in ("xs", "ys", "ts", "ps")]
+    got = v2v.events_to_voxel_torch(*args, int(c["bins"]), sensor_size=hw, temporal_bilinear=bool(c["bilinear"]))
+    assert got.is_cuda and got.dtype == torch.float32
+    assert np.allclose(got.cpu().numpy(), c["ref"], **TOL)
+    p, n = v2v.events_to_neg_pos_voxel_torch(*args, int(c["bins"]), sensor_size=hw, temporal_bilinear=bool(c["bilinear"]))
+    assert np.allclose(p.cpu().numpy(), c["ref_pos"], **TOL) and np.allclose(n.cpu().numpy(), c["ref_neg"], **TOL)
+    if not bool(c["bilinear"]):
+        assert np.array_equal(got.cpu().numpy(), c["ref"])
+
+
+@pytest.mark.parametrize("name", ["scat_img_bil_pad", "scat_img_nearest_clip_nopad", "scat_img_nearest_default"])
+def test_events_to_image_torch_golden(cuda_device, name):
+    import v2v_b200 as v2v
+    c = golden("scatter").case(name)
+    got = v2v.events_to_image_torch(torch.from_numpy(c["xs"]), torch.from_numpy(c["ys"]), torch.from_numpy(c["ps"]),
+                                    sensor_size=(int(c["H"]), int(c["W"])), clip_out_of_range=bool(c["clip"]),
+                                    interpolation="bilinear" if int(c["bilinear"]) else None, padding=bool(c["padding"]))
+    assert got.shape == c["ref"].shape
+    assert np.allclose(got.cpu().numpy(), c["ref"], **TOL)
+
+
+def test_events_to_image_np_and_count_map(cuda_device):
+    import v2v_b200 as v2v
+    c = golden("scatter").case("scat_img_np")
+    got = v2v.events_to_image(c["xs"], c["ys"], c["ps"], sensor_size=(int(c["H"]), int(c["W"])))
+    assert np.allclose(got, c["ref"], rtol=1e-12, atol=1e-12)
+    cm = v2v.event_count_map(c["xs"], c["ys"], int(c["H"]), int(c["W"])).cpu().numpy()
+    assert np.array_equal(cm, orc.event_count_map(c["xs"], c["ys"], int(c["H"]), int(c["W"])))
+
+
+def synth_stream(ne, h, w, wn, seed, hot_frac=0.0):
+    g = np.random.Generator(np.random.PCG64(seed))
+    xs = g.integers(0, w, ne).astype(np.uint16)
+    ys = g.integers(0, h, ne).astype(np.uint16)
+    if hot_frac:
+        sel = g.random(ne) < hot_frac
+        xs[sel], ys[sel] = 3, 5
+    ts = np.sort(g.random(ne) * 1.0 + 100.0)
+    ps = (g.random(ne) < 0.5).astype(np.uint8)
+    cuts = np.sort(g.integers(0, ne + 1, wn - 1))
+    off = np.concatenate([[0], cuts, [ne]]).astype(np.int64)
+    return ts, xs, ys, ps, off
+
+
+@pytest.mark.parametrize("bins,interp", [(5, False), (5, True), (15, False), (15, True)])
+def test_windows_vs_oracle(cuda_device, bins, interp):
+    """HQF/MVSEC-shaped sensor, many ragged windows (some empty) in one launch; hot pixel included."""
+    import v2v_b200 as v2v
+    h, w, wn = 260, 346, 23
+    ts, xs, ys, ps, off = synth_stream(200_000, h, w, wn, 17, hot_frac=0.01)
+    off[5] = off[4]                                   # an empty window
+    off = np.sort(off)
+    got, dropped = v2v.voxelize_windows(xs, ys, ts, ps, off, bins, h, w, mode="h5_interp" if interp else "h5_discrete",
+                                        return_dropped=True)
+    assert int(dropped) == 0
+    got = got.cpu().numpy()
+    for k in range(wn):
+        s = slice(off[k], off[k + 1])
+        ref = orc.make_voxel(ts[s], xs[s], ys[s], ps[s], bins, h, w, interp)
+        if interp:
+            assert np.allclose(got[k], ref, **TOL)
+        else:
+            assert np.array_equal(got[k], ref.astype(np.float32))
+
+
+def test_scatter_full_size_properties(cuda_device):
+    """BASELINE config 4 size (10 M events, 260x346, 400 windows): conservation instead of a full oracle run."""
+    import v2v_b200 as v2v
+    h, w, wn, ne = 260, 346, 400, 10_000_000
+    ts, xs, ys, ps, off = synth_stream(ne, h, w, wn, 23, hot_frac=0.01)
+    pol = 2 * ps.astype(np.int64) - 1
+    csum = np.concatenate([[0], np.cumsum(pol)])
+    per_win = csum[off[1:]] - csum[off[:-1]]
+    vd = v2v.voxelize_windows(xs, ys, ts, ps, off, 5, h, w, mode="h5_discrete")
+    assert np.array_equal(vd.sum(dim=(1, 2, 3)).cpu().numpy().astype(np.int64), per_win)
+    vi = v2v.voxelize_windows(xs, ys, ts, ps, off, 5, h, w, mode="h5_interp", out_dtype=torch.float64)
+    assert np.allclose(vi.sum(dim=(1, 2, 3)).cpu().numpy(), per_win, atol=1e-2)
+    # bins collapse: summing the interpolated voxel over bins equals the discrete one summed over bins (up to the guard)
+    assert torch.allclose(vi.sum(dim=1), vd.sum(dim=1).to(torch.float64), atol=1e-3)
+    # spot check a few windows against the oracle
+    for k in (0, 137, 399):
+        s = slice(off[k], off[k + 1])
+        assert np.array_equal(vd[k].cpu().numpy(), orc.make_voxel(ts[s], xs[s], ys[s], ps[s], 5, h, w, False).astype(np.float32))
+        assert np.allclose(vi[k].cpu().numpy(), orc.make_voxel(ts[s], xs[s], ys[s], ps[s], 5, h, w, True), **TOL)
+
+
+def test_out_of_sensor_events_are_dropped_and_counted(cuda_device):
+    import v2v_b200 as v2v
+    ts = np.linspace(0, 0.01, 6)
+    xs = np.array([0, 1, 50, 2, 3, 4], dtype=np.int16)
+    ys = np.array([0, 1, 1, -1, 3, 40], dtype=np.int16)
+    ps = np.ones(6, dtype=np.uint8)
+    v, dropped = v2v.voxelize_windows(xs, ys, ts, ps, [0, 6], 5, 8, 8, return_dropped=True)
+    assert int(dropped) == 3 and float(v.sum()) == 3.0
+
+
+def test_mixin_matches_reference_signature(cuda_device):
+    import v2v_b200 as v2v
+    c = golden("scatter").case("scat_mv_disc5")
+
+    class DS(v2v.MakeVoxelMixin):
+        num_bins, H, W, interpolate_bins = int(c["bins"]), int(c["H"]), int(c["W"]), False
+    assert np.array_equal(DS().make_voxel([c["ts"], c["xs"], c["ys"], c["ps"]]), c["ref"])

@@ -1,0 +1,86 @@
+"""GPU parity of the v2e-style kernel against the reference's golden outputs (counts bit-exact)."""
+import numpy as np
+import pytest
+import torch
+
+import v2v_oracle as orc
+from conftest import golden, synth_video
+
+pytestmark = pytest.mark.gpu
+
+
+def params_of(c):
+    p = {k[2:]: float(v) for k, v in c.items() if k.startswith("p_")}
+    p["threshold_model"] = str(c["threshold_model"])
+    return p
+
+
+@pytest.mark.parametrize("name", golden("v2e").cases)
+def test_v2e_golden_replay(cuda_device, name):
+    """Explicit random fields recorded from the reference run -> identical counts."""
+    from v2v_b200.v2e import frames_to_voxel_v2e
+    c = golden("v2e").case(name)
+    p = params_of(c)
+    fr = torch.from_numpy(c["video"]).to(cuda_device)
+    out = frames_to_voxel_v2e(
+        fr, c["pos_thres"][None], c["neg_thres"][None], fps=float(c["fps"]), cutoff_hz=p["cutoff_hz"],
+        leak_rate_hz=p["leak_rate_hz"], shot_noise_rate_hz=p["shot_noise_rate_hz"],
+        leak_jitter_fraction=p["leak_jitter_fraction"], noise_rate=c["noise_rate"][None],
+        pos_thres_nominal=p["thres_mean_mean"] + p["thres_diff_mean"] / 2,
+        neg_thres_nominal=p["thres_mean_mean"] - p["thres_diff_mean"] / 2, noise="explicit",
+        leak_randn=c["leak_randn"][None] if "leak_randn" in c else None,
+        pos_shot=c["pos_shot"][None] if "pos_shot" in c else None,
+        neg_shot=c["neg_shot"][None] if "neg_shot" in c else None, lut=c["lut"], with_stats=True)
+    got = out["voxel"][0, :, 0].cpu().numpy().astype(np.float64)
+    assert np.array_equal(got, c["ref"])
+
+
+@pytest.mark.parametrize("name", golden("v2e").cases)
+def test_v2e_reference_signature_same_seed(cuda_device, name):
+    """video_to_voxel(...) with rng='numpy' and the reference's seed reproduces the reference."""
+    from v2v_b200.v2e import video_to_voxel
+    c = golden("v2e").case(name)
+    p = params_of(c)
+    got = video_to_voxel(c["video"].astype(np.float64), int(c["fps"]), refractory_period_s=0, seed=int(c["seed"]),
+                         rng="numpy", lut=c["lut"], **p)
+    assert got.dtype == np.float64 and np.array_equal(got, c["ref"])
+
+
+def test_v2e_large_vectorised_vs_oracle(cuda_device):
+    """Config-3 style: HDR-degraded clip at a size that takes the 4-pixel path; noisy preset replayed."""
+    from v2v_b200.v2e import frames_to_voxel_v2e
+    n, h, w = 11, 480, 640
+    vid = synth_video("walk", n, h, w, 77)
+    vid = np.clip((vid - 127.5) * 2.3 + 127.5, 0, 255).astype(np.uint8)         # data/v2v_datasets.py:473-477
+    p = dict(threshold_model="pn_related", thres_mean_mean=0.2, thres_mean_std=0.05, thres_diff_mean=0.0,
+             thres_diff_std=0.05, cutoff_hz=30.0, leak_rate_hz=0.1, shot_noise_rate_hz=5.0, leak_jitter_fraction=0.1,
+             noise_rate_cov_decades=0.1)
+    rec = {}
+    np.random.seed(5)
+    ref = orc.v2e_video_to_voxel(vid.astype(np.float64), 24, p, np.random, record=rec)
+    fr = torch.from_numpy(vid).to(cuda_device)
+    out = frames_to_voxel_v2e(fr, rec["pos_thres"][None], rec["neg_thres"][None], fps=24, cutoff_hz=30.0, leak_rate_hz=0.1,
+                              shot_noise_rate_hz=5.0, leak_jitter_fraction=0.1, noise_rate=rec["noise_rate"][None],
+                              pos_thres_nominal=0.2, neg_thres_nominal=0.2, noise="explicit",
+                              leak_randn=np.stack(rec["leak_randn"])[None],
+                              pos_shot=np.stack(rec["pos_shot"]).astype(np.int32)[None],
+                              neg_shot=np.stack(rec["neg_shot"]).astype(np.int32)[None])
+    assert np.array_equal(out["voxel"][0, :, 0].cpu().numpy().astype(np.float64), ref)
+
+
+def test_v2e_philox_statistics(cuda_device):
+    from v2v_b200.v2e import frames_to_voxel_v2e
+    n, h, w = 25, 256, 256
+    vid = np.full((n, h, w), 100, dtype=np.uint8)
+    fr = torch.from_numpy(vid).to(cuda_device)
+    thr = np.full((1, h, w), 0.2)
+    kw = dict(fps=24, cutoff_hz=30.0, leak_rate_hz=0.1, shot_noise_rate_hz=5.0, leak_jitter_fraction=0.1,
+              noise_rate=np.ones((1, h, w), np.float32), noise="philox", with_stats=True)
+    a = frames_to_voxel_v2e(fr, thr, thr, seed=1, **kw)
+    b = frames_to_voxel_v2e(fr, thr, thr, seed=1, **kw)
+    assert torch.equal(a["voxel"], b["voxel"])
+    st = a["stats"].cpu().numpy()[0]
+    # static scene: shot noise only, expectation rate/2 * duration per pixel and polarity (+ a few leak events)
+    expect = 2.5 * (n - 1) / 24 * h * w
+    assert abs(st[1] - expect) / expect < 0.05
+    assert abs(st[0] - expect) / expect < 0.10

@@ -1,0 +1,21 @@
+"""v2v_b200 — B200-native video-to-voxel hot path of HYLZ-2019/V2V.
+
+Host layer (Python) above the C ABI of ``lib/libv2v_b200.so`` (include/v2v_b200.h).
+Importing the package does not need a GPU; every compute call does and fails
+loudly without one (no CPU fallback).
+"""
+from . import _lib
+from ._lib import V2VError, launch_count
+from .esim import EventEmulator, EsimOutput, esim_log_lut, frames_to_voxel, draw_reference_randomness
+from .events import (MakeVoxelMixin, event_count_map, events_to_image, events_to_image_torch,
+                     events_to_neg_pos_voxel_torch, events_to_voxel, events_to_voxel_torch, make_voxel,
+                     voxelize_windows)
+from .datasets import ImgsToVoxelsMixin, V2VVoxelizer, sample_v2e_params
+from .pipeline import HostPipeline
+
+__all__ = [
+    "V2VError", "launch_count", "EventEmulator", "EsimOutput", "esim_log_lut", "frames_to_voxel",
+    "draw_reference_randomness", "MakeVoxelMixin", "event_count_map", "events_to_image",
+    "events_to_image_torch", "events_to_neg_pos_voxel_torch", "events_to_voxel", "events_to_voxel_torch",
+    "make_voxel", "voxelize_windows", "ImgsToVoxelsMixin", "V2VVoxelizer", "sample_v2e_params", "HostPipeline",
+]

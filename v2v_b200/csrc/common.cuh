@@ -1,0 +1,124 @@
+// Shared device/host helpers for the v2v_b200 kernels (sm_100a only).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+
+#include "../../include/v2v_b200.h"
+
+namespace v2v {
+
+// ---- host-side error plumbing ---------------------------------------------
+void set_error(const char* fmt, ...);
+int cuda_fail(cudaError_t e, const char* what);
+void count_launch(int n = 1);
+
+#define V2V_REQUIRE(cond, code, ...)  \
+  do {                                \
+    if (!(cond)) {                    \
+      ::v2v::set_error(__VA_ARGS__);  \
+      return (code);                  \
+    }                                 \
+  } while (0)
+
+#define V2V_CUDA(expr)                                            \
+  do {                                                            \
+    cudaError_t _e = (expr);                                      \
+    if (_e != cudaSuccess) return ::v2v::cuda_fail(_e, #expr);    \
+  } while (0)
+
+static inline bool aligned(const void* p, size_t a) { return (reinterpret_cast<uintptr_t>(p) % a) == 0; }
+
+// ---- streaming loads / stores ----------------------------------------------
+// Inputs are read exactly once and outputs written exactly once: keep them out
+// of L1 and mark them evict-first in L2.
+__device__ __forceinline__ uint32_t ld_stream_u32(const void* p) {
+  uint32_t v;
+  asm volatile("ld.global.nc.L1::no_allocate.u32 %0, [%1];" : "=r"(v) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ uint8_t ld_stream_u8(const void* p) {
+  uint32_t v;
+  asm volatile("ld.global.nc.L1::no_allocate.u8 %0, [%1];" : "=r"(v) : "l"(p));
+  return static_cast<uint8_t>(v);
+}
+__device__ __forceinline__ void st_stream_f32x4(float* p, float a, float b, float c, float d) {
+  asm volatile("st.global.cs.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+__device__ __forceinline__ void st_stream_f32(float* p, float a) {
+  asm volatile("st.global.cs.f32 [%0], %1;" ::"l"(p), "f"(a) : "memory");
+}
+__device__ __forceinline__ double2 ld_stream_f64x2(const double* p) {
+  double2 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
+  return v;
+}
+
+// ---- exact floor division ---------------------------------------------------
+// floor(a/b) as a mathematical quantity for a >= 0, b > 0 (np.floor_divide on
+// float64 is fmod-based and equals it; see oracle/ and SURVEY §7).  `rb` is
+// RN(1/b).  The candidate floor(a*rb) is off by at most one; the sign of a
+// single-rounded FMA residual is exact, which fixes it.
+__device__ __forceinline__ double floor_div_exact(double a, double b, double rb) {
+  double q = floor(__dmul_rn(a, rb));
+  double r = __fma_rn(-q, b, a);
+  if (r < 0.0) {
+    q -= 1.0;
+  } else if (__fma_rn(-(q + 1.0), b, a) >= 0.0) {
+    q += 1.0;
+  }
+  return q;
+}
+
+// ---- Philox4x32-10 -----------------------------------------------------------
+struct Philox {
+  static constexpr uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+  __host__ __device__ static inline uint4 run(uint4 c, uint2 k) {
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+#ifdef __CUDA_ARCH__
+      uint32_t hi0 = __umulhi(M0, c.x), lo0 = M0 * c.x;
+      uint32_t hi1 = __umulhi(M1, c.z), lo1 = M1 * c.z;
+#else
+      uint64_t p0 = static_cast<uint64_t>(M0) * c.x, p1 = static_cast<uint64_t>(M1) * c.z;
+      uint32_t hi0 = static_cast<uint32_t>(p0 >> 32), lo0 = static_cast<uint32_t>(p0);
+      uint32_t hi1 = static_cast<uint32_t>(p1 >> 32), lo1 = static_cast<uint32_t>(p1);
+#endif
+      c = make_uint4(hi1 ^ c.y ^ k.x, lo1, hi0 ^ c.w ^ k.y, lo0);
+      k.x += W0;
+      k.y += W1;
+    }
+    return c;
+  }
+};
+
+// Two standard normals from two 32-bit words (Box–Muller, float32 math: the
+// in-kernel generator is a statistical stand-in for the reference's MT19937
+// stream, which cannot be reproduced on a GPU — parity runs use EXPLICIT noise).
+__device__ __forceinline__ float2 box_muller(uint32_t a, uint32_t b) {
+  // u1 in (0,1], u2 in [0,1)
+  float u1 = (static_cast<float>(a >> 8) + 1.0f) * (1.0f / 16777216.0f);
+  float u2 = static_cast<float>(b >> 8) * (1.0f / 16777216.0f);
+  float r = sqrtf(-2.0f * __logf(u1));
+  float s, c;
+  __sincosf(6.28318530717958647692f * u2, &s, &c);
+  return make_float2(r * c, r * s);
+}
+
+// Uniform double in [0,1) with 53 random bits (same construction as numpy's
+// legacy random_sample: (a>>5, b>>6) -> (a*2^26+b)/2^53).
+__device__ __forceinline__ double uniform53(uint32_t a, uint32_t b) {
+  return (static_cast<double>(a >> 5) * 67108864.0 + static_cast<double>(b >> 6)) * (1.0 / 9007199254740992.0);
+}
+
+__device__ __forceinline__ long long warp_sum(long long v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+}  // namespace v2v
