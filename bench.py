@@ -98,7 +98,7 @@ def cpu_reference_run(n_frames, clips, procs):
         res = [_cpu_clip_job(j) for j in jobs]
     else:
         with mp.get_context("spawn").Pool(procs) as pool:
-            pool.map(_cpu_clip_job, [(0, 2, 8, 8)] * procs)        # warm the workers (imports) outside the timing
+            pool.map(_cpu_clip_job, [(0, 6, 8, 8)] * procs)        # warm the workers (imports) outside the timing
             t0 = time.perf_counter()
             res = pool.map(_cpu_clip_job, jobs)
     wall = time.perf_counter() - t0
@@ -125,7 +125,7 @@ def run_reference_arm(args):
     import multiprocessing as mp
     jobs_per_step = cores
     with mp.get_context("spawn").Pool(cores) as pool:
-        pool.map(_cpu_clip_job, [(0, 2, 8, 8)] * cores)
+        pool.map(_cpu_clip_job, [(0, 6, 8, 8)] * cores)
         for s in range(args.warmup + args.steps):
             jobs = [(5000 + s * jobs_per_step + i, n_frames, H, W) for i in range(jobs_per_step)]
             t0 = time.perf_counter()
@@ -163,48 +163,73 @@ def workload_config(clips_per_step, note=""):
 # ----------------------------------------------------------------------------------------------
 
 class ClockSampler:
-    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """SM clock / throttle reasons during the timed region, sampled in-process through NVML every 20 ms
+    (a polling nvidia-smi subprocess takes driver locks that stall kernel launches; it is only the fallback)."""
 
     def __init__(self, index):
-        self.index, self.rows, self.proc = index, [], None
+        self.index, self.rows, self.stop_flag, self.thread, self.h = index, [], False, None, None
+        self.nv = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        except Exception:
+            self.nv = None
+
+    def _loop(self):
+        nv = self.nv
+        while not self.stop_flag:
+            try:
+                sm = nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)
+                try:
+                    rs = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    rs = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                self.rows.append((time.perf_counter(), sm, rs))
+            except Exception:
+                pass
+            time.sleep(0.02)
 
     def start(self):
-        try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            threading.Thread(target=self._read, daemon=True).start()
-        except Exception:
-            self.proc = None
-
-    def _read(self):
-        for ln in self.proc.stdout:
-            self.rows.append((time.perf_counter(), ln.strip()))
+        if self.nv is not None:
+            self.thread = threading.Thread(target=self._loop, daemon=True)
+            self.thread.start()
 
     def stop(self, t0, t1):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.proc.terminate()
-        sm, mx, reasons = [], None, set()
-        for t, ln in self.rows:
-            f = [x.strip() for x in ln.split(",")]
-            if len(f) < 7:
-                continue
-            try:
-                mx = float(f[1])
-                if t0 - 0.05 <= t <= t1 + 0.05:
-                    sm.append(float(f[0]))
-                    for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
-                        if v.lower().startswith("active"):
-                            reasons.add(name)
-            except ValueError:
-                continue
-        if not sm:      # timed region shorter than one sample: take every sample we have
-            sm = [float(ln.split(",")[0]) for _, ln in self.rows if ln and ln.split(",")[0].strip().replace(".", "").isdigit()]
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
-                "samples": len(sm)}
+        if self.nv is None:
+            return self._smi_once()
+        time.sleep(0.05)
+        self.stop_flag = True
+        self.thread.join(timeout=1.0)
+        nv = self.nv
+        try:
+            mx = float(nv.nvmlDeviceGetMaxClockInfo(self.h, nv.NVML_CLOCK_SM))
+        except Exception:
+            mx = None
+        names = {"hw_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8),
+                 "hw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40),
+                 "sw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20),
+                 "sw_power_cap": getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4)}
+        inside = [(sm, rs) for t, sm, rs in self.rows if t0 <= t <= t1] or [(sm, rs) for _, sm, rs in self.rows[-3:]]
+        reasons = sorted({n for _, rs in inside for n, bit in names.items() if rs & bit})
+        sms = [sm for sm, _ in inside]
+        return {"sm_mhz": float(np.median(sms)) if sms else None, "sm_max_mhz": mx, "reasons": reasons,
+                "samples": len(sms), "source": "nvml"}
+
+    def _smi_once(self):
+        try:
+            q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+                "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+            out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}", "--format=csv,noheader,nounits"],
+                                 capture_output=True, text=True, timeout=10).stdout.strip().split(",")
+            f = [x.strip() for x in out]
+            reasons = [n for n, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[2:6])
+                       if v.lower().startswith("active")]
+            return {"sm_mhz": float(f[0]), "sm_max_mhz": float(f[1]), "reasons": reasons, "samples": 1,
+                    "source": "nvidia-smi after the timed region (NVML unavailable)"}
+        except Exception:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["clock query unavailable"], "samples": 0}
 
 
 # ----------------------------------------------------------------------------------------------
@@ -272,11 +297,11 @@ def run_ours(args):
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-        time.sleep(0.25)
     launches0 = v2v.launch_count()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     t_wall0 = time.perf_counter()
+    torch.cuda.nvtx.range_push("timed")
     ev0.record()
     for i in range(args.steps):
         o = step(args.warmup + i)
@@ -285,6 +310,7 @@ def run_ours(args):
         dist.all_reduce(stats_total)                               # the only collective: event-count statistics
     ev1.record()
     barrier()
+    torch.cuda.nvtx.range_pop()
     t_wall1 = time.perf_counter()
     launches = v2v.launch_count() - launches0
     ms = ev0.elapsed_time(ev1)

@@ -99,6 +99,13 @@ typedef struct v2v_esim_desc {
 
 int v2v_esim_frames_to_voxel(const v2v_esim_desc* desc, void* stream);
 
+/* Audit hook for V2V_NOISE_PHILOX: writes the random fields the kernel draws for (seed, clip_index_base,
+ * B, N, H, W, base_noise_std, hot_pixel_fraction, hot_pixel_std) of `desc`: u0 [B,H,W], hot_noise [B,H,W],
+ * base_noise [B,N-1,H,W] (already multiplied by base_noise_std).  Any output may be NULL.  Replaying them with
+ * V2V_NOISE_EXPLICIT and base_noise_std = 1 reproduces the PHILOX run exactly, which is how the in-kernel
+ * generator is checked against the CPU oracle. */
+int v2v_esim_philox_fields(const v2v_esim_desc* desc, double* u0, double* hot_noise, double* base_noise, void* stream);
+
 /* ======================================================================= *
  * 2. v2e-style frames -> voxel
  *    replaces  video_to_voxel / EventEmulator.generate_events
@@ -136,6 +143,10 @@ int v2v_v2e_frames_to_voxel(const v2v_v2e_desc* desc, void* stream);
 /* Per-frame shot-noise normalisers (the full-frame means of generate_shot_noise,
  * data/v2v_core_v2e.py:90-96): scales[b,k-1] = (rate/2*dt_k)/mean_pixels(inten_factor*nominal/thres). */
 int v2v_v2e_shot_scales(const v2v_v2e_desc* desc, double* shot_pos_scale, double* shot_neg_scale, void* stream);
+
+/* Audit hook for V2V_NOISE_PHILOX (like v2v_esim_philox_fields): leak_randn [B,N-1,H,W] float64, pos_shot /
+ * neg_shot [B,N-1,H,W] int32 exactly as the kernel draws them; replay with V2V_NOISE_EXPLICIT is bit-identical. */
+int v2v_v2e_philox_fields(const v2v_v2e_desc* desc, double* leak_randn, int32_t* pos_shot, int32_t* neg_shot, void* stream);
 
 /* ======================================================================= *
  * 3. Event stream -> voxel (segmented by windows)

@@ -189,7 +189,7 @@ def _v2e_thresholds(params, a, b):
     return pos, neg, np.divide(pos_nom, pos), np.divide(neg_nom, neg)
 
 
-def v2e_video_to_voxel(video, fps, params, rs=np.random, lut=None, record=None):
+def v2e_video_to_voxel(video, fps, params, rs=np.random, lut=None, record=None, maps=None):
     """v2e-style simulation, float64 [N-1,H,W] of (pos - neg) counts per interval.
 
     Restates video_to_voxel / EventEmulator.generate_events
@@ -204,6 +204,10 @@ def v2e_video_to_voxel(video, fps, params, rs=np.random, lut=None, record=None):
     dict every drawn field is stored in it (lists per frame) so that a GPU run
     can replay exactly the same fields:  thr_a, thr_b, noise_randn, and per
     frame k>=1: leak_randn[k-1], pos_shot[k-1], neg_shot[k-1].
+
+    ``maps=(pos_thres, neg_thres, noise_rate)`` replaces the first-frame draws
+    (:333-349) by given per-pixel maps (already clipped) — used to replay GPU
+    runs whose maps were prepared elsewhere; no draw is consumed for them.
     """
     video = np.asarray(video)
     n, h, w = video.shape
@@ -241,6 +245,13 @@ def v2e_video_to_voxel(video, fps, params, rs=np.random, lut=None, record=None):
             lp = (1 - eps) * lp + eps * log_new
         else:
             lp = log_new
+        if base is None and maps is not None:
+            pos_thr, neg_thr, noise_rate = maps
+            pos_nom = params["thres_mean_mean"] + params["thres_diff_mean"] / 2
+            neg_nom = params["thres_mean_mean"] - params["thres_diff_mean"] / 2
+            pos_pp, neg_pp = np.divide(pos_nom, pos_thr), np.divide(neg_nom, neg_thr)
+            base = lp
+            continue
         if base is None:                                              # :474-478
             a = rs.normal(loc=params["thres_mean_mean"], scale=params["thres_mean_std"], size=shape)
             if model == "pn_related":

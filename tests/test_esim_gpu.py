@@ -3,6 +3,8 @@
 Bar: crossing counts bit-exact; voxels bit-exact as float32 (integer valued) and within 1e-5 relative
 in the external-noise mode (float64 sums rounded to float32).
 """
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -130,8 +132,6 @@ def test_near_multiple_thresholds(cuda_device):
         for _ in range(int(g.integers(0, 4))):
             target = np.nextafter(target, np.inf if g.random() < 0.5 else -np.inf)
         pot0 = target - d                       # potential lands (almost) on a multiple of the threshold
-        ref, _ = orc.esim_video_to_voxel(vid, thr, thr, 0.0, np.zeros((h, w)), np.zeros((h, w)), np.zeros((1, h, w)),
-                                         False, lut, return_state=True), None
         # feed pot0 through potential_in (u0 path would re-derive it)
         fr = torch.from_numpy(vid).to(cuda_device)
         o = v2v.frames_to_voxel(fr, thr, thr, num_bins=1, potential_in=pot0[None], return_potential=True, lut=lut)
@@ -264,3 +264,73 @@ def test_errors(cuda_device):
     out = v2v.frames_to_voxel(torch.zeros((1, 1, 8, 8), dtype=torch.uint8, device=cuda_device), 0.2, 0.2, num_bins=5)
     assert out.voxel.shape == (1, 0, 5, 8, 8)                     # single frame: no intervals
     assert v2v.EventEmulator(rng="numpy").video_to_voxel(np.zeros((1, 4, 4), np.uint8)).shape == (0, 4, 4)
+
+
+# ---------------------------------------------------------------------------------------------
+# the throughput kernel (csrc/esim_fast.cu): taken for per-clip thresholds, fpb=1, noise none/philox,
+# and B*H*W >= 148*2048 pixels with H*W % 4 == 0
+# ---------------------------------------------------------------------------------------------
+
+@pytest.mark.parametrize("kind,pos,neg", [("walk", 0.2, 0.2), ("iid", 0.05, 0.0625), ("iid", 1.3, 0.9), ("walk", 0.11, 0.1)])
+def test_fast_kernel_noise_free_vs_oracle(cuda_device, kind, pos, neg):
+    import v2v_b200 as v2v
+    lut = orc.esim_log_lut()
+    n, h, w = 16, 480, 640                      # ragged trip count: 15 intervals = 3 trips of 4 + tail of 3
+    vid = synth_video(kind, n, h, w, 21)
+    g = np.random.Generator(np.random.PCG64(8))
+    u0 = g.random((h, w))
+    fr = torch.from_numpy(vid).to(cuda_device)
+    o = v2v.frames_to_voxel(fr, pos, neg, num_bins=5, u0=u0[None], lut=lut, with_stats=True, return_potential=True,
+                            frame_out="frames")
+    ref, pot = orc.esim_video_to_voxel(vid, pos, neg, 0.0, u0, np.zeros((h, w)), np.zeros((n - 1, h, w)), False, lut,
+                                       return_state=True)
+    assert np.array_equal(o.voxel[0].cpu().numpy().astype(np.float64), orc.bin_accumulate(ref, 5, 1))
+    assert np.array_equal(o.potential[0].cpu().numpy(), pot)
+    st = o.stats[0].cpu().numpy()
+    assert st[0] == int(np.maximum(ref, 0).sum()) and st[1] == int(np.maximum(-ref, 0).sum())
+    assert np.array_equal(o.frames[0].cpu().numpy(), orc.pack_frames(vid[..., None], 5, 3, False))
+    # the generic kernel must agree bit for bit
+    os.environ["V2V_ESIM_GENERIC"] = "1"
+    try:
+        o2 = v2v.frames_to_voxel(fr, pos, neg, num_bins=5, u0=u0[None], lut=lut, with_stats=True, return_potential=True)
+    finally:
+        del os.environ["V2V_ESIM_GENERIC"]
+    assert torch.equal(o.voxel, o2.voxel) and torch.equal(o.potential, o2.potential) and torch.equal(o.stats, o2.stats)
+
+
+def test_philox_run_equals_oracle_on_dumped_fields(cuda_device):
+    """Production mode end to end: the Philox kernels (fast and generic) == the CPU oracle fed with the very
+    random fields the generator produced (dumped through the audit hook)."""
+    import v2v_b200 as v2v
+    lut = orc.esim_log_lut()
+    n, h, w = 11, 480, 640
+    vid = synth_video("walk", n, h, w, 31)
+    fr = torch.from_numpy(vid).to(cuda_device)
+    pos, neg, std, frac, hstd = 0.18, 0.26, 0.07, 0.002, 6.0
+    kw = dict(num_bins=5, noise="philox", base_noise_std=std, hot_pixel_fraction=frac, hot_pixel_std=hstd, seed=77,
+              clip_index_base=5, with_stats=True, return_potential=True)
+    fast = v2v.frames_to_voxel(fr, pos, neg, **kw)
+    os.environ["V2V_ESIM_GENERIC"] = "1"
+    try:
+        gen = v2v.frames_to_voxel(fr, pos, neg, **kw)
+    finally:
+        del os.environ["V2V_ESIM_GENERIC"]
+    assert torch.equal(fast.voxel, gen.voxel) and torch.equal(fast.potential, gen.potential)
+    assert torch.equal(fast.stats, gen.stats)
+    u0, hot, bn = v2v.philox_fields(n, h, w, base_noise_std=std, hot_pixel_fraction=frac, hot_pixel_std=hstd, seed=77,
+                                    clip_index_base=5)
+    u0, hot, bn = u0[0].cpu().numpy(), hot[0].cpu().numpy(), bn[0].cpu().numpy()
+    # sanity of the generator itself
+    assert 0.0 <= u0.min() and u0.max() < 1.0 and abs(u0.mean() - 0.5) < 0.01
+    nz = (hot != 0).mean()
+    assert abs(nz - frac) < 0.0008
+    z = bn / np.float32(std)
+    assert abs(z.mean()) < 0.01 and abs(z.std() - 1.0) < 0.01
+    assert abs((np.abs(z) > 3).mean() - 0.0027) < 0.0005
+    ref, pot = orc.esim_video_to_voxel(vid, pos, neg, 1.0, u0, hot, bn, False, lut, return_state=True)
+    assert np.array_equal(fast.voxel[0].cpu().numpy().astype(np.float64), orc.bin_accumulate(ref, 5, 1))
+    assert np.array_equal(fast.potential[0].cpu().numpy(), pot)
+    # and explicit replay on the GPU
+    rep = v2v.frames_to_voxel(fr, pos, neg, num_bins=5, noise="explicit", base_noise_std=1.0, u0=u0[None], hot_noise=hot[None],
+                              base_gauss=bn[None], lut=lut)
+    assert torch.equal(rep.voxel, fast.voxel)

@@ -69,18 +69,48 @@ def test_v2e_large_vectorised_vs_oracle(cuda_device):
 
 
 def test_v2e_philox_statistics(cuda_device):
+    """In-kernel Philox leak jitter + Poisson shot noise: deterministic per seed; the run equals the CPU oracle
+    replaying the very fields the generator drew (audit hook); the fields have the right distribution."""
     from v2v_b200.v2e import frames_to_voxel_v2e
-    n, h, w = 25, 256, 256
-    vid = np.full((n, h, w), 100, dtype=np.uint8)
+    n, h, w = 13, 256, 256
+    vid = synth_video("walk", n, h, w, 8)
     fr = torch.from_numpy(vid).to(cuda_device)
-    thr = np.full((1, h, w), 0.2)
+    p = dict(threshold_model="pn_related", thres_mean_mean=0.2, thres_mean_std=0.03, thres_diff_mean=0.0,
+             thres_diff_std=0.03, cutoff_hz=30.0, leak_rate_hz=0.1, shot_noise_rate_hz=5.0, leak_jitter_fraction=0.1,
+             noise_rate_cov_decades=0.1)
+    g = np.random.Generator(np.random.PCG64(1))
+    pos = np.clip(g.normal(0.2, 0.03, (h, w)), 0.01, None)
+    neg = np.clip(g.normal(0.2, 0.03, (h, w)), 0.01, None)
+    nrate = np.exp(np.log(10) * 0.1 * g.standard_normal((h, w)).astype(np.float32)).astype(np.float32)
     kw = dict(fps=24, cutoff_hz=30.0, leak_rate_hz=0.1, shot_noise_rate_hz=5.0, leak_jitter_fraction=0.1,
-              noise_rate=np.ones((1, h, w), np.float32), noise="philox", with_stats=True)
-    a = frames_to_voxel_v2e(fr, thr, thr, seed=1, **kw)
-    b = frames_to_voxel_v2e(fr, thr, thr, seed=1, **kw)
-    assert torch.equal(a["voxel"], b["voxel"])
-    st = a["stats"].cpu().numpy()[0]
-    # static scene: shot noise only, expectation rate/2 * duration per pixel and polarity (+ a few leak events)
-    expect = 2.5 * (n - 1) / 24 * h * w
-    assert abs(st[1] - expect) / expect < 0.05
-    assert abs(st[0] - expect) / expect < 0.10
+              noise_rate=nrate[None], noise="philox", with_stats=True)
+    a = frames_to_voxel_v2e(fr, pos[None], neg[None], seed=1, return_fields=True, **kw)
+    b = frames_to_voxel_v2e(fr, pos[None], neg[None], seed=1, **kw)
+    c = frames_to_voxel_v2e(fr, pos[None], neg[None], seed=2, **kw)
+    assert torch.equal(a["voxel"], b["voxel"]) and not torch.equal(a["voxel"], c["voxel"])
+    f = {k: v[0].cpu().numpy() for k, v in a["fields"].items()}
+    # distribution of the drawn fields
+    z = f["leak_randn"]
+    assert abs(z.mean()) < 0.01 and abs(z.std() - 1) < 0.01
+    lam = 2.5 / 24                                      # rate/2 * dt, averaged over the frame by construction
+    assert abs(f["pos_shot"].mean() - lam) / lam < 0.03 and abs(f["neg_shot"].mean() - lam) / lam < 0.03
+    # oracle replay of exactly these fields (maps given, per-frame draws replayed in the reference's order)
+    class Replay:
+        def __init__(self):
+            self.leak, self.shots = list(f["leak_randn"]), []
+            for x, y in zip(f["pos_shot"], f["neg_shot"]):
+                self.shots += [x, y]
+
+        def randn(self, *shape):
+            return self.leak.pop(0)
+
+        def poisson(self, lam):
+            return self.shots.pop(0)
+
+    ref = orc.v2e_video_to_voxel(vid.astype(np.float64), 24, p, Replay(), maps=(pos, neg, nrate))
+    assert np.array_equal(a["voxel"][0, :, 0].cpu().numpy().astype(np.float64), ref)
+    # explicit replay on the GPU agrees too
+    e = frames_to_voxel_v2e(fr, pos[None], neg[None], fps=24, cutoff_hz=30.0, leak_rate_hz=0.1, shot_noise_rate_hz=5.0,
+                            leak_jitter_fraction=0.1, noise_rate=nrate[None], noise="explicit",
+                            leak_randn=f["leak_randn"][None], pos_shot=f["pos_shot"][None], neg_shot=f["neg_shot"][None])
+    assert torch.equal(e["voxel"], a["voxel"])

@@ -6,7 +6,8 @@ loudly without one (no CPU fallback).
 """
 from . import _lib
 from ._lib import V2VError, launch_count
-from .esim import EventEmulator, EsimOutput, esim_log_lut, frames_to_voxel, draw_reference_randomness
+from .esim import (EventEmulator, EsimOutput, esim_log_lut, frames_to_voxel, draw_reference_randomness,
+                   philox_fields)
 from .events import (MakeVoxelMixin, event_count_map, events_to_image, events_to_image_torch,
                      events_to_neg_pos_voxel_torch, events_to_voxel, events_to_voxel_torch, make_voxel,
                      voxelize_windows)
@@ -15,7 +16,7 @@ from .pipeline import HostPipeline
 
 __all__ = [
     "V2VError", "launch_count", "EventEmulator", "EsimOutput", "esim_log_lut", "frames_to_voxel",
-    "draw_reference_randomness", "MakeVoxelMixin", "event_count_map", "events_to_image",
+    "draw_reference_randomness", "philox_fields", "MakeVoxelMixin", "event_count_map", "events_to_image",
     "events_to_image_torch", "events_to_neg_pos_voxel_torch", "events_to_voxel", "events_to_voxel_torch",
     "make_voxel", "voxelize_windows", "ImgsToVoxelsMixin", "V2VVoxelizer", "sample_v2e_params", "HostPipeline",
 ]

@@ -91,8 +91,10 @@ SYMBOLS = {
     "v2v_device_info": (C.c_int, [C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "v2v_launch_count": (C.c_longlong, []),
     "v2v_esim_frames_to_voxel": (C.c_int, [C.POINTER(EsimDesc), _p]),
+    "v2v_esim_philox_fields": (C.c_int, [C.POINTER(EsimDesc), _p, _p, _p, _p]),
     "v2v_v2e_frames_to_voxel": (C.c_int, [C.POINTER(V2eDesc), _p]),
     "v2v_v2e_shot_scales": (C.c_int, [C.POINTER(V2eDesc), _p, _p, _p]),
+    "v2v_v2e_philox_fields": (C.c_int, [C.POINTER(V2eDesc), _p, _p, _p, _p]),
     "v2v_events_to_voxel": (C.c_int, [C.POINTER(ScatterDesc), _p]),
     "v2v_events_to_image": (C.c_int, [C.POINTER(ImageDesc), _p]),
 }

@@ -96,17 +96,35 @@ struct Philox {
   }
 };
 
-// Two standard normals from two 32-bit words (Box–Muller, float32 math: the
-// in-kernel generator is a statistical stand-in for the reference's MT19937
-// stream, which cannot be reproduced on a GPU — parity runs use EXPLICIT noise).
-__device__ __forceinline__ float2 box_muller(uint32_t a, uint32_t b) {
-  // u1 in (0,1], u2 in [0,1)
-  float u1 = (static_cast<float>(a >> 8) + 1.0f) * (1.0f / 16777216.0f);
-  float u2 = static_cast<float>(b >> 8) * (1.0f / 16777216.0f);
-  float r = sqrtf(-2.0f * __logf(u1));
-  float s, c;
-  __sincosf(6.28318530717958647692f * u2, &s, &c);
+// Two scaled normals from ONE 32-bit word (Box-Muller in float32 on the SFU: lg2 / sqrt / sin / cos
+// approximations): low 16 bits -> radius, high 16 bits -> angle, so one Philox4x32 call yields 8 normals.
+// The radius has 65536 levels (tail cut at sqrt(2 ln 65536) = 4.71 sigma, 2.6e-6 of the mass).  The
+// in-kernel generator is a statistical stand-in for the reference's MT19937 + polar method, which cannot
+// be reproduced on a GPU; bit-parity runs use EXPLICIT noise fields instead.
+__device__ __forceinline__ float2 box_muller16(uint32_t w, float scale) {
+  // mantissa trick: floats in [1,2) straight from the random bits, no int->float conversion
+  const float f1 = __uint_as_float(((w << 7) & 0x007fff80u) | 0x3f800000u);
+  const float f2 = __uint_as_float(((w >> 9) & 0x007fff80u) | 0x3f800000u);
+  const float u1 = 2.0f - f1;                                  // (0,1], 16 bits
+  float l, r, s, c;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l) : "f"(u1));
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(l * -1.3862943611198906f));             // sqrt(-2 ln u1)
+  const float th = fmaf(f2, 6.28318530717958647692f, -6.28318530717958647692f);              // [0, 2 pi)
+  asm("sin.approx.ftz.f32 %0, %1;" : "=f"(s) : "f"(th));
+  asm("cos.approx.ftz.f32 %0, %1;" : "=f"(c) : "f"(th));
+  r *= scale;
   return make_float2(r * c, r * s);
+}
+
+// Full-resolution pair from two words (used once per pixel for the hot-pixel amplitude).
+__device__ __forceinline__ float2 box_muller(uint32_t a, uint32_t b) {
+  const float f1 = __uint_as_float((a & 0x007fffffu) | 0x3f800000u);
+  const float f2 = __uint_as_float((b & 0x007fffffu) | 0x3f800000u);
+  const float u1 = 2.0f - f1;
+  float r;
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(__log2f(u1) * -1.3862943611198906f));
+  const float th = fmaf(f2, 6.28318530717958647692f, -6.28318530717958647692f);
+  return make_float2(r * __cosf(th), r * __sinf(th));
 }
 
 // Uniform double in [0,1) with 53 random bits (same construction as numpy's

@@ -9,22 +9,14 @@
 // Log intensities come from the 256-entry float64 LUT the host built with the
 // reference's NumPy expression (never recomputed here: bit parity).  HBM bound:
 // 1 byte in + 4/frames_per_bin bytes out per pixel-interval.
-#include "common.cuh"
+#include "esim_common.cuh"
+
+#include <cstdlib>
 
 namespace v2v {
 namespace {
 
-struct EsimArgs {
-  v2v_esim_desc d;
-  int64_t HW;
-  int32_t T;          // voxels per clip
-  int32_t G;          // bins * fpb
-  int64_t row_stride, plane_stride;
-  int32_t padded;     // voxel rows are strided (row_stride != W)
-  int32_t Tf;         // frames written per clip in frame_out
-};
-
-constexpr int kThreads = 256;
+constexpr int kThreads = kEsimThreads;
 
 template <int P>
 struct PixWord;
@@ -55,7 +47,8 @@ __global__ void __launch_bounds__(kThreads) esim_kernel(const EsimArgs a) {
   const int N = d.N;
   const int64_t clip_pix = static_cast<int64_t>(b) * HW + pix0;   // offset in [B,H,W] maps
   const uint64_t clip_id = d.clip_index_base + static_cast<uint64_t>(b);
-  const uint2 key = make_uint2(static_cast<uint32_t>(d.seed), static_cast<uint32_t>(d.seed >> 32));
+  const NoiseKey nkey = make_noise_key(d.seed, clip_id);
+  const float nstd_f = static_cast<float>((NOISE != V2V_NOISE_NONE && d.base_noise_std) ? d.base_noise_std[b] : 0.0);
 
   // ---- per-pixel / per-clip constants ----
   double pos[PERPIXEL ? P : 1], neg[PERPIXEL ? P : 1], rpos[PERPIXEL ? P : 1], rneg[PERPIXEL ? P : 1];
@@ -90,17 +83,8 @@ __global__ void __launch_bounds__(kThreads) esim_kernel(const EsimArgs a) {
     hot[k] = 0.0;
     double u = -1.0;
     if (NOISE == V2V_NOISE_PHILOX) {
-      const uint64_t px = static_cast<uint64_t>(pix0 + k);
-      uint4 r = Philox::run(make_uint4(static_cast<uint32_t>(px), static_cast<uint32_t>(px >> 32),
-                                       static_cast<uint32_t>(clip_id), 0x80000000u | static_cast<uint32_t>((clip_id >> 32) & 0xffffu)),
-                            key);
-      u = uniform53(r.x, r.y);
-      if (uniform53(r.z, r.w) < d.hot_pixel_fraction[b]) {
-        uint4 r2 = Philox::run(make_uint4(static_cast<uint32_t>(px), static_cast<uint32_t>(px >> 32),
-                                          static_cast<uint32_t>(clip_id), 0xC0000000u | static_cast<uint32_t>((clip_id >> 32) & 0xffffu)),
-                               key);
-        hot[k] = __dmul_rn(d.hot_pixel_std[b], static_cast<double>(box_muller(r2.x, r2.y).x));
-      }
+      philox_init_pixel(static_cast<uint64_t>(pix0 + k), nkey, d.hot_pixel_fraction[b],
+                        static_cast<float>(d.hot_pixel_std[b]), &u, &hot[k]);
     } else if (NOISE == V2V_NOISE_EXPLICIT) {
       if (d.hot_noise) hot[k] = d.hot_noise[clip_pix + k];
     }
@@ -181,20 +165,13 @@ __global__ void __launch_bounds__(kThreads) esim_kernel(const EsimArgs a) {
             for (int k = 0; k < P; ++k) bn[k] = 0.0;
           }
         } else if (NOISE == V2V_NOISE_PHILOX) {
-          // one Philox call per aligned group of 4 pixels and interval -> 4 normals
-          const uint64_t g4 = static_cast<uint64_t>(pix0) >> 2;
-          uint4 r = Philox::run(make_uint4(static_cast<uint32_t>(g4), static_cast<uint32_t>(i - 1),
-                                           static_cast<uint32_t>(clip_id),
-                                           static_cast<uint32_t>((g4 >> 32) & 0x3fffu) << 16 | static_cast<uint32_t>((clip_id >> 32) & 0xffffu)),
-                                key);
-          const float2 n01 = box_muller(r.x, r.y), n23 = box_muller(r.z, r.w);
-          const float nn[4] = {n01.x, n01.y, n23.x, n23.y};
           if (P == 4) {
+            float ev[4], od[4];
+            philox_noise8(static_cast<uint64_t>(pix0) >> 2, static_cast<uint32_t>(i - 1) >> 1, nkey, nstd_f, ev, od);
 #pragma unroll
-            for (int k = 0; k < P; ++k) bn[k] = __dmul_rn(nstd, static_cast<double>(nn[k]));
+            for (int k = 0; k < P; ++k) bn[k] = static_cast<double>(((i - 1) & 1) ? od[k % 4] : ev[k % 4]);
           } else {
-            const int sel = static_cast<int>(pix0 & 3);
-            bn[0] = __dmul_rn(nstd, static_cast<double>(sel == 0 ? nn[0] : sel == 1 ? nn[1] : sel == 2 ? nn[2] : nn[3]));
+            bn[0] = static_cast<double>(philox_noise1(static_cast<uint64_t>(pix0), static_cast<uint32_t>(i - 1), nkey, nstd_f));
           }
         }
 
@@ -318,6 +295,28 @@ int dispatch_mode(const EsimArgs& a, cudaStream_t s) {
   return V2V_ERR_INVALID_ARG;
 }
 
+// Materialise the Philox noise fields exactly as the simulation kernels draw them (test / audit hook):
+// feeding them back through V2V_NOISE_EXPLICIT (with base_noise_std = 1) must reproduce a PHILOX run bit for bit.
+__global__ void esim_philox_fields_kernel(const EsimArgs a, double* u0, double* hot, double* bn) {
+  const v2v_esim_desc& d = a.d;
+  const int b = blockIdx.y;
+  const int64_t pix = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (pix >= a.HW) return;
+  const NoiseKey nkey = make_noise_key(d.seed, d.clip_index_base + static_cast<uint64_t>(b));
+  const int64_t o = static_cast<int64_t>(b) * a.HW + pix;
+  double u, h;
+  philox_init_pixel(static_cast<uint64_t>(pix), nkey, d.hot_pixel_fraction[b], static_cast<float>(d.hot_pixel_std[b]), &u, &h);
+  if (u0) u0[o] = u;
+  if (hot) hot[o] = h;
+  if (bn) {
+    const float nstd_f = static_cast<float>(d.base_noise_std[b]);
+    for (int i = 0; i < d.N - 1; ++i) {
+      bn[(static_cast<int64_t>(b) * (d.N - 1) + i) * a.HW + pix] =
+          static_cast<double>(philox_noise1(static_cast<uint64_t>(pix), static_cast<uint32_t>(i), nkey, nstd_f));
+    }
+  }
+}
+
 }  // namespace
 }  // namespace v2v
 
@@ -367,5 +366,26 @@ extern "C" int v2v_esim_frames_to_voxel(const v2v_esim_desc* desc, void* stream)
   // small problems: one pixel per thread spreads the serial recurrence over more SMs
   if (static_cast<int64_t>(d.B) * HW < 148LL * 2048) vec4 = false;
   if (!vec4) return dispatch_mode<1, 4, 1>(a, s);
+  // V2V_ESIM_GENERIC=1 forces the generic kernel (tests compare the two paths bit for bit)
+  const char* force = getenv("V2V_ESIM_GENERIC");
+  if (esim_fast_eligible(a) && !(force && force[0] == '1')) return launch_esim_fast(a, s);
   return dispatch_mode<4, 4, 1>(a, s);
+}
+
+extern "C" int v2v_esim_philox_fields(const v2v_esim_desc* desc, double* u0, double* hot_noise, double* base_noise, void* stream) {
+  using namespace v2v;
+  V2V_REQUIRE(desc != nullptr, V2V_ERR_INVALID_ARG, "desc is NULL");
+  const v2v_esim_desc& d = *desc;
+  V2V_REQUIRE(d.B >= 0 && d.N >= 1 && d.H >= 0 && d.W >= 0 && d.B <= 65535, V2V_ERR_INVALID_ARG, "bad shape");
+  V2V_REQUIRE(d.base_noise_std && d.hot_pixel_fraction && d.hot_pixel_std, V2V_ERR_INVALID_ARG,
+              "base_noise_std, hot_pixel_fraction and hot_pixel_std must be non-NULL");
+  EsimArgs a;
+  a.d = d;
+  a.HW = static_cast<int64_t>(d.H) * d.W;
+  if (d.B == 0 || a.HW == 0) return V2V_OK;
+  dim3 grid(static_cast<unsigned int>((a.HW + 255) / 256), static_cast<unsigned int>(d.B));
+  esim_philox_fields_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(a, u0, hot_noise, base_noise);
+  count_launch();
+  V2V_CUDA(cudaGetLastError());
+  return V2V_OK;
 }

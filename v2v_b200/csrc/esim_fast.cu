@@ -1,0 +1,284 @@
+// ESIM frames -> voxel: the throughput kernel for the shipped configuration
+// (per-clip thresholds, frames_per_bin == 1, noise none or in-kernel Philox
+// applied to the potential; reference data/v2v_core_esim.py:26-69 with
+// put_noise_external=False, data/v2v_datasets.py:399-400 with fpb=1).
+//
+// Same arithmetic as the generic kernel in esim.cu, restructured so that the
+// warp issues as few instructions per pixel-interval as possible (the generic
+// kernel is instruction-issue bound at ~40 % of HBM bandwidth):
+//   * 4 pixels per lane, whole clip in registers, frames through a register
+//     ring of 2*PF words, voxels as one 128-bit streaming store per frame;
+//   * the LUT is replicated 16x in shared memory ([value][lane&15]) so the
+//     64-bit lookups of a half-warp never collide, whatever the pixel values;
+//   * a crossing by exactly one threshold (the common case) is handled with
+//     predicated float64 adds, no branch; only multi-threshold crossings take
+//     the divergent exact floor-division path.
+#include "esim_common.cuh"
+
+#include <cstdlib>
+
+namespace v2v {
+namespace {
+
+constexpr int kPF = 4;        // frames per loop trip; 2*kPF frames in flight
+constexpr int kLutCopies = 16;
+
+__device__ __forceinline__ int hi32(double x) { return __double2hiint(x); }
+
+// Exact multi-threshold crossing on the ORIGINAL potential x (data/v2v_core_esim.py:51-58).
+// Also correct for |x| below the threshold (count 0), so the caller's trigger may be conservative.
+__device__ __forceinline__ double multi_cross(double x, double pos, double neg, double rpos, double rneg, int* cnt) {
+  const bool down = x < 0.0;
+  const double a = fabs(x), thr = down ? neg : pos, rthr = down ? rneg : rpos;
+  if (a < thr) {
+    *cnt = 0;
+    return x;
+  }
+  const double q = floor_div_exact(a, thr, rthr);
+  const double an = __dsub_rn(a, __dmul_rn(q, thr));
+  *cnt = down ? -static_cast<int>(q) : static_cast<int>(q);
+  return down ? -an : an;
+}
+
+// The common case, branch-free: at most one threshold is crossed, so q*thr == thr exactly and
+// x - q*pos == fma(-pos, q, x) with q in {0.0, 1.0} (one rounding, same value as the reference's
+// separately rounded product and difference because the product is exact).
+template <bool STATS>
+__device__ __forceinline__ void single_cross(double& x, float& ov, float& net, float& tot, double pos, double mneg, double neg) {
+  const bool up = x >= pos, dn = x <= mneg;                                 // :52,55
+  // x + sel with sel in {-pos, +neg, 0}: one rounded add, equal to x - 1*pos / x + 1*neg  (:57-58)
+  double sel = up ? -pos : 0.0;
+  sel = dn ? neg : sel;
+  x = __dadd_rn(x, sel);
+  ov = up ? 1.0f : 0.0f;
+  ov = dn ? -1.0f : ov;
+  if (STATS) {            // float accumulators are exact below 2^24 events per thread; flushed by the caller
+    net += ov;
+    tot += fabsf(ov);
+  }
+}
+
+template <int NOISE, bool FRAMES, bool STATS, int MINB>
+__global__ void __launch_bounds__(kEsimThreads, MINB) esim_fast_kernel(const EsimArgs a) {
+  __shared__ double lut_s[256 * kLutCopies];
+  const v2v_esim_desc& d = a.d;
+  {
+    const double v = d.lut[threadIdx.x];                    // kEsimThreads == 256
+#pragma unroll
+    for (int c = 0; c < kLutCopies; ++c) lut_s[threadIdx.x * kLutCopies + c] = v;
+  }
+  __syncthreads();
+
+  const int b = blockIdx.y;
+  const int64_t pix0 = (static_cast<int64_t>(blockIdx.x) * kEsimThreads + threadIdx.x) * 4;
+  const int64_t HW = a.HW;
+  if (pix0 >= HW) return;
+  const int N = d.N;
+  const int64_t clip_pix = static_cast<int64_t>(b) * HW + pix0;
+  const NoiseKey nkey = make_noise_key(d.seed, d.clip_index_base + static_cast<uint64_t>(b));
+  const uint64_t g4 = static_cast<uint64_t>(pix0) >> 2;
+
+  const double pos = d.pos_thres[b], neg = d.neg_thres[b];
+  const double mneg = -neg;
+  const double rpos = __drcp_rn(pos), rneg = __drcp_rn(neg);
+  const int hibig = hi32(__dadd_rn(fmin(pos, neg), fmin(pos, neg)));
+  const float nstd_f = NOISE == V2V_NOISE_PHILOX ? static_cast<float>(d.base_noise_std[b]) : 0.f;
+  // byte offset of this lane's LUT copy
+  const uint32_t lut_base = static_cast<uint32_t>(__cvta_generic_to_shared(lut_s)) + (threadIdx.x & (kLutCopies - 1)) * 8u;
+  auto lut_at = [&](uint32_t v) -> double {
+    double r;
+    asm("ld.shared.f64 %0, [%1];" : "=d"(r) : "r"(lut_base + v * (kLutCopies * 8u)));
+    return r;
+  };
+  auto byte_of = [](uint32_t w, int k) -> uint32_t {      // one PRMT instead of shift+mask
+    uint32_t v;
+    asm("prmt.b32 %0, %1, 0, %2;" : "=r"(v) : "r"(w), "r"(0x4440u | static_cast<uint32_t>(k)));
+    return v;
+  };
+
+  const uint8_t* fr = d.frames + (static_cast<int64_t>(b) * N) * HW + pix0;
+  double pot[4], lprev[4], hot[4];
+  const uint32_t w0 = ld_stream_u32(fr);
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    lprev[k] = lut_at(byte_of(w0, k));
+    hot[k] = 0.0;
+    double u = -1.0;
+    if (NOISE == V2V_NOISE_PHILOX)
+      philox_init_pixel(static_cast<uint64_t>(pix0 + k), nkey, d.hot_pixel_fraction[b], static_cast<float>(d.hot_pixel_std[b]), &u, &hot[k]);
+    if (d.u0) u = d.u0[clip_pix + k];
+    if (d.potential_in) pot[k] = d.potential_in[clip_pix + k];
+    else if (u >= 0.0) pot[k] = __dsub_rn(__dmul_rn(u, __dadd_rn(pos, neg)), neg);
+    else pot[k] = 0.0;
+  }
+
+  int64_t out_off = pix0;
+  if (a.padded) {
+    const int64_t row = pix0 / d.W;
+    out_off = row * a.row_stride + (pix0 - row * d.W);
+  }
+  float* vox = d.voxel + static_cast<int64_t>(b) * a.T * d.num_bins * a.plane_stride + out_off;
+  float* fout = FRAMES ? d.frame_out + static_cast<int64_t>(b) * a.Tf * HW + pix0 : nullptr;
+  int gsub = 0;
+  if (FRAMES && d.frame_out_mode == 2) {
+    st_stream_f32x4(fout, __fdiv_rn(static_cast<float>(w0 & 0xffu), 255.0f), __fdiv_rn(static_cast<float>((w0 >> 8) & 0xffu), 255.0f),
+                    __fdiv_rn(static_cast<float>((w0 >> 16) & 0xffu), 255.0f), __fdiv_rn(static_cast<float>(w0 >> 24), 255.0f));
+    fout += HW;
+  }
+  unsigned int npos = 0, nneg = 0;      // multi-threshold events (exact integers)
+  float net = 0.f, tot = 0.f;           // single-threshold events: net = #pos - #neg, tot = #pos + #neg
+
+  bool any_hot = false;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) any_hot = any_hot || hot[k] != 0.0;
+
+  auto step = [&](const uint32_t w, const float (&bnf)[4]) {
+    float o[4];
+    double x0[4];
+    bool rare = false;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const double L = lut_at(byte_of(w, k));
+      double x = __dadd_rn(pot[k], __dsub_rn(L, lprev[k]));          // :42-43
+      lprev[k] = L;
+      if (NOISE == V2V_NOISE_PHILOX) {                                // :46-49
+        x = __dadd_rn(x, static_cast<double>(bnf[k]));
+        if (any_hot) x = __dadd_rn(x, hot[k]);                        // x + 0.0 == x: skipped for the 99.8 % of threads without a hot pixel
+      }
+      x0[k] = x;
+      // trigger of the exact multi-threshold path: |x| >= 2*min(pos,neg), tested on the high word
+      rare = rare || ((hi32(x) & 0x7fffffff) >= hibig);
+      single_cross<STATS>(x, o[k], net, tot, pos, mneg, neg);      // :51-58 with q in {0,1}
+      pot[k] = x;
+    }
+    if (rare) {                                                       // a few % of warp-steps on natural video
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        if ((hi32(x0[k]) & 0x7fffffff) >= hibig) {
+          if (STATS) {                                                // undo what single_cross counted
+            net -= o[k];
+            tot -= fabsf(o[k]);
+          }
+          int cnt;
+          pot[k] = multi_cross(x0[k], pos, neg, rpos, rneg, &cnt);   // conservative trigger: correct for any x
+          o[k] = static_cast<float>(cnt);
+          if (STATS) {
+            if (cnt > 0) npos += static_cast<unsigned int>(cnt);
+            else nneg += static_cast<unsigned int>(-cnt);
+          }
+        }
+      }
+    }
+    st_stream_f32x4(vox, o[0], o[1], o[2], o[3]);
+    vox += a.plane_stride;
+    if (FRAMES) {                                                     // data/v2v_datasets.py:329-338,352
+      if (++gsub == a.G) {
+        gsub = 0;
+        st_stream_f32x4(fout, __fdiv_rn(static_cast<float>(w & 0xffu), 255.0f), __fdiv_rn(static_cast<float>((w >> 8) & 0xffu), 255.0f),
+                        __fdiv_rn(static_cast<float>((w >> 16) & 0xffu), 255.0f), __fdiv_rn(static_cast<float>(w >> 24), 255.0f));
+        fout += HW;
+      }
+    }
+  };
+
+  // ---- main loop: kPF frames per trip, the next trip's words already in flight ----
+  const int M = N - 1;                       // intervals
+  const int trips = M / kPF;
+  uint32_t cur[kPF], nxt[kPF];
+  if (trips > 0) {
+#pragma unroll
+    for (int u = 0; u < kPF; ++u) cur[u] = ld_stream_u32(fr + static_cast<int64_t>(1 + u) * HW);
+  }
+  int i = 1;
+  const float zero4[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int t = 0; t < trips; ++t) {
+    if (t + 1 < trips) {
+#pragma unroll
+      for (int u = 0; u < kPF; ++u) nxt[u] = ld_stream_u32(fr + static_cast<int64_t>(i + kPF + u) * HW);
+    }
+    if (NOISE == V2V_NOISE_PHILOX) {
+      // intervals i-1 .. i+2 = 4t .. 4t+3: two Philox calls, 8 normals each
+      float e0[4], o0[4], e1[4], o1[4];
+      philox_noise8(g4, static_cast<uint32_t>(2 * t), nkey, nstd_f, e0, o0);
+      step(cur[0], e0);
+      step(cur[1], o0);
+      philox_noise8(g4, static_cast<uint32_t>(2 * t + 1), nkey, nstd_f, e1, o1);
+      step(cur[2], e1);
+      step(cur[3], o1);
+    } else {
+#pragma unroll
+      for (int u = 0; u < kPF; ++u) step(cur[u], zero4);
+    }
+    i += kPF;
+#pragma unroll
+    for (int u = 0; u < kPF; ++u) cur[u] = nxt[u];
+  }
+  for (; i < N; ++i) {                                                // ragged tail (< kPF intervals)
+    float bn1[4] = {0.f, 0.f, 0.f, 0.f};
+    if (NOISE == V2V_NOISE_PHILOX) {
+      float ev[4], od[4];
+      philox_noise8(g4, static_cast<uint32_t>(i - 1) >> 1, nkey, nstd_f, ev, od);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) bn1[k] = ((i - 1) & 1) ? od[k] : ev[k];
+    }
+    step(ld_stream_u32(fr + static_cast<int64_t>(i) * HW), bn1);
+  }
+
+  if (d.potential_out) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) d.potential_out[clip_pix + k] = pot[k];
+  }
+  if (STATS) {
+    npos += static_cast<unsigned int>((tot + net) * 0.5f);
+    nneg += static_cast<unsigned int>((tot - net) * 0.5f);
+    unsigned long long* st = reinterpret_cast<unsigned long long*>(d.stats + 2 * b);
+    if (__activemask() == 0xffffffffu) {
+      const long long sp = warp_sum(static_cast<long long>(npos)), sn = warp_sum(static_cast<long long>(nneg));
+      if ((threadIdx.x & 31) == 0) {
+        if (sp) atomicAdd(st, static_cast<unsigned long long>(sp));
+        if (sn) atomicAdd(st + 1, static_cast<unsigned long long>(sn));
+      }
+    } else {
+      if (npos) atomicAdd(st, static_cast<unsigned long long>(npos));
+      if (nneg) atomicAdd(st + 1, static_cast<unsigned long long>(nneg));
+    }
+  }
+}
+
+}  // namespace
+
+bool esim_fast_eligible(const EsimArgs& a) {
+  const v2v_esim_desc& d = a.d;
+  if (d.frames_per_bin != 1 || d.threshold_mode != V2V_THRES_PER_CLIP) return false;
+  if (d.noise_mode == V2V_NOISE_EXPLICIT) return false;
+  if (d.noise_mode == V2V_NOISE_PHILOX && d.put_noise_external) return false;
+  return true;
+}
+
+int launch_esim_fast(const EsimArgs& a, cudaStream_t s) {
+  const int64_t groups = a.HW / 4;
+  dim3 grid(static_cast<unsigned int>((groups + kEsimThreads - 1) / kEsimThreads), static_cast<unsigned int>(a.d.B));
+  const bool ph = a.d.noise_mode == V2V_NOISE_PHILOX, fr = a.d.frame_out_mode != 0, st = a.d.stats != nullptr;
+  // occupancy knob (CTAs per SM the register allocator must allow); V2V_ESIM_MINB overrides for tuning
+  int minb = 3;
+  if (const char* e = getenv("V2V_ESIM_MINB")) minb = atoi(e);
+#define V2V_F(NM, FR, ST)                                                               \
+  do {                                                                                  \
+    if (minb == 2) esim_fast_kernel<NM, FR, ST, 2><<<grid, kEsimThreads, 0, s>>>(a);    \
+    else if (minb == 4) esim_fast_kernel<NM, FR, ST, 4><<<grid, kEsimThreads, 0, s>>>(a); \
+    else esim_fast_kernel<NM, FR, ST, 3><<<grid, kEsimThreads, 0, s>>>(a);              \
+  } while (0)
+  if (ph) {
+    if (fr) { if (st) V2V_F(V2V_NOISE_PHILOX, true, true); else V2V_F(V2V_NOISE_PHILOX, true, false); }
+    else    { if (st) V2V_F(V2V_NOISE_PHILOX, false, true); else V2V_F(V2V_NOISE_PHILOX, false, false); }
+  } else {
+    if (fr) { if (st) V2V_F(V2V_NOISE_NONE, true, true); else V2V_F(V2V_NOISE_NONE, true, false); }
+    else    { if (st) V2V_F(V2V_NOISE_NONE, false, true); else V2V_F(V2V_NOISE_NONE, false, false); }
+  }
+#undef V2V_F
+  count_launch();
+  V2V_CUDA(cudaGetLastError());
+  return V2V_OK;
+}
+
+}  // namespace v2v

@@ -47,6 +47,25 @@ __device__ __forceinline__ int poisson_small(double lam, double u) {
   return k;
 }
 
+
+// Per pixel / interval Philox draws of the v2e model: leak jitter normal and the two Poisson uniforms.
+__device__ __forceinline__ void v2e_philox_draw(uint64_t px, uint32_t interval, uint64_t clip_id, uint2 key,
+                                                float* leak_z, double* u_pos, double* u_neg) {
+  const uint4 r = Philox::run(make_uint4(static_cast<uint32_t>(px), interval, static_cast<uint32_t>(clip_id),
+                                         0x40000000u | (static_cast<uint32_t>(px >> 32) & 0x3fffu) << 16 |
+                                             static_cast<uint32_t>((clip_id >> 32) & 0xffffu)),
+                              key);
+  *leak_z = box_muller(r.x, r.y).x;
+  *u_pos = static_cast<double>(r.z) * (1.0 / 4294967296.0);
+  *u_neg = static_cast<double>(r.w) * (1.0 / 4294967296.0);
+}
+
+__device__ __forceinline__ double v2e_shot_lambda(uint32_t v, double pre_prob, double scale) {
+  const double inten = __ddiv_rn(__dadd_rn(static_cast<double>(v), 20.0), 275.0);     // :190
+  const double fac = __dsub_rn(1.0, __dmul_rn(0.75, inten));                          // :90
+  return fac * pre_prob * scale;                                                      // :91-99
+}
+
 __device__ __forceinline__ uint32_t load_pix4(const uint8_t* p) { return ld_stream_u32(p); }
 
 template <int P, bool F32STATE>
@@ -148,16 +167,14 @@ __global__ void __launch_bounds__(kV2eThreads) v2e_kernel(const V2eArgs a) {
           lp[k] = static_cast<double>(lognew);
         }
         if (d.noise_mode == V2V_NOISE_PHILOX && (leak || shot)) {
-          const uint64_t px = static_cast<uint64_t>(pix0 + k);
-          uint4 r = Philox::run(make_uint4(static_cast<uint32_t>(px), static_cast<uint32_t>(i - 1), static_cast<uint32_t>(clip_id),
-                                           0x40000000u | (static_cast<uint32_t>(px >> 32) & 0x3fffu) << 16 | static_cast<uint32_t>((clip_id >> 32) & 0xffffu)),
-                                key);
-          if (leak) lr[k] = static_cast<double>(box_muller(r.x, r.y).x);
+          float lz;
+          double up, un;
+          v2e_philox_draw(static_cast<uint64_t>(pix0 + k), static_cast<uint32_t>(i - 1), clip_id, key, &lz, &up, &un);
+          if (leak) lr[k] = static_cast<double>(lz);
           if (shot) {
-            const double fac = __dsub_rn(1.0, __dmul_rn(0.75, inten));                // :90
             const int64_t si = static_cast<int64_t>(b) * (N - 1) + (i - 1);
-            sp[k] = poisson_small(fac * ppp[k] * d.shot_pos_scale[si], static_cast<double>(r.z) * (1.0 / 4294967296.0));
-            sn[k] = poisson_small(fac * npp[k] * d.shot_neg_scale[si], static_cast<double>(r.w) * (1.0 / 4294967296.0));
+            sp[k] = poisson_small(v2e_shot_lambda(v, ppp[k], d.shot_pos_scale[si]), up);
+            sn[k] = poisson_small(v2e_shot_lambda(v, npp[k], d.shot_neg_scale[si]), un);
           }
         }
         if (leak) {                                                                 // :192-211
@@ -234,6 +251,33 @@ __global__ void __launch_bounds__(256) v2e_shot_scale_kernel(const V2eArgs a, do
   }
 }
 
+
+// Audit hook: the random fields a PHILOX run draws, for explicit replay / oracle checks.
+__global__ void v2e_philox_fields_kernel(const V2eArgs a, double* leak_randn, int32_t* pos_shot, int32_t* neg_shot) {
+  const v2v_v2e_desc& d = a.d;
+  const int b = blockIdx.y;
+  const int64_t pix = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (pix >= a.HW) return;
+  const uint64_t clip_id = d.clip_index_base + static_cast<uint64_t>(b);
+  const uint2 key = make_uint2(static_cast<uint32_t>(d.seed), static_cast<uint32_t>(d.seed >> 32));
+  const bool shot = d.shot_noise_rate_hz > 0.0;
+  const int64_t mp = static_cast<int64_t>(b) * a.HW + pix;
+  const double ppp = __ddiv_rn(d.pos_thres_nominal, d.pos_thres[mp]), npp = __ddiv_rn(d.neg_thres_nominal, d.neg_thres[mp]);
+  for (int i = 1; i < d.N; ++i) {
+    float lz;
+    double up, un;
+    v2e_philox_draw(static_cast<uint64_t>(pix), static_cast<uint32_t>(i - 1), clip_id, key, &lz, &up, &un);
+    const int64_t o = (static_cast<int64_t>(b) * (d.N - 1) + (i - 1)) * a.HW + pix;
+    if (leak_randn) leak_randn[o] = static_cast<double>(lz);
+    if (shot && pos_shot && neg_shot) {
+      const uint32_t v = d.frames[(static_cast<int64_t>(b) * d.N + i) * a.HW + pix];
+      const int64_t si = static_cast<int64_t>(b) * (d.N - 1) + (i - 1);
+      pos_shot[o] = poisson_small(v2e_shot_lambda(v, ppp, d.shot_pos_scale[si]), up);
+      neg_shot[o] = poisson_small(v2e_shot_lambda(v, npp, d.shot_neg_scale[si]), un);
+    }
+  }
+}
+
 int validate(const v2v_v2e_desc& d, V2eArgs* a) {
   V2V_REQUIRE(d.B >= 0 && d.N >= 1 && d.H >= 0 && d.W >= 0, V2V_ERR_INVALID_ARG, "bad shape");
   V2V_REQUIRE(d.num_bins >= 1 && d.frames_per_bin >= 1, V2V_ERR_INVALID_ARG, "num_bins and frames_per_bin must be >= 1");
@@ -295,6 +339,24 @@ extern "C" int v2v_v2e_shot_scales(const v2v_v2e_desc* desc, double* shot_pos_sc
   V2V_REQUIRE(d.frames && d.pos_thres && d.neg_thres, V2V_ERR_INVALID_ARG, "frames and threshold maps must be non-NULL");
   dim3 grid(static_cast<unsigned int>(d.N - 1), static_cast<unsigned int>(d.B));
   v2e_shot_scale_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(a, shot_pos_scale, shot_neg_scale);
+  count_launch();
+  V2V_CUDA(cudaGetLastError());
+  return V2V_OK;
+}
+
+extern "C" int v2v_v2e_philox_fields(const v2v_v2e_desc* desc, double* leak_randn, int32_t* pos_shot, int32_t* neg_shot, void* stream) {
+  using namespace v2v;
+  V2V_REQUIRE(desc != nullptr, V2V_ERR_INVALID_ARG, "desc is NULL");
+  V2eArgs a;
+  int rc = validate(*desc, &a);
+  if (rc != V2V_OK) return rc;
+  const v2v_v2e_desc& d = *desc;
+  if (d.B == 0 || a.HW == 0 || d.N == 1) return V2V_OK;
+  V2V_REQUIRE(d.frames && d.pos_thres && d.neg_thres, V2V_ERR_INVALID_ARG, "frames and threshold maps must be non-NULL");
+  V2V_REQUIRE(!(d.shot_noise_rate_hz > 0.0 && pos_shot) || (d.shot_pos_scale && d.shot_neg_scale), V2V_ERR_INVALID_ARG,
+              "shot fields need the scales from v2v_v2e_shot_scales");
+  dim3 grid(static_cast<unsigned int>((a.HW + 255) / 256), static_cast<unsigned int>(d.B));
+  v2e_philox_fields_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(a, leak_randn, pos_shot, neg_shot);
   count_launch();
   V2V_CUDA(cudaGetLastError());
   return V2V_OK;

@@ -116,6 +116,9 @@ def frames_to_voxel(frames: torch.Tensor, pos_thres, neg_thres, *, num_bins: int
         raise ValueError(f"noise must be one of {sorted(_NOISE)}")
 
     def thr(x, name):
+        if (isinstance(x, torch.Tensor) and x.device == dev and x.dtype == torch.float64 and x.dim() == 1
+                and x.shape[0] == B and x.is_contiguous()):
+            return x, _lib.THRES_PER_CLIP                      # already in place: no host work
         t = x if isinstance(x, torch.Tensor) else torch.as_tensor(np.asarray(x, dtype=np.float64))
         t = t.to(device=dev, dtype=torch.float64)
         if t.dim() == 0:
@@ -140,11 +143,14 @@ def frames_to_voxel(frames: torch.Tensor, pos_thres, neg_thres, *, num_bins: int
         pm = _lib.THRES_PER_PIXEL
 
     def per_clip(x):
+        if (isinstance(x, torch.Tensor) and x.device == dev and x.dtype == torch.float64 and x.dim() == 1
+                and x.shape[0] == B and x.is_contiguous()):
+            return x
         t = torch.as_tensor(np.asarray(x, dtype=np.float64)) if not isinstance(x, torch.Tensor) else x
         t = t.to(device=dev, dtype=torch.float64)
         return (t.expand(B) if t.dim() == 0 else t).contiguous()
 
-    std_t = per_clip(base_noise_std)
+    std_t = per_clip(base_noise_std) if noise != "none" else None
     frac_t = per_clip(hot_pixel_fraction) if noise == "philox" else None
     hstd_t = per_clip(hot_pixel_std) if noise == "philox" else None
     u0_t = _as_dev(u0, dev, torch.float64, (B, H, W), "u0")
@@ -193,13 +199,38 @@ def frames_to_voxel(frames: torch.Tensor, pos_thres, neg_thres, *, num_bins: int
     s = stream if stream is not None else torch.cuda.current_stream(dev)
     with torch.cuda.device(dev):
         _lib.check(_lib.load().v2v_esim_frames_to_voxel(C.byref(d), C.c_void_p(s.cuda_stream)))
-    # inputs created above must outlive the launch on stream `s`
-    for t in (frames, pos_t, neg_t, std_t, frac_t, hstd_t, u0_t, hot_t, g_t, pin_t, lut_t):
-        if t is not None:
-            t.record_stream(s)
+    if stream is not None:       # tensors created on the current stream but consumed on `stream`
+        for t in (frames, pos_t, neg_t, std_t, frac_t, hstd_t, u0_t, hot_t, g_t, pin_t, lut_t):
+            if t is not None:
+                t.record_stream(s)
     vox = store[..., :H, :W] if (Hp, Wp) != (H, W) else store
     return EsimOutput(voxel=vox, frames=fr_t, stats=stats_t, potential=pout_t,
                       padded=store if (Hp, Wp) != (H, W) else None)
+
+
+def philox_fields(n_frames: int, height: int, width: int, *, base_noise_std, hot_pixel_fraction, hot_pixel_std,
+                  seed: int = 0, clip_index_base: int = 0, device="cuda"):
+    """The random fields a ``noise="philox"`` run draws, as float64 tensors (u0 [B,H,W], hot_noise [B,H,W],
+    base_noise [B,N-1,H,W] already scaled by base_noise_std).  Replaying them through ``noise="explicit"`` with
+    ``base_noise_std=1`` reproduces the Philox run bit for bit — the hook the tests use to check the in-kernel
+    generator path against the CPU oracle."""
+    dev = torch.device(device)
+    to = lambda x: torch.as_tensor(np.atleast_1d(np.asarray(x, dtype=np.float64))).to(dev).contiguous()
+    std_t, frac_t, hstd_t = to(base_noise_std), to(hot_pixel_fraction), to(hot_pixel_std)
+    B = std_t.shape[0]
+    u0 = torch.empty((B, height, width), dtype=torch.float64, device=dev)
+    hot = torch.empty_like(u0)
+    bn = torch.empty((B, n_frames - 1, height, width), dtype=torch.float64, device=dev)
+    d = _lib.EsimDesc()
+    d.B, d.N, d.H, d.W = B, n_frames, height, width
+    d.num_bins = d.frames_per_bin = 1
+    d.noise_mode = _lib.NOISE_PHILOX
+    d.base_noise_std, d.hot_pixel_fraction, d.hot_pixel_std = _ptr(std_t), _ptr(frac_t), _ptr(hstd_t)
+    d.seed, d.clip_index_base = int(seed) & 0xFFFFFFFFFFFFFFFF, int(clip_index_base)
+    s = torch.cuda.current_stream(dev)
+    with torch.cuda.device(dev):
+        _lib.check(_lib.load().v2v_esim_philox_fields(C.byref(d), _ptr(u0), _ptr(hot), _ptr(bn), C.c_void_p(s.cuda_stream)))
+    return u0, hot, bn
 
 
 def draw_reference_randomness(n_frames, height, width, hot_pixel_fraction, hot_pixel_std, rs=np.random):

@@ -58,7 +58,8 @@ def frames_to_voxel_v2e(frames: torch.Tensor, pos_thres, neg_thres, *, fps: floa
                         shot_noise_rate_hz: float = 0.0, leak_jitter_fraction: float = 0.0, noise_rate=None,
                         pos_thres_nominal: float = 0.2, neg_thres_nominal: float = 0.2, noise: str = "none",
                         leak_randn=None, pos_shot=None, neg_shot=None, seed: int = 0, clip_index_base: int = 0,
-                        with_stats: bool = False, lut: Optional[np.ndarray] = None) -> dict:
+                        with_stats: bool = False, lut: Optional[np.ndarray] = None,
+                        return_fields: bool = False) -> dict:
     """CUDA uint8 ``[B,N,H,W]`` + per-pixel threshold maps ``[B,H,W]`` -> float32 ``[B,T,bins,H,W]``."""
     if frames.dim() == 3:
         frames = frames.unsqueeze(0)
@@ -104,8 +105,15 @@ def frames_to_voxel_v2e(frames: torch.Tensor, pos_thres, neg_thres, *, fps: floa
             _lib.check(lib.v2v_v2e_shot_scales(C.byref(d), C.c_void_p(scales[0].data_ptr()),
                                                C.c_void_p(scales[1].data_ptr()), C.c_void_p(s.cuda_stream)))
             d.shot_pos_scale, d.shot_neg_scale = _ptr(scales[0]), _ptr(scales[1])
+        fields = None
+        if return_fields and noise == "philox":          # audit hook: what the generator drew for this very call
+            fl = torch.zeros((B, N - 1, H, W), dtype=torch.float64, device=dev)
+            fp = torch.zeros((B, N - 1, H, W), dtype=torch.int32, device=dev)
+            fn = torch.zeros_like(fp)
+            _lib.check(lib.v2v_v2e_philox_fields(C.byref(d), _ptr(fl), _ptr(fp), _ptr(fn), C.c_void_p(s.cuda_stream)))
+            fields = {"leak_randn": fl, "pos_shot": fp, "neg_shot": fn}
         _lib.check(lib.v2v_v2e_frames_to_voxel(C.byref(d), C.c_void_p(s.cuda_stream)))
-    return {"voxel": vox, "stats": stats_t}
+    return {"voxel": vox, "stats": stats_t, "fields": fields}
 
 
 def video_to_voxel(video, FPS, threshold_model, thres_mean_mean, thres_mean_std, thres_diff_mean, thres_diff_std,
