@@ -163,10 +163,11 @@ def workload_config(clips_per_step, note=""):
 # ----------------------------------------------------------------------------------------------
 
 class ClockSampler:
-    """SM clock / throttle reasons during the timed region, sampled in-process through NVML every 20 ms
+    """SM clock / throttle reasons during the timed region, sampled in-process through NVML every `period` s
     (a polling nvidia-smi subprocess takes driver locks that stall kernel launches; it is only the fallback)."""
 
-    def __init__(self, index):
+    def __init__(self, index, period=0.1):
+        self.period = period
         self.index, self.rows, self.stop_flag, self.thread, self.h = index, [], False, None, None
         self.nv = None
         try:
@@ -189,7 +190,7 @@ class ClockSampler:
                 self.rows.append((time.perf_counter(), sm, rs))
             except Exception:
                 pass
-            time.sleep(0.02)
+            time.sleep(self.period)
 
     def start(self):
         if self.nv is not None:
@@ -261,6 +262,7 @@ def run_ours(args):
 
     import torch
     import v2v_b200 as v2v
+    from v2v_b200 import dist as vdist
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback)")
     torch.cuda.set_device(local)
@@ -294,8 +296,8 @@ def run_ours(args):
     for i in range(args.warmup):
         step(i)
     barrier()
-    sampler = ClockSampler(local)
-    if rank == 0:
+    sampler = ClockSampler(local, args.clock_period)
+    if rank == 0 and not args.no_clocks:
         sampler.start()
     launches0 = v2v.launch_count()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -306,8 +308,8 @@ def run_ours(args):
     for i in range(args.steps):
         o = step(args.warmup + i)
         stats_total += o.stats.sum(dim=0)
-    if dist is not None:
-        dist.all_reduce(stats_total)                               # the only collective: event-count statistics
+    job = vdist.pack_stats(stats_total.view(1, 2), args.steps * B * PIX_INTERVALS_PER_CLIP, args.steps * B, device=dev)
+    vdist.allreduce_stats(job)                                     # the only collective: event-count statistics (NCCL)
     ev1.record()
     barrier()
     torch.cuda.nvtx.range_pop()
@@ -318,7 +320,7 @@ def run_ours(args):
         t = torch.tensor([ms], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
-    clocks = sampler.stop(t_wall0, t_wall1) if rank == 0 else None
+    clocks = (sampler.stop(t_wall0, t_wall1) if not args.no_clocks else sampler._smi_once()) if rank == 0 else None
 
     # kernel-only duration for the roofline: per-launch CUDA events on the launching stream
     evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
@@ -383,7 +385,7 @@ def run_ours(args):
                          "noise_free_launch_ms": clean_ms,
                          "noise_free_frac": B * ALGO_BYTES_PER_CLIP / (clean_ms * 1e-3) / 1e9 / peak},
             "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
-            "event_stats": {"positive": int(stats_total[0]), "negative": int(stats_total[1])},
+            "event_stats": vdist.stats_dict(job),
         }
         print(json.dumps(line))
     if dist is not None:
@@ -393,7 +395,7 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--clips", type=int, default=16, help="clips per step per GPU")
@@ -402,6 +404,8 @@ def main():
     ap.add_argument("--e2e-chunk", type=int, default=2)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-clocks", action="store_true", help="(experiments) do not sample clocks during the timed region")
+    ap.add_argument("--clock-period", type=float, default=0.1)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":

@@ -61,7 +61,9 @@ __device__ __forceinline__ void single_cross(double& x, float& ov, float& net, f
 template <int NOISE, bool FRAMES, bool STATS, int MINB>
 __global__ void __launch_bounds__(kEsimThreads, MINB) esim_fast_kernel(const EsimArgs a) {
   __shared__ double lut_s[256 * kLutCopies];
+  __shared__ unsigned long long cta_stats[2];
   const v2v_esim_desc& d = a.d;
+  if (STATS && threadIdx.x < 2) cta_stats[threadIdx.x] = 0ull;
   {
     const double v = d.lut[threadIdx.x];                    // kEsimThreads == 256
 #pragma unroll
@@ -72,7 +74,7 @@ __global__ void __launch_bounds__(kEsimThreads, MINB) esim_fast_kernel(const Esi
   const int b = blockIdx.y;
   const int64_t pix0 = (static_cast<int64_t>(blockIdx.x) * kEsimThreads + threadIdx.x) * 4;
   const int64_t HW = a.HW;
-  if (pix0 >= HW) return;
+  if (pix0 < HW) {          // (no early return: every thread reaches the stats barrier at the end)
   const int N = d.N;
   const int64_t clip_pix = static_cast<int64_t>(b) * HW + pix0;
   const NoiseKey nkey = make_noise_key(d.seed, d.clip_index_base + static_cast<uint64_t>(b));
@@ -97,15 +99,19 @@ __global__ void __launch_bounds__(kEsimThreads, MINB) esim_fast_kernel(const Esi
   };
 
   const uint8_t* fr = d.frames + (static_cast<int64_t>(b) * N) * HW + pix0;
-  double pot[4], lprev[4], hot[4];
+  double pot[4], lprev[4];
+  float hotf[4];            // Philox hot-pixel noise is double(float) by construction: keep the float
   const uint32_t w0 = ld_stream_u32(fr);
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
     lprev[k] = lut_at(byte_of(w0, k));
-    hot[k] = 0.0;
+    hotf[k] = 0.f;
     double u = -1.0;
-    if (NOISE == V2V_NOISE_PHILOX)
-      philox_init_pixel(static_cast<uint64_t>(pix0 + k), nkey, d.hot_pixel_fraction[b], static_cast<float>(d.hot_pixel_std[b]), &u, &hot[k]);
+    if (NOISE == V2V_NOISE_PHILOX) {
+      double hk;
+      philox_init_pixel(static_cast<uint64_t>(pix0 + k), nkey, d.hot_pixel_fraction[b], static_cast<float>(d.hot_pixel_std[b]), &u, &hk);
+      hotf[k] = static_cast<float>(hk);     // exact: hk was produced from a float
+    }
     if (d.u0) u = d.u0[clip_pix + k];
     if (d.potential_in) pot[k] = d.potential_in[clip_pix + k];
     else if (u >= 0.0) pot[k] = __dsub_rn(__dmul_rn(u, __dadd_rn(pos, neg)), neg);
@@ -130,7 +136,7 @@ __global__ void __launch_bounds__(kEsimThreads, MINB) esim_fast_kernel(const Esi
 
   bool any_hot = false;
 #pragma unroll
-  for (int k = 0; k < 4; ++k) any_hot = any_hot || hot[k] != 0.0;
+  for (int k = 0; k < 4; ++k) any_hot = any_hot || hotf[k] != 0.f;
 
   auto step = [&](const uint32_t w, const float (&bnf)[4]) {
     float o[4];
@@ -143,7 +149,7 @@ __global__ void __launch_bounds__(kEsimThreads, MINB) esim_fast_kernel(const Esi
       lprev[k] = L;
       if (NOISE == V2V_NOISE_PHILOX) {                                // :46-49
         x = __dadd_rn(x, static_cast<double>(bnf[k]));
-        if (any_hot) x = __dadd_rn(x, hot[k]);                        // x + 0.0 == x: skipped for the 99.8 % of threads without a hot pixel
+        if (any_hot) x = __dadd_rn(x, static_cast<double>(hotf[k]));                        // x + 0.0 == x: skipped for the 99.8 % of threads without a hot pixel
       }
       x0[k] = x;
       // trigger of the exact multi-threshold path: |x| >= 2*min(pos,neg), tested on the high word
@@ -229,19 +235,26 @@ __global__ void __launch_bounds__(kEsimThreads, MINB) esim_fast_kernel(const Esi
     for (int k = 0; k < 4; ++k) d.potential_out[clip_pix + k] = pot[k];
   }
   if (STATS) {
+    // warp shuffle -> shared atomics -> one pair of global atomics per CTA (the whole CTA belongs to clip b)
     npos += static_cast<unsigned int>((tot + net) * 0.5f);
     nneg += static_cast<unsigned int>((tot - net) * 0.5f);
-    unsigned long long* st = reinterpret_cast<unsigned long long*>(d.stats + 2 * b);
-    if (__activemask() == 0xffffffffu) {
+    const unsigned int m = __activemask();
+    if (m == 0xffffffffu) {
       const long long sp = warp_sum(static_cast<long long>(npos)), sn = warp_sum(static_cast<long long>(nneg));
       if ((threadIdx.x & 31) == 0) {
-        if (sp) atomicAdd(st, static_cast<unsigned long long>(sp));
-        if (sn) atomicAdd(st + 1, static_cast<unsigned long long>(sn));
+        atomicAdd(&cta_stats[0], static_cast<unsigned long long>(sp));
+        atomicAdd(&cta_stats[1], static_cast<unsigned long long>(sn));
       }
     } else {
-      if (npos) atomicAdd(st, static_cast<unsigned long long>(npos));
-      if (nneg) atomicAdd(st + 1, static_cast<unsigned long long>(nneg));
+      atomicAdd(&cta_stats[0], static_cast<unsigned long long>(npos));
+      atomicAdd(&cta_stats[1], static_cast<unsigned long long>(nneg));
     }
+  }
+  }  // valid
+  if (STATS) {
+    __syncthreads();
+    if (threadIdx.x < 2 && cta_stats[threadIdx.x])
+      atomicAdd(reinterpret_cast<unsigned long long*>(d.stats + 2 * blockIdx.y) + threadIdx.x, cta_stats[threadIdx.x]);
   }
 }
 
@@ -260,12 +273,11 @@ int launch_esim_fast(const EsimArgs& a, cudaStream_t s) {
   dim3 grid(static_cast<unsigned int>((groups + kEsimThreads - 1) / kEsimThreads), static_cast<unsigned int>(a.d.B));
   const bool ph = a.d.noise_mode == V2V_NOISE_PHILOX, fr = a.d.frame_out_mode != 0, st = a.d.stats != nullptr;
   // occupancy knob (CTAs per SM the register allocator must allow); V2V_ESIM_MINB overrides for tuning
-  int minb = 3;
+  int minb = 2;
   if (const char* e = getenv("V2V_ESIM_MINB")) minb = atoi(e);
 #define V2V_F(NM, FR, ST)                                                               \
   do {                                                                                  \
-    if (minb == 2) esim_fast_kernel<NM, FR, ST, 2><<<grid, kEsimThreads, 0, s>>>(a);    \
-    else if (minb == 4) esim_fast_kernel<NM, FR, ST, 4><<<grid, kEsimThreads, 0, s>>>(a); \
+    if (minb <= 2) esim_fast_kernel<NM, FR, ST, 2><<<grid, kEsimThreads, 0, s>>>(a);    \
     else esim_fast_kernel<NM, FR, ST, 3><<<grid, kEsimThreads, 0, s>>>(a);              \
   } while (0)
   if (ph) {
