@@ -153,6 +153,8 @@ int v2v_v2e_philox_fields(const v2v_v2e_desc* desc, double* leak_randn, int32_t*
  *    replaces  TestH5Dataset.make_voxel          data/testh5.py:60-90
  *              events_to_voxel_torch             utils/event_utils.py:466-507
  *              events_to_neg_pos_voxel_torch     utils/event_utils.py:509-541
+ *    Precondition: timestamps are non-decreasing inside every window (true for every h5 file the
+ *    converters of scripts/*_to_h5.py write); each bin then owns a contiguous range of events.
  * ======================================================================= */
 
 enum v2v_dtype {
@@ -189,6 +191,8 @@ typedef struct v2v_scatter_desc {
   const int64_t* window_offsets; /* [Wn+1] ascending event offsets; window w = [off[w], off[w+1]) */
   void* voxel;                   /* [Wn,num_bins,H,W]; fully written (zeros where no event) */
   long long* dropped;            /* [1] += events skipped (out-of-sensor / out-of-range bin), or NULL */
+  void* workspace;               /* optional scratch, >= Wn*((num_bins+2)*8+64) bytes: enables the bin-boundary pre-pass */
+  int64_t workspace_bytes;
 } v2v_scatter_desc;
 
 int v2v_events_to_voxel(const v2v_scatter_desc* desc, void* stream);

@@ -132,3 +132,25 @@ def test_mixin_matches_reference_signature(cuda_device):
     class DS(v2v.MakeVoxelMixin):
         num_bins, H, W, interpolate_bins = int(c["bins"]), int(c["H"]), int(c["W"]), False
     assert np.array_equal(DS().make_voxel([c["ts"], c["xs"], c["ys"], c["ps"]]), c["ref"])
+
+
+def test_large_bins_take_the_32bit_fallback(cuda_device):
+    """More than 32767 events in one bin of one window (and half of them on one pixel): the packed 16-bit
+    counters are not usable, the kernel must fall back to two 32-bit passes and stay exact."""
+    import v2v_b200 as v2v
+    h, w, ne = 64, 96, 400_000
+    g = np.random.Generator(np.random.PCG64(9))
+    xs = g.integers(0, w, ne).astype(np.uint16)
+    ys = g.integers(0, h, ne).astype(np.uint16)
+    hot = g.random(ne) < 0.5
+    xs[hot], ys[hot] = 7, 63
+    ts = np.sort(g.random(ne)) * 0.2 + 1.0
+    ps = (g.random(ne) < 0.9).astype(np.uint8)            # strongly positive: |count| on the hot pixel > 32767 per bin
+    for bins in (5, 3):
+        got = v2v.make_voxel([ts, xs, ys, ps], bins, h, w, False)
+        ref = orc.make_voxel(ts, xs, ys, ps, bins, h, w, False)
+        assert np.abs(ref).max() > 32767
+        assert np.array_equal(got, ref)
+    gi = v2v.make_voxel([ts, xs, ys, ps], 5, h, w, True)
+    ri = orc.make_voxel(ts, xs, ys, ps, 5, h, w, True)
+    assert np.allclose(gi, ri, rtol=1e-5, atol=1e-5)

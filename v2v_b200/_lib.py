@@ -71,6 +71,7 @@ class ScatterDesc(C.Structure):
         ("out_dtype", C.c_int32),
         ("xs", _p), ("ys", _p), ("ts", _p), ("ps", _p),
         ("window_offsets", _p), ("voxel", _p), ("dropped", _p),
+        ("workspace", _p), ("workspace_bytes", C.c_int64),
     ]
 
 

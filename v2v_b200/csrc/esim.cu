@@ -360,15 +360,19 @@ extern "C" int v2v_esim_frames_to_voxel(const v2v_esim_desc* desc, void* stream)
   cudaStream_t s = static_cast<cudaStream_t>(stream);
 
   // 4 pixels per thread needs 4-byte aligned frame words and 16-byte aligned voxel quads
-  bool vec4 = (HW % 4 == 0) && aligned(d.frames, 4) && aligned(d.voxel, 16) && (a.plane_stride % 4 == 0) &&
-              (!a.padded || (d.W % 4 == 0 && a.row_stride % 4 == 0)) && (!d.frame_out || aligned(d.frame_out, 16)) &&
-              (!d.base_gauss || aligned(d.base_gauss, 16));
-  // small problems: one pixel per thread spreads the serial recurrence over more SMs
-  if (static_cast<int64_t>(d.B) * HW < 148LL * 2048) vec4 = false;
-  if (!vec4) return dispatch_mode<1, 4, 1>(a, s);
-  // V2V_ESIM_GENERIC=1 forces the generic kernel (tests compare the two paths bit for bit)
-  const char* force = getenv("V2V_ESIM_GENERIC");
-  if (esim_fast_eligible(a) && !(force && force[0] == '1')) return launch_esim_fast(a, s);
+  const bool vec4 = (HW % 4 == 0) && aligned(d.frames, 4) && aligned(d.voxel, 16) && (a.plane_stride % 4 == 0) &&
+                    (!a.padded || (d.W % 4 == 0 && a.row_stride % 4 == 0)) && (!d.frame_out || aligned(d.frame_out, 16)) &&
+                    (!d.base_gauss || aligned(d.base_gauss, 16));
+  // small launches: one pixel per thread spreads the serial recurrence over more SMs (noise-free only: with
+  // Philox the 4-pixel kernel shares one generator call between its pixels and wins at every size)
+  const bool big = static_cast<int64_t>(d.B) * HW >= 148LL * 2048;
+  const char* force = getenv("V2V_ESIM_GENERIC");      // "1": generic kernel (tests compare the two paths bit for bit)
+  const char* small = getenv("V2V_ESIM_SMALL");        // tuning: "fast" / "p1" for small launches
+  const bool generic_only = force && force[0] == '1';
+  bool small_fast = d.noise_mode == V2V_NOISE_PHILOX;
+  if (small) small_fast = small[0] == 'f';
+  if (vec4 && !generic_only && esim_fast_eligible(a) && (big || small_fast)) return launch_esim_fast(a, s);
+  if (!vec4 || !big) return dispatch_mode<1, 4, 1>(a, s);
   return dispatch_mode<4, 4, 1>(a, s);
 }
 

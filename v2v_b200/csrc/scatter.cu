@@ -5,12 +5,15 @@
 // (utils/event_utils.py:466-541) and events_to_image_torch (:330-376).
 //
 // Voxel kernel: shared-memory privatised, write-once.  A work item is
-// (window, strip of rows): the CTA zeroes a [bins, rows, W] tile of accumulators
-// in shared memory, scans the window's events (coalesced reads of ys; the other
-// three streams are only touched for events that fall in the strip), adds with
-// shared-memory integer atomics, then streams the finished strip to HBM once.
-// The output is never zero-filled or read back: HBM traffic is the event
-// stream (first strip; the others hit L2) plus 4 B per voxel cell.
+// (window, bin, strip of rows).  Timestamps are non-decreasing inside a window,
+// so every bin owns a contiguous range of the window's events: warp 0 finds it
+// with a 32-ary search (same bin arithmetic as the scatter itself) while the
+// other warps zero a [rows, W] tile of accumulators in shared memory; the CTA
+// then scans only that range (coalesced reads of ys, 4 loads in flight per
+// thread; xs/ps only for events inside the strip), adds with shared-memory
+// integer atomics and streams the finished strip to HBM once.  The output is
+// never zero-filled or read back: HBM traffic is the event stream (first strip
+// of a bin; the others hit L2) plus 4 B per voxel cell.
 //
 // Accumulation is exact and order independent where the reference's is not:
 //   h5 discrete  : int32 counts (reference: float64 adds of +-1, exact too);
@@ -19,16 +22,22 @@
 //   torch modes  : float32 shared atomics (reference: sequential float32).
 #include "common.cuh"
 
+#include <cstdlib>
+
 namespace v2v {
 namespace {
 
 constexpr int kScatterThreads = 512;
-constexpr int kSmemBudget = 200 * 1024;   // one CTA per SM
+constexpr int kSmemBudget = 100 * 1024;   // two CTAs per SM
 constexpr int kFixShift = 30, kLoBits = 15;
 
+struct WinConst;
 struct ScatterArgs {
   v2v_scatter_desc d;
   int rows_per_strip, num_strips;
+  int packed16;        // h5 discrete: strips are sized for 2-byte cells
+  int64_t* bounds;     // [Wn, bins+2]: first event with bin_floor >= k for k = -1 .. bins (from the pre-pass), or NULL
+  struct WinConst* wcs; // [Wn] window constants from the pre-pass (valid when bounds != NULL)
 };
 
 __device__ __forceinline__ long long load_int(const void* p, int dtype, int64_t i, bool* ok) {
@@ -79,143 +88,301 @@ __device__ __forceinline__ long long tau_us(const void* ts, int dtype, int64_t i
   return static_cast<long long>(__fmul_rn(__fsub_rn(t[i], t[i0]), 1e6f));
 }
 
+// Bin index of event e in its window (the quantity that orders the events of a window: timestamps are
+// non-decreasing inside a window, so "bin(e) >= b" is a monotone predicate and every bin owns a contiguous range).
+struct WinConst {
+  double h5_tpb, h5_den;
+  float t_first, t_span, t_tpb;
+  int64_t e0;
+};
+
 template <int MODE>
-__global__ void __launch_bounds__(kScatterThreads, 1) scatter_kernel(const ScatterArgs a) {
+__device__ __forceinline__ WinConst window_constants(const v2v_scatter_desc& d, int64_t e0, int64_t e1) {
+  WinConst c;
+  c.e0 = e0;
+  c.h5_tpb = c.h5_den = 0.0;
+  c.t_first = c.t_span = c.t_tpb = 0.f;
+  const int B = d.num_bins;
+  if (MODE == V2V_SCATTER_H5_DISCRETE || MODE == V2V_SCATTER_H5_INTERP) {
+    const long long tl = tau_us(d.ts, d.ts_dtype, e1 - 1, e0);
+    c.h5_tpb = __ddiv_rn(__dadd_rn(static_cast<double>(tl), 0.001), static_cast<double>(B));       // testh5.py:71
+    c.h5_den = __dadd_rn(static_cast<double>(tl), 0.0001);                                         // :76-77 (ts[0]==0)
+  } else {
+    c.t_first = load_f32(d.ts, d.ts_dtype, e0);
+    c.t_span = __fsub_rn(load_f32(d.ts, d.ts_dtype, e1 - 1), c.t_first);                           // event_utils.py:489
+    c.t_tpb = __fdiv_rn(__fadd_rn(c.t_span, 0.001f), static_cast<float>(B));                       // :503
+  }
+  return c;
+}
+
+// floor of the (possibly fractional) bin coordinate of event e; *frac_coord receives the coordinate for the
+// interpolating modes.  Same expressions, same dtypes as the reference.
+template <int MODE>
+__device__ __forceinline__ double bin_floor(const v2v_scatter_desc& d, const WinConst& c, int64_t e, double* coord) {
+  const int B = d.num_bins;
+  if (MODE == V2V_SCATTER_H5_DISCRETE) {
+    const long long tau = tau_us(d.ts, d.ts_dtype, e, c.e0);
+    return floor(__ddiv_rn(static_cast<double>(tau), c.h5_tpb));                                   // testh5.py:72
+  } else if (MODE == V2V_SCATTER_H5_INTERP) {
+    const long long tau = tau_us(d.ts, d.ts_dtype, e, c.e0);
+    const double tn = __dmul_rn(__ddiv_rn(static_cast<double>(tau), c.h5_den), static_cast<double>(B - 1));   // :77
+    *coord = tn;
+    return floor(tn);
+  } else if (MODE == V2V_SCATTER_TORCH_DISCRETE) {
+    const float rel = __fsub_rn(load_f32(d.ts, d.ts_dtype, e), c.t_first);
+    return static_cast<double>(floorf(__fdiv_rn(rel, c.t_tpb)));                                   // event_utils.py:504
+  } else {
+    const float rel = __fsub_rn(load_f32(d.ts, d.ts_dtype, e), c.t_first);
+    const float tn = __fmul_rn(__fdiv_rn(rel, c.t_span), static_cast<float>(B - 1));               // :490
+    *coord = static_cast<double>(tn);
+    return static_cast<double>(floorf(tn));
+  }
+}
+
+// first event in [lo,hi) whose bin_floor is >= target, or hi (32-ary search by one warp)
+template <int MODE>
+__device__ __forceinline__ int64_t first_with_bin_ge(const v2v_scatter_desc& d, const WinConst& c, int64_t lo, int64_t hi,
+                                                      double target, int lane) {
+  while (hi - lo > 0) {
+    const int64_t n = hi - lo;
+    const int64_t step = (n + 31) / 32;
+    const int64_t probe = lo + static_cast<int64_t>(lane) * step;     // probes lo, lo+step, ...
+    bool ge = true;                                                   // positions >= hi count as "true"
+    if (probe < hi) {
+      double co;
+      ge = bin_floor<MODE>(d, c, probe, &co) >= target;
+    }
+    const unsigned int m = __ballot_sync(0xffffffffu, ge);
+    if (m == 0u) {                                                    // false at all 32 probes: answer lies after the last one
+      lo = lo + 31 * step + 1;
+      continue;
+    }
+    const int first = __ffs(m) - 1;                                   // first probing lane whose predicate holds
+    if (first == 0) return lo;                                        // predicate already true at lo
+    const int64_t nlo = lo + static_cast<int64_t>(first - 1) * step + 1;
+    int64_t nhi = lo + static_cast<int64_t>(first) * step;
+    if (nhi > hi) nhi = hi;
+    if (step == 1) return nhi;
+    lo = nlo;
+    hi = nhi;
+  }
+  return lo;
+}
+
+// Pre-pass: all bin boundaries of all windows, one warp per (window, k).  Takes the dependent search
+// round-trips out of the scatter kernel's critical path.
+template <int MODE>
+__global__ void __launch_bounds__(256) scatter_bounds_kernel(const ScatterArgs a) {
+  const v2v_scatter_desc& d = a.d;
+  const int B = d.num_bins;
+  const int64_t total = static_cast<int64_t>(d.num_windows) * (B + 2);
+  const int64_t wid = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  if (wid >= total) return;
+  const int win = static_cast<int>(wid / (B + 2)), k = static_cast<int>(wid - static_cast<int64_t>(win) * (B + 2)) - 1;
+  const int64_t e0 = d.window_offsets[win], e1 = d.window_offsets[win + 1];
+  int64_t r = e0;
+  WinConst wc;
+  wc.e0 = e0;
+  if (e1 > e0) {
+    wc = window_constants<MODE>(d, e0, e1);
+    r = first_with_bin_ge<MODE>(d, wc, e0, e1, static_cast<double>(k), threadIdx.x & 31);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    a.bounds[wid] = r;
+    if (k == -1) a.wcs[win] = wc;
+  }
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(kScatterThreads, 2) scatter_kernel(const ScatterArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
+  __shared__ int64_t s_range[2];
+  __shared__ WinConst s_wc;
   const v2v_scatter_desc& d = a.d;
   const int W = d.W, H = d.H, B = d.num_bins;
   const int R = a.rows_per_strip;
   constexpr bool kInterp = MODE == V2V_SCATTER_H5_INTERP;
   constexpr bool kTorch = MODE == V2V_SCATTER_TORCH_DISCRETE || MODE == V2V_SCATTER_TORCH_BILINEAR;
+  constexpr bool kTwoTap = MODE == V2V_SCATTER_H5_INTERP || MODE == V2V_SCATTER_TORCH_BILINEAR;
   constexpr bool kH5 = !kTorch;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 
-  const int64_t items = static_cast<int64_t>(d.num_windows) * a.num_strips;
+  int* acc_i = reinterpret_cast<int*>(smem_raw);
+  float* acc_f = reinterpret_cast<float*>(smem_raw);
+  int* acc_lo = acc_i + R * W;                  // second word of the fixed-point pair (h5 interp only)
+
+  // work item = (window, bin, strip of rows); items of one window are adjacent so its events stay in L2
+  const int64_t per_win = static_cast<int64_t>(B) * a.num_strips;
+  const int64_t items = static_cast<int64_t>(d.num_windows) * per_win;
   for (int64_t item = blockIdx.x; item < items; item += gridDim.x) {
-    const int win = static_cast<int>(item / a.num_strips);
-    const int strip = static_cast<int>(item - static_cast<int64_t>(win) * a.num_strips);
+    const int win = static_cast<int>(item / per_win);
+    const int rem = static_cast<int>(item - static_cast<int64_t>(win) * per_win);
+    const int bin = rem / a.num_strips, strip = rem - bin * a.num_strips;
     const int r0 = strip * R;
     const int rows = min(R, H - r0);
-    const int cells = B * rows * W;             // tile cells; plane stride inside the tile = rows*W
-    int* acc_i = reinterpret_cast<int*>(smem_raw);
-    float* acc_f = reinterpret_cast<float*>(smem_raw);
-    int* acc_lo = acc_i + B * R * W;            // second word of the fixed-point pair (interp only)
+    const int64_t e0 = d.window_offsets[win], e1 = d.window_offsets[win + 1];
 
-    // zero the tile
+    // event range of this bin: one round trip to the pre-pass table, or searched here by warp 0
+    if (warp == 0) {
+      int64_t lo = e0, hi = e0;
+      if (e1 > e0) {
+        WinConst wc;
+        // discrete: events with bin == b;  two-tap: events with floor(coord) in {b-1, b}
+        if (a.bounds) {
+          const int64_t* bw = a.bounds + static_cast<int64_t>(win) * (B + 2) + 1;      // bw[k], k = -1 .. B
+          lo = bw[kTwoTap ? bin - 1 : bin];
+          hi = bw[bin + 1];
+          wc = a.wcs[win];
+        } else {
+          wc = window_constants<MODE>(d, e0, e1);
+          lo = first_with_bin_ge<MODE>(d, wc, e0, e1, static_cast<double>(kTwoTap ? bin - 1 : bin), lane);
+          hi = first_with_bin_ge<MODE>(d, wc, lo, e1, static_cast<double>(bin + 1), lane);
+        }
+        if (lane == 0) s_wc = wc;
+        // events whose bin falls outside [0, B) are dropped: counted once per window
+        if (lane == 0 && strip == 0 && d.dropped) {
+          long long nd = 0;
+          if (bin == 0 && !kTwoTap) nd += lo - e0;                    // bin < 0 (unsorted / negative timestamps)
+          if (bin == B - 1) nd += e1 - hi;                            // bin >= B
+          if (nd) atomicAdd(reinterpret_cast<unsigned long long*>(d.dropped), static_cast<unsigned long long>(nd));
+        }
+      }
+      if (lane == 0) { s_range[0] = lo; s_range[1] = hi; }
+    }
+    __syncthreads();
+    const int64_t lo = s_range[0], hi = s_range[1];
+    const WinConst wc = s_wc;
+    // h5 discrete: packed 16-bit counters (two cells per word, biased by 0x8000) are exact whenever the bin holds
+    // at most 32767 events; otherwise the strip is done as two half-height passes with 32-bit counters
+    const bool packed = MODE == V2V_SCATTER_H5_DISCRETE && a.packed16 && (hi - lo) <= 32767;
+    const int passes = (MODE == V2V_SCATTER_H5_DISCRETE && a.packed16 && !packed) ? 2 : 1;
+    const int strip_r0 = r0, strip_rows = rows;
+    for (int pass = 0; pass < passes; ++pass) {
+    const int prow = passes == 2 ? (R + 1) / 2 : R;
+    const int r0 = strip_r0 + pass * prow;
+    const int rows = max(0, min(prow, strip_r0 + strip_rows - r0));
+    if (rows == 0) break;
+    const int tile_words_now = packed ? (rows * W + 1) / 2 : (kInterp ? R * W + rows * W : rows * W);   // interp: hi words at 0, lo words at R*W
     {
-      const int words = kInterp ? 2 * B * R * W : cells;
-      for (int i = threadIdx.x; i < words; i += kScatterThreads) acc_i[i] = 0;
+      int4* z = reinterpret_cast<int4*>(smem_raw);
+      const int n4 = (tile_words_now + 3) / 4;
+      const int zv = packed ? static_cast<int>(0x80008000u) : 0;
+      for (int i = threadIdx.x; i < n4; i += kScatterThreads) z[i] = make_int4(zv, zv, zv, zv);
     }
     __syncthreads();
 
-    const int64_t e0 = d.window_offsets[win], e1 = d.window_offsets[win + 1];
-    if (e1 > e0) {
-      // window-level constants
-      double h5_tpb = 0.0, h5_den = 0.0;
-      float t_first = 0.f, t_span = 0.f, t_tpb = 0.f;
-      if (kH5) {
-        const long long tl = tau_us(d.ts, d.ts_dtype, e1 - 1, e0);
-        h5_tpb = __ddiv_rn(__dadd_rn(static_cast<double>(tl), 0.001), static_cast<double>(B));       // :71
-        h5_den = __dadd_rn(static_cast<double>(tl), 0.0001);                                         // :76-77 (ts[0]==0)
-      } else {
-        t_first = load_f32(d.ts, d.ts_dtype, e0);
-        t_span = __fsub_rn(load_f32(d.ts, d.ts_dtype, e1 - 1), t_first);                             // event_utils.py:489
-        t_tpb = __fdiv_rn(__fadd_rn(t_span, 0.001f), static_cast<float>(B));                         // :503
-      }
-      long long ndrop = 0;
-      for (int64_t e = e0 + threadIdx.x; e < e1; e += kScatterThreads) {
+    long long ndrop = 0;
+    constexpr int kU = 8;                                  // events per thread in flight
+    for (int64_t eb = lo; eb < hi; eb += kU * kScatterThreads) {
+      // all loads of kU events are issued before any dependent work (one memory round-trip per trip)
+      long long yv[kU], xv[kU];
+      float pv[kU];
+      bool okv[kU];
+#pragma unroll
+      for (int u = 0; u < kU; ++u) {
+        const int64_t e = eb + u * kScatterThreads + threadIdx.x;
+        okv[u] = e < hi;
         bool ok = true;
-        const long long y = load_int(d.ys, d.ys_dtype, e, &ok);
-        const long long ry = y - r0;
-        const bool in_strip = ok && ry >= 0 && ry < rows;
-        if (!in_strip) {
-          if (strip == 0 && (!ok || y < 0 || y >= H)) ++ndrop;      // counted once per event
+        yv[u] = okv[u] ? load_int(d.ys, d.ys_dtype, e, &ok) : -1;
+        xv[u] = okv[u] ? load_int(d.xs, d.xs_dtype, e, &ok) : -1;
+        pv[u] = okv[u] ? load_f32(d.ps, d.ps_dtype, e) : 0.f;
+        if (!ok) yv[u] = xv[u] = -1;
+      }
+#pragma unroll
+      for (int u = 0; u < kU; ++u) {
+        if (!okv[u]) continue;
+        const int64_t e = eb + u * kScatterThreads + threadIdx.x;
+        const long long y = yv[u], ry = y - r0;
+        if (ry < 0 || ry >= rows) {
+          // out-of-sensor rows are reported once: by strip 0, and for two-tap modes by the event's primary bin only
+          if (strip == 0 && pass == 0 && (y < 0 || y >= H)) {
+            bool primary = true;
+            if (kTwoTap) { double co; primary = bin_floor<MODE>(d, wc, e, &co) == static_cast<double>(bin); }
+            if (primary) ++ndrop;
+          }
           continue;
         }
-        const long long x = load_int(d.xs, d.xs_dtype, e, &ok);
-        if (!ok || x < 0 || x >= W) { ++ndrop; continue; }
+        const long long x = xv[u];
+        if (x < 0 || x >= W) {
+          bool primary = true;
+          if (kTwoTap) { double co; primary = bin_floor<MODE>(d, wc, e, &co) == static_cast<double>(bin); }
+          if (primary) ++ndrop;
+          continue;
+        }
         const int cell = static_cast<int>(ry) * W + static_cast<int>(x);
-        const int plane = rows * W;
-
-        // polarity -> weight
-        float pw;
+        float pw;                                                                     // polarity -> weight
         {
-          const float p = load_f32(d.ps, d.ps_dtype, e);
+          const float p = pv[u];
           if (d.polarity_mode == V2V_POL_POS_ONLY) pw = p > 0.f ? 1.f : 0.f;          // event_utils.py:533
           else if (d.polarity_mode == V2V_POL_NEG_ONLY) pw = p <= 0.f ? 1.f : 0.f;    // :534
           else pw = kH5 ? (2.f * p - 1.f) : p;                                        // testh5.py:67
         }
-
-        if (MODE == V2V_SCATTER_H5_DISCRETE) {
-          const long long tau = tau_us(d.ts, d.ts_dtype, e, e0);
-          const double bf = floor(__ddiv_rn(static_cast<double>(tau), h5_tpb));       // :72
-          if (!(bf >= 0.0 && bf < static_cast<double>(B))) { ++ndrop; continue; }
-          atomicAdd(&acc_i[static_cast<int>(bf) * plane + cell], static_cast<int>(pw));
-        } else if (MODE == V2V_SCATTER_H5_INTERP) {
-          const long long tau = tau_us(d.ts, d.ts_dtype, e, e0);
-          const double tn = __dmul_rn(__ddiv_rn(static_cast<double>(tau), h5_den), static_cast<double>(B - 1));   // :77
-          const double fl = floor(tn);
-          if (!(fl >= 0.0 && fl < static_cast<double>(B))) { ++ndrop; continue; }
-          const int b0 = static_cast<int>(fl);
-#pragma unroll
-          for (int k = 0; k < 2; ++k) {
-            const int bi = b0 + k;
-            if (bi >= B) break;
-            const double wgt = fmax(0.0, __dsub_rn(1.0, fabs(__dsub_rn(tn, static_cast<double>(bi)))));   // :79
-            const long long fx = __double2ll_rn(__dmul_rn(wgt * static_cast<double>(pw), 1073741824.0));
-            if (fx != 0) {
-              const int hi = static_cast<int>(fx >> kLoBits);
-              const unsigned int lo = static_cast<unsigned int>(fx & ((1 << kLoBits) - 1));
-              if (hi) atomicAdd(&acc_i[bi * plane + cell], hi);
-              if (lo) atomicAdd(reinterpret_cast<unsigned int*>(&acc_lo[bi * plane + cell]), lo);
-            }
-          }
+        if (MODE == V2V_SCATTER_H5_DISCRETE) {                                        // testh5.py:73
+          if (packed) atomicAdd(&acc_i[cell >> 1], static_cast<int>(pw) * ((cell & 1) ? 65536 : 1));
+          else atomicAdd(&acc_i[cell], static_cast<int>(pw));
         } else if (MODE == V2V_SCATTER_TORCH_DISCRETE) {
-          const float rel = __fsub_rn(load_f32(d.ts, d.ts_dtype, e), t_first);
-          const float bf = floorf(__fdiv_rn(rel, t_tpb));                                                     // :504
-          if (!(bf >= 0.f && bf < static_cast<float>(B))) { ++ndrop; continue; }
-          atomicAdd(&acc_f[static_cast<int>(bf) * plane + cell], pw);
-        } else {   // TORCH_BILINEAR
-          const float rel = __fsub_rn(load_f32(d.ts, d.ts_dtype, e), t_first);
-          const float tn = __fmul_rn(__fdiv_rn(rel, t_span), static_cast<float>(B - 1));                      // :490
-          const float fl = floorf(tn);
-          if (!(fl >= 0.f && fl < static_cast<float>(B))) { ++ndrop; continue; }
-          const int b0 = static_cast<int>(fl);
-#pragma unroll
-          for (int k = 0; k < 2; ++k) {
-            const int bi = b0 + k;
-            if (bi >= B) break;
-            const float wgt = fmaxf(0.f, __fsub_rn(1.0f, fabsf(__fsub_rn(tn, static_cast<float>(bi)))));     // :494
-            const float v = __fmul_rn(pw, wgt);                                                               // :495
-            if (v != 0.f) atomicAdd(&acc_f[bi * plane + cell], v);
+          atomicAdd(&acc_f[cell], pw);                                                // event_utils.py:505
+        } else if (MODE == V2V_SCATTER_H5_INTERP) {
+          double tn;
+          bin_floor<MODE>(d, wc, e, &tn);
+          const double wgt = fmax(0.0, __dsub_rn(1.0, fabs(__dsub_rn(tn, static_cast<double>(bin)))));   // testh5.py:79
+          const long long fx = __double2ll_rn(__dmul_rn(wgt * static_cast<double>(pw), 1073741824.0));
+          if (fx != 0) {
+            const int hiw = static_cast<int>(fx >> kLoBits);
+            const unsigned int low = static_cast<unsigned int>(fx & ((1 << kLoBits) - 1));
+            if (hiw) atomicAdd(&acc_i[cell], hiw);
+            if (low) atomicAdd(reinterpret_cast<unsigned int*>(&acc_lo[cell]), low);
           }
+        } else {   // TORCH_BILINEAR
+          double tnd;
+          bin_floor<MODE>(d, wc, e, &tnd);
+          const float tn = static_cast<float>(tnd);
+          const float wgt = fmaxf(0.f, __fsub_rn(1.0f, fabsf(__fsub_rn(tn, static_cast<float>(bin)))));  // event_utils.py:494
+          const float v = __fmul_rn(pw, wgt);                                                            // :495
+          if (v != 0.f) atomicAdd(&acc_f[cell], v);
         }
       }
-      if (d.dropped && ndrop) atomicAdd(reinterpret_cast<unsigned long long*>(d.dropped), static_cast<unsigned long long>(ndrop));
     }
+    if (d.dropped && ndrop) atomicAdd(reinterpret_cast<unsigned long long*>(d.dropped), static_cast<unsigned long long>(ndrop));
     __syncthreads();
 
-    // stream the strip out: [win, b, r0 + r, x]
+    // stream the strip out once: [win, bin, r0 + r, x]
     {
-      const int plane = rows * W;
-      const int64_t out_base = (static_cast<int64_t>(win) * B) * H * W + static_cast<int64_t>(r0) * W;
-      for (int i = threadIdx.x; i < cells; i += kScatterThreads) {
-        const int b = i / plane, rem = i - b * plane;
-        double v;
+      const int cells = rows * W;
+      const int64_t out_base = ((static_cast<int64_t>(win) * B + bin) * H + r0) * W;
+      auto value = [&](int i) -> double {          // float64 outputs (drop-in make_voxel)
         if (kInterp) {
           const long long tot = static_cast<long long>(acc_i[i]) * (1 << kLoBits) +
                                 static_cast<long long>(reinterpret_cast<unsigned int*>(acc_lo)[i]);
-          v = static_cast<double>(tot) * (1.0 / 1073741824.0);
-        } else if (kTorch) {
-          v = static_cast<double>(acc_f[i]);
-        } else {
-          v = static_cast<double>(acc_i[i]);
+          return static_cast<double>(tot) * (1.0 / 1073741824.0);
         }
-        const int64_t o = out_base + static_cast<int64_t>(b) * H * W + rem;
-        if (d.out_dtype == V2V_F64) static_cast<double*>(d.voxel)[o] = v;
-        else st_stream_f32(static_cast<float*>(d.voxel) + o, static_cast<float>(v));
+        if (packed) return static_cast<double>(static_cast<int>((static_cast<unsigned int>(acc_i[i >> 1]) >> ((i & 1) * 16)) & 0xffffu) - 32768);
+        return kTorch ? static_cast<double>(acc_f[i]) : static_cast<double>(acc_i[i]);
+      };
+      auto valuef = [&](int i) -> float {          // float32 outputs without 64-bit conversions where possible
+        if (kInterp) return static_cast<float>(value(i));
+        if (packed) return static_cast<float>(static_cast<int>((static_cast<unsigned int>(acc_i[i >> 1]) >> ((i & 1) * 16)) & 0xffffu) - 32768);
+        return kTorch ? acc_f[i] : static_cast<float>(acc_i[i]);
+      };
+      if (d.out_dtype == V2V_F64) {
+        double* o = static_cast<double*>(d.voxel) + out_base;
+        for (int i = threadIdx.x; i < cells; i += kScatterThreads) o[i] = value(i);
+      } else {
+        float* o = static_cast<float*>(d.voxel) + out_base;
+        // 128-bit stores where the strip start is 16-byte aligned
+        const int head = static_cast<int>((4 - (out_base & 3)) & 3);
+        for (int i = threadIdx.x; i < min(head, cells); i += kScatterThreads) st_stream_f32(o + i, valuef(i));
+        const int n4 = (cells - min(head, cells)) / 4;
+        for (int q = threadIdx.x; q < n4; q += kScatterThreads) {
+          const int i = head + 4 * q;
+          st_stream_f32x4(o + i, valuef(i), valuef(i + 1), valuef(i + 2),
+                          valuef(i + 3));
+        }
+        for (int i = head + 4 * n4 + threadIdx.x; i < cells; i += kScatterThreads) st_stream_f32(o + i, valuef(i));
       }
     }
     __syncthreads();
+    }  // pass
   }
 }
 
@@ -285,22 +452,42 @@ extern "C" int v2v_events_to_voxel(const v2v_scatter_desc* desc, void* stream) {
 
   ScatterArgs a;
   a.d = d;
-  const int cell_bytes = d.mode == V2V_SCATTER_H5_INTERP ? 8 : 4;
-  const int64_t row_bytes = static_cast<int64_t>(d.num_bins) * d.W * cell_bytes;
-  V2V_REQUIRE(row_bytes <= kSmemBudget, V2V_ERR_UNSUPPORTED, "num_bins*W=%d*%d does not fit one shared-memory row tile", d.num_bins, d.W);
-  a.rows_per_strip = static_cast<int>(kSmemBudget / row_bytes);
+  // one tile = one bin x a strip of rows; sized so that two CTAs share an SM
+  a.packed16 = d.mode == V2V_SCATTER_H5_DISCRETE;
+  if (const char* e = getenv("V2V_SCATTER_PACKED16")) a.packed16 = a.packed16 && atoi(e) != 0;
+  const int cell_bytes = d.mode == V2V_SCATTER_H5_INTERP ? 8 : (a.packed16 ? 2 : 4);
+  const int64_t row_bytes = static_cast<int64_t>(d.W) * cell_bytes;
+  int budget = kSmemBudget;
+  if (const char* e = getenv("V2V_SCATTER_SMEM_KB")) budget = atoi(e) * 1024;
+  V2V_REQUIRE(row_bytes <= budget, V2V_ERR_UNSUPPORTED, "W=%d does not fit one shared-memory row tile", d.W);
+  a.rows_per_strip = static_cast<int>(budget / row_bytes);
   if (a.rows_per_strip > d.H) a.rows_per_strip = d.H;
   a.num_strips = (d.H + a.rows_per_strip - 1) / a.rows_per_strip;
-  const size_t smem = static_cast<size_t>(a.rows_per_strip) * row_bytes;
-  const int64_t items = static_cast<int64_t>(d.num_windows) * a.num_strips;
+  a.rows_per_strip = (d.H + a.num_strips - 1) / a.num_strips;                 // balance the strips
+  // (the 32-bit fallback of a packed strip uses two passes of ceil(R/2) rows: one extra row of slack)
+  const size_t smem = (static_cast<size_t>(a.rows_per_strip + (a.packed16 ? 1 : 0)) * row_bytes + 31) / 16 * 16;
+  const int64_t items = static_cast<int64_t>(d.num_windows) * d.num_bins * a.num_strips;
   int dev = 0, sms = 148;
   V2V_CUDA(cudaGetDevice(&dev));
   V2V_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   const int grid = static_cast<int>(items < 4LL * sms ? items : 4LL * sms);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
+  a.bounds = nullptr;
+  a.wcs = nullptr;
+  const size_t nb = static_cast<size_t>(d.num_windows) * (d.num_bins + 2) * sizeof(int64_t);
+  const size_t need = nb + static_cast<size_t>(d.num_windows) * sizeof(WinConst);
+  if (d.workspace && static_cast<size_t>(d.workspace_bytes) >= need && aligned(d.workspace, 8)) {
+    a.bounds = static_cast<int64_t*>(d.workspace);
+    a.wcs = reinterpret_cast<WinConst*>(static_cast<char*>(d.workspace) + nb);
+  }
 #define V2V_LAUNCH(M)                                                                                      \
   do {                                                                                                     \
-    V2V_CUDA(cudaFuncSetAttribute(scatter_kernel<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget)); \
+    if (a.bounds) {                                                                                        \
+      const int64_t warps = static_cast<int64_t>(d.num_windows) * (d.num_bins + 2);                        \
+      scatter_bounds_kernel<M><<<static_cast<int>((warps * 32 + 255) / 256), 256, 0, s>>>(a);              \
+      count_launch();                                                                                      \
+    }                                                                                                      \
+    V2V_CUDA(cudaFuncSetAttribute(scatter_kernel<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem))); \
     scatter_kernel<M><<<grid, kScatterThreads, smem, s>>>(a);                                              \
   } while (0)
   switch (d.mode) {

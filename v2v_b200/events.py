@@ -88,6 +88,7 @@ def voxelize_windows(xs, ys, ts, ps, window_offsets, num_bins: int, height: int,
     elif tuple(out.shape) != (wn, num_bins, height, width) or not out.is_contiguous() or not out.is_cuda:
         raise ValueError("out has the wrong shape / layout")
     dropped = torch.zeros(1, dtype=torch.int64, device=dev)
+    work = torch.empty(wn * (num_bins + 2 + 8), dtype=torch.int64, device=dev)  # bin-boundary table of the pre-pass
 
     d = _lib.ScatterDesc()
     d.num_events, d.num_windows = ne, wn
@@ -97,6 +98,7 @@ def voxelize_windows(xs, ys, ts, ps, window_offsets, num_bins: int, height: int,
     d.out_dtype = {torch.float32: _lib.F32, torch.float64: _lib.F64}[out.dtype]
     d.xs, d.ys, d.ts, d.ps = _ptr(xs_t), _ptr(ys_t), _ptr(ts_t), _ptr(ps_t)
     d.window_offsets, d.voxel, d.dropped = _ptr(off_t), _ptr(out), _ptr(dropped)
+    d.workspace, d.workspace_bytes = _ptr(work), work.numel() * 8
     s = stream if stream is not None else torch.cuda.current_stream(dev)
     with torch.cuda.device(dev):
         _lib.check(_lib.load().v2v_events_to_voxel(C.byref(d), C.c_void_p(s.cuda_stream)))
