@@ -145,7 +145,8 @@ def test_large_bins_take_the_32bit_fallback(cuda_device):
     hot = g.random(ne) < 0.5
     xs[hot], ys[hot] = 7, 63
     ts = np.sort(g.random(ne)) * 0.2 + 1.0
-    ps = (g.random(ne) < 0.9).astype(np.uint8)            # strongly positive: |count| on the hot pixel > 32767 per bin
+    ps = (g.random(ne) < 0.5).astype(np.uint8)
+    ps[hot] = 1                                           # hot pixel: > 32767 positive events per bin
     for bins in (5, 3):
         got = v2v.make_voxel([ts, xs, ys, ps], bins, h, w, False)
         ref = orc.make_voxel(ts, xs, ys, ps, bins, h, w, False)

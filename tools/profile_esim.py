@@ -19,6 +19,7 @@ ap.add_argument("--noise", default="philox")
 ap.add_argument("--clips", type=int, default=8)
 ap.add_argument("--iters", type=int, default=3)
 ap.add_argument("--time", action="store_true")
+ap.add_argument("--stats", action="store_true")
 a = ap.parse_args()
 dev = torch.device("cuda:0")
 frames = bench.make_clips(torch, dev, a.clips, 100)
@@ -26,7 +27,7 @@ vz = v2v.V2VVoxelizer(bench.TRAIN_CFG, device=dev)
 params = vz.sample_batch_params(a.clips, rs=np.random.RandomState(1234))
 col = lambda k: torch.tensor([p[k] for p in params], dtype=torch.float64, device=dev)
 out = torch.empty((a.clips, 24, 5, bench.H, bench.W), dtype=torch.float32, device=dev)
-kw = dict(num_bins=5, out=out)
+kw = dict(num_bins=5, out=out, with_stats=a.stats)
 if a.noise == "philox":
     kw.update(noise="philox", base_noise_std=col("base_noise_std"), hot_pixel_fraction=col("hot_pixel_fraction"),
               hot_pixel_std=col("hot_pixel_std"), seed=1)
@@ -41,5 +42,5 @@ torch.cuda.synchronize()
 if a.time:
     ms = [x.elapsed_time(y) for x, y in evs]
     gb = a.clips * bench.ALGO_BYTES_PER_CLIP / 1e9
-    print(f"noise={a.noise} clips={a.clips} variant={os.environ.get('V2V_ESIM_VARIANT','')} "
+    print(f"noise={a.noise} stats={int(a.stats)} clips={a.clips} variant={os.environ.get('V2V_ESIM_VARIANT','')} "
           f"ms={np.min(ms[1:] or ms):.3f} GB/s={gb / (np.min(ms[1:] or ms) * 1e-3):.0f}")

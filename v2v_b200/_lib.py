@@ -9,7 +9,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libv2v_b200.so")
+LIB_PATH = os.environ.get("V2V_B200_LIB") or os.path.join(_HERE, "lib", "libv2v_b200.so")   # env: A/B tuning only
 
 # enums (include/v2v_b200.h)
 NOISE_NONE, NOISE_EXPLICIT, NOISE_PHILOX = 0, 1, 2

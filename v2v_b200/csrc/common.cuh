@@ -96,24 +96,31 @@ struct Philox {
   }
 };
 
-// Two scaled normals from ONE 32-bit word (Box-Muller in float32 on the SFU: lg2 / sqrt / sin / cos
-// approximations): low 16 bits -> radius, high 16 bits -> angle, so one Philox4x32 call yields 8 normals.
-// The radius has 65536 levels (tail cut at sqrt(2 ln 65536) = 4.71 sigma, 2.6e-6 of the mass).  The
-// in-kernel generator is a statistical stand-in for the reference's MT19937 + polar method, which cannot
-// be reproduced on a GPU; bit-parity runs use EXPLICIT noise fields instead.
-__device__ __forceinline__ float2 box_muller16(uint32_t w, float scale) {
-  // mantissa trick: floats in [1,2) straight from the random bits, no int->float conversion
-  const float f1 = __uint_as_float(((w << 7) & 0x007fff80u) | 0x3f800000u);
-  const float f2 = __uint_as_float(((w >> 9) & 0x007fff80u) | 0x3f800000u);
-  const float u1 = 2.0f - f1;                                  // (0,1], 16 bits
-  float l, r, s, c;
+// Two scaled normals from ONE 32-bit word (Box-Muller): the low 20 bits give the radius (lg2 + sqrt on the SFU,
+// tail cut at sqrt(2 ln 2^20) = 5.27 sigma), the high 12 bits pick one of 4096 directions from a (cos, sin) table in
+// shared memory (bin centres, filled once per CTA), so one Philox4x32 call yields 8 normals with 2 SFU ops each.
+// `c2` = -2 ln2 * scale^2 folds the noise standard deviation into the radius.  The in-kernel generator is a statistical
+// stand-in for the reference's MT19937 + polar method, which cannot be reproduced on a GPU; bit-parity runs use
+// EXPLICIT noise fields instead, and the audit hooks dump exactly what this function produced.
+constexpr int kTrigEntries = 4096;
+
+__device__ __forceinline__ void fill_trig_table(float2* tab) {      // call with the whole CTA, then __syncthreads()
+  for (int k = threadIdx.x; k < kTrigEntries; k += blockDim.x) {
+    float s, c;
+    sincospif(static_cast<float>(2 * k + 1) * (1.0f / kTrigEntries), &s, &c);
+    tab[k] = make_float2(c, s);
+  }
+}
+
+__device__ __forceinline__ float2 box_muller16(uint32_t w, float c2, const float2* trig) {
+  // mantissa trick: a float in [1,2) straight from the random bits, no int->float conversion
+  const float f1 = __uint_as_float(((w << 3) & 0x007ffff8u) | 0x3f800000u);
+  const float u1 = 2.0f - f1;                                  // (0,1], 20 bits
+  float l, r;
   asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l) : "f"(u1));
-  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(l * -1.3862943611198906f));             // sqrt(-2 ln u1)
-  const float th = fmaf(f2, 6.28318530717958647692f, -6.28318530717958647692f);              // [0, 2 pi)
-  asm("sin.approx.ftz.f32 %0, %1;" : "=f"(s) : "f"(th));
-  asm("cos.approx.ftz.f32 %0, %1;" : "=f"(c) : "f"(th));
-  r *= scale;
-  return make_float2(r * c, r * s);
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(l * c2));  // scale * sqrt(-2 ln u1)
+  const float2 cs = trig[w >> 20];
+  return make_float2(r * cs.x, r * cs.y);
 }
 
 // Full-resolution pair from two words (used once per pixel for the hot-pixel amplitude).

@@ -34,6 +34,8 @@ struct PixWord<1> {
 template <int P, int NOISE, bool EXTERNAL, bool PERPIXEL, int PF, int LUTC>
 __global__ void __launch_bounds__(kThreads) esim_kernel(const EsimArgs a) {
   __shared__ double lut_s[256 * LUTC];
+  __shared__ float2 trig_s[NOISE == V2V_NOISE_PHILOX ? kTrigEntries : 1];
+  if (NOISE == V2V_NOISE_PHILOX) fill_trig_table(trig_s);
   const v2v_esim_desc& d = a.d;
   for (int i = threadIdx.x; i < 256 * LUTC; i += kThreads) lut_s[i] = d.lut[i / LUTC];
   __syncthreads();
@@ -48,7 +50,7 @@ __global__ void __launch_bounds__(kThreads) esim_kernel(const EsimArgs a) {
   const int64_t clip_pix = static_cast<int64_t>(b) * HW + pix0;   // offset in [B,H,W] maps
   const uint64_t clip_id = d.clip_index_base + static_cast<uint64_t>(b);
   const NoiseKey nkey = make_noise_key(d.seed, clip_id);
-  const float nstd_f = static_cast<float>((NOISE != V2V_NOISE_NONE && d.base_noise_std) ? d.base_noise_std[b] : 0.0);
+  const float nc2 = noise_c2(static_cast<float>((NOISE != V2V_NOISE_NONE && d.base_noise_std) ? d.base_noise_std[b] : 0.0));
 
   // ---- per-pixel / per-clip constants ----
   double pos[PERPIXEL ? P : 1], neg[PERPIXEL ? P : 1], rpos[PERPIXEL ? P : 1], rneg[PERPIXEL ? P : 1];
@@ -167,11 +169,11 @@ __global__ void __launch_bounds__(kThreads) esim_kernel(const EsimArgs a) {
         } else if (NOISE == V2V_NOISE_PHILOX) {
           if (P == 4) {
             float ev[4], od[4];
-            philox_noise8(static_cast<uint64_t>(pix0) >> 2, static_cast<uint32_t>(i - 1) >> 1, nkey, nstd_f, ev, od);
+            philox_noise8(static_cast<uint64_t>(pix0) >> 2, static_cast<uint32_t>(i - 1) >> 1, nkey, nc2, trig_s, ev, od);
 #pragma unroll
             for (int k = 0; k < P; ++k) bn[k] = static_cast<double>(((i - 1) & 1) ? od[k % 4] : ev[k % 4]);
           } else {
-            bn[0] = static_cast<double>(philox_noise1(static_cast<uint64_t>(pix0), static_cast<uint32_t>(i - 1), nkey, nstd_f));
+            bn[0] = static_cast<double>(philox_noise1(static_cast<uint64_t>(pix0), static_cast<uint32_t>(i - 1), nkey, nc2, trig_s));
           }
         }
 
@@ -298,6 +300,9 @@ int dispatch_mode(const EsimArgs& a, cudaStream_t s) {
 // Materialise the Philox noise fields exactly as the simulation kernels draw them (test / audit hook):
 // feeding them back through V2V_NOISE_EXPLICIT (with base_noise_std = 1) must reproduce a PHILOX run bit for bit.
 __global__ void esim_philox_fields_kernel(const EsimArgs a, double* u0, double* hot, double* bn) {
+  __shared__ float2 trig_s[kTrigEntries];
+  fill_trig_table(trig_s);
+  __syncthreads();
   const v2v_esim_desc& d = a.d;
   const int b = blockIdx.y;
   const int64_t pix = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
@@ -309,10 +314,10 @@ __global__ void esim_philox_fields_kernel(const EsimArgs a, double* u0, double* 
   if (u0) u0[o] = u;
   if (hot) hot[o] = h;
   if (bn) {
-    const float nstd_f = static_cast<float>(d.base_noise_std[b]);
+    const float nc2 = noise_c2(static_cast<float>(d.base_noise_std[b]));
     for (int i = 0; i < d.N - 1; ++i) {
       bn[(static_cast<int64_t>(b) * (d.N - 1) + i) * a.HW + pix] =
-          static_cast<double>(philox_noise1(static_cast<uint64_t>(pix), static_cast<uint32_t>(i), nkey, nstd_f));
+          static_cast<double>(philox_noise1(static_cast<uint64_t>(pix), static_cast<uint32_t>(i), nkey, nc2, trig_s));
     }
   }
 }

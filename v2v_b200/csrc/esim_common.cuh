@@ -21,7 +21,7 @@ constexpr int kEsimThreads = 256;
 // (seed, clip, pixel, interval), independent of launch geometry:
 //   base noise : one Philox call per aligned group of 4 pixels and PAIR of intervals,
 //                counter (group lo32, interval/2, clip lo32, tag0|group hi|clip hi16)
-//                -> 8 normals (16-bit Box-Muller); bn = double(float(base_noise_std) * r * cos/sin)
+//                -> 8 normals (Box-Muller, 20-bit radius, 4096 tabulated directions); bn = double(std*r*cos|sin)
 //   init fields: counter (pixel lo32, pixel hi32, clip lo32, tag2|clip hi16)
 //                -> u0 (53 bit), hot-mask uniform (53 bit)
 //   hot normal : same counter with tag3 -> z; hot = double(float(hot_pixel_std) * z)
@@ -40,13 +40,15 @@ __device__ __forceinline__ NoiseKey make_noise_key(uint64_t seed, uint64_t clip_
 
 // Base noise of the aligned 4-pixel group g4 for the interval pair (2*pair, 2*pair+1), already multiplied
 // by float(base_noise_std): even[k] belongs to pixel 4*g4+k at interval 2*pair, odd[k] at 2*pair+1.
-__device__ __forceinline__ void philox_noise8(uint64_t g4, uint32_t pair, const NoiseKey& nk, float scale,
+__device__ __forceinline__ float noise_c2(float scale) { return -1.3862943611198906f * scale * scale; }
+
+__device__ __forceinline__ void philox_noise8(uint64_t g4, uint32_t pair, const NoiseKey& nk, float c2, const float2* trig,
                                               float (&even)[4], float (&odd)[4]) {
   const uint4 r = Philox::run(make_uint4(static_cast<uint32_t>(g4), pair, nk.clip_lo,
                                          (static_cast<uint32_t>(g4 >> 32) & 0x3fffu) << 16 | nk.clip_hi16),
                               nk.key);
-  const float2 p0 = box_muller16(r.x, scale), p1 = box_muller16(r.y, scale), p2 = box_muller16(r.z, scale),
-               p3 = box_muller16(r.w, scale);
+  const float2 p0 = box_muller16(r.x, c2, trig), p1 = box_muller16(r.y, c2, trig), p2 = box_muller16(r.z, c2, trig),
+               p3 = box_muller16(r.w, c2, trig);
   even[0] = p0.x; odd[0] = p0.y;
   even[1] = p1.x; odd[1] = p1.y;
   even[2] = p2.x; odd[2] = p2.y;
@@ -54,9 +56,9 @@ __device__ __forceinline__ void philox_noise8(uint64_t g4, uint32_t pair, const 
 }
 
 // Same values for one pixel and one interval (generic kernel, field dump).
-__device__ __forceinline__ float philox_noise1(uint64_t px, uint32_t interval, const NoiseKey& nk, float scale) {
+__device__ __forceinline__ float philox_noise1(uint64_t px, uint32_t interval, const NoiseKey& nk, float c2, const float2* trig) {
   float ev[4], od[4];
-  philox_noise8(px >> 2, interval >> 1, nk, scale, ev, od);
+  philox_noise8(px >> 2, interval >> 1, nk, c2, trig, ev, od);
   const int k = static_cast<int>(px & 3);
   const float e = k == 0 ? ev[0] : k == 1 ? ev[1] : k == 2 ? ev[2] : ev[3];
   const float o = k == 0 ? od[0] : k == 1 ? od[1] : k == 2 ? od[2] : od[3];

@@ -60,8 +60,11 @@ __device__ __forceinline__ void single_cross(double& x, float& ov, float& net, f
 
 template <int NOISE, bool FRAMES, bool STATS, int MINB>
 __global__ void __launch_bounds__(kEsimThreads, MINB) esim_fast_kernel(const EsimArgs a) {
-  __shared__ double lut_s[256 * kLutCopies];
+  extern __shared__ __align__(16) unsigned char dyn_smem[];     // [LUT copies 32 KB][trig table 32 KB, Philox only]
+  double* lut_s = reinterpret_cast<double*>(dyn_smem);
+  float2* trig_s = reinterpret_cast<float2*>(dyn_smem + 256 * kLutCopies * sizeof(double));
   __shared__ unsigned long long cta_stats[2];
+  if (NOISE == V2V_NOISE_PHILOX) fill_trig_table(trig_s);
   const v2v_esim_desc& d = a.d;
   if (STATS && threadIdx.x < 2) cta_stats[threadIdx.x] = 0ull;
   {
@@ -84,9 +87,9 @@ __global__ void __launch_bounds__(kEsimThreads, MINB) esim_fast_kernel(const Esi
   const double mneg = -neg;
   const double rpos = __drcp_rn(pos), rneg = __drcp_rn(neg);
   const int hibig = hi32(__dadd_rn(fmin(pos, neg), fmin(pos, neg)));
-  const float nstd_f = NOISE == V2V_NOISE_PHILOX ? static_cast<float>(d.base_noise_std[b]) : 0.f;
+  const float nc2 = NOISE == V2V_NOISE_PHILOX ? noise_c2(static_cast<float>(d.base_noise_std[b])) : 0.f;
   // byte offset of this lane's LUT copy
-  const uint32_t lut_base = static_cast<uint32_t>(__cvta_generic_to_shared(lut_s)) + (threadIdx.x & (kLutCopies - 1)) * 8u;
+  const uint32_t lut_base = static_cast<uint32_t>(__cvta_generic_to_shared(dyn_smem)) + (threadIdx.x & (kLutCopies - 1)) * 8u;
   auto lut_at = [&](uint32_t v) -> double {
     double r;
     asm("ld.shared.f64 %0, [%1];" : "=d"(r) : "r"(lut_base + v * (kLutCopies * 8u)));
@@ -205,10 +208,10 @@ __global__ void __launch_bounds__(kEsimThreads, MINB) esim_fast_kernel(const Esi
     if (NOISE == V2V_NOISE_PHILOX) {
       // intervals i-1 .. i+2 = 4t .. 4t+3: two Philox calls, 8 normals each
       float e0[4], o0[4], e1[4], o1[4];
-      philox_noise8(g4, static_cast<uint32_t>(2 * t), nkey, nstd_f, e0, o0);
+      philox_noise8(g4, static_cast<uint32_t>(2 * t), nkey, nc2, trig_s, e0, o0);
       step(cur[0], e0);
       step(cur[1], o0);
-      philox_noise8(g4, static_cast<uint32_t>(2 * t + 1), nkey, nstd_f, e1, o1);
+      philox_noise8(g4, static_cast<uint32_t>(2 * t + 1), nkey, nc2, trig_s, e1, o1);
       step(cur[2], e1);
       step(cur[3], o1);
     } else {
@@ -223,7 +226,7 @@ __global__ void __launch_bounds__(kEsimThreads, MINB) esim_fast_kernel(const Esi
     float bn1[4] = {0.f, 0.f, 0.f, 0.f};
     if (NOISE == V2V_NOISE_PHILOX) {
       float ev[4], od[4];
-      philox_noise8(g4, static_cast<uint32_t>(i - 1) >> 1, nkey, nstd_f, ev, od);
+      philox_noise8(g4, static_cast<uint32_t>(i - 1) >> 1, nkey, nc2, trig_s, ev, od);
 #pragma unroll
       for (int k = 0; k < 4; ++k) bn1[k] = ((i - 1) & 1) ? od[k] : ev[k];
     }
@@ -272,13 +275,23 @@ int launch_esim_fast(const EsimArgs& a, cudaStream_t s) {
   const int64_t groups = a.HW / 4;
   dim3 grid(static_cast<unsigned int>((groups + kEsimThreads - 1) / kEsimThreads), static_cast<unsigned int>(a.d.B));
   const bool ph = a.d.noise_mode == V2V_NOISE_PHILOX, fr = a.d.frame_out_mode != 0, st = a.d.stats != nullptr;
-  // occupancy knob (CTAs per SM the register allocator must allow); V2V_ESIM_MINB overrides for tuning
-  int minb = 2;
+  // occupancy knob (CTAs per SM the register allocator must allow), from a same-box sweep on B200
+  // (profiles/r01_esim_minb_sweep.txt); V2V_ESIM_MINB overrides for tuning
+  int minb = ph ? (st ? 2 : 3) : (st ? 3 : 4);
   if (const char* e = getenv("V2V_ESIM_MINB")) minb = atoi(e);
-#define V2V_F(NM, FR, ST)                                                               \
-  do {                                                                                  \
-    if (minb <= 2) esim_fast_kernel<NM, FR, ST, 2><<<grid, kEsimThreads, 0, s>>>(a);    \
-    else esim_fast_kernel<NM, FR, ST, 3><<<grid, kEsimThreads, 0, s>>>(a);              \
+  const size_t smem = 256 * kLutCopies * sizeof(double) + (ph ? kTrigEntries * sizeof(float2) : 0);
+#define V2V_F(NM, FR, ST)                                                                                        \
+  do {                                                                                                           \
+    if (minb <= 2) {                                                                                             \
+      V2V_CUDA(cudaFuncSetAttribute(esim_fast_kernel<NM, FR, ST, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem))); \
+      esim_fast_kernel<NM, FR, ST, 2><<<grid, kEsimThreads, smem, s>>>(a);                                       \
+    } else if (minb >= 4) {                                                                                      \
+      V2V_CUDA(cudaFuncSetAttribute(esim_fast_kernel<NM, FR, ST, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem))); \
+      esim_fast_kernel<NM, FR, ST, 4><<<grid, kEsimThreads, smem, s>>>(a);                                       \
+    } else {                                                                                                     \
+      V2V_CUDA(cudaFuncSetAttribute(esim_fast_kernel<NM, FR, ST, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem))); \
+      esim_fast_kernel<NM, FR, ST, 3><<<grid, kEsimThreads, smem, s>>>(a);                                       \
+    }                                                                                                            \
   } while (0)
   if (ph) {
     if (fr) { if (st) V2V_F(V2V_NOISE_PHILOX, true, true); else V2V_F(V2V_NOISE_PHILOX, true, false); }
