@@ -334,3 +334,32 @@ def test_philox_run_equals_oracle_on_dumped_fields(cuda_device):
     rep = v2v.frames_to_voxel(fr, pos, neg, num_bins=5, noise="explicit", base_noise_std=1.0, u0=u0[None], hot_noise=hot[None],
                               base_gauss=bn[None], lut=lut)
     assert torch.equal(rep.voxel, fast.voxel)
+
+
+def test_host_pipeline_and_batch_api(cuda_device):
+    """Public host-buffer API == direct batched call; batch_to_tensors returns the train-loop layout."""
+    import v2v_b200 as v2v
+    B, n, h, w = 5, 11, 480, 640
+    vids = np.stack([synth_video("walk", n, h, w, 70 + b) for b in range(B)])
+    vz = v2v.V2VVoxelizer(dict(num_bins=5, base_noise_std_range=[0, 0.1], hot_pixel_std_range=[0, 10]), device=cuda_device)
+    params = vz.sample_batch_params(B, rs=np.random.RandomState(3))
+    fr = torch.from_numpy(vids).to(cuda_device)
+    ref = vz.batch_to_tensors(fr, params, seed=9, clip_index_base=40, with_stats=True)
+    assert ref["events"].shape == (B, 2, 5, h, w) and ref["frame"].shape == (B, 2, 1, h, w)
+    assert ref["events"].dtype == torch.float32 and ref["frame"].dtype == torch.float32
+    assert np.array_equal(ref["frame"][1].cpu().numpy(), orc.pack_frames(vids[1][..., None], 5, 2, False))
+    # padded consumer layout: same values, zero pads
+    pad = vz.batch_to_tensors(fr, params, seed=9, clip_index_base=40, pad_multiple=16 * 31)     # 480 -> 496, 640 -> 992
+    assert pad["events_padded"].shape[-2:] == (496, 992) and torch.equal(pad["events"], ref["events"])
+    assert float(pad["events_padded"][..., 480:, :].abs().sum()) == 0.0
+    # host pipeline (pinned in / pinned out, 2 clips per chunk -> ragged last chunk)
+    host_in = torch.from_numpy(vids).pin_memory()
+    host_out = torch.empty((B, 2, 5, h, w), dtype=torch.float32).pin_memory()
+    pipe = v2v.HostPipeline(vz, cuda_device, clips_per_chunk=2, seed=9)
+    st = pipe.run(host_in, params, host_out, clip_index_base=40)
+    torch.cuda.synchronize()
+    assert torch.equal(host_out, ref["events"].cpu())
+    assert torch.equal(st.cpu(), ref["stats"].cpu())
+    # sharding invariance: clips simulated one by one with their global index give the same noise streams
+    one = vz.batch_to_tensors(fr[3:4], params[3:4], seed=9, clip_index_base=43)
+    assert torch.equal(one["events"][0], ref["events"][3])

@@ -94,6 +94,26 @@ struct Philox {
     }
     return c;
   }
+  // Same function with the 10 round keys precomputed on the host (kernel parameters live in the constant bank,
+  // so the key schedule costs no instructions on the device).
+  __host__ static inline void round_keys(uint64_t seed, uint32_t (&rk)[20]) {
+    uint32_t kx = static_cast<uint32_t>(seed), ky = static_cast<uint32_t>(seed >> 32);
+    for (int r = 0; r < 10; ++r) {
+      rk[2 * r] = kx;
+      rk[2 * r + 1] = ky;
+      kx += W0;
+      ky += W1;
+    }
+  }
+  __device__ static __forceinline__ uint4 run_rk(uint4 c, const uint32_t (&rk)[20]) {
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+      const uint32_t hi0 = __umulhi(M0, c.x), lo0 = M0 * c.x;
+      const uint32_t hi1 = __umulhi(M1, c.z), lo1 = M1 * c.z;
+      c = make_uint4(hi1 ^ c.y ^ rk[2 * r], lo1, hi0 ^ c.w ^ rk[2 * r + 1], lo0);
+    }
+    return c;
+  }
 };
 
 // Two scaled normals from ONE 32-bit word (Box-Muller): the low 20 bits give the radius (lg2 + sqrt on the SFU,

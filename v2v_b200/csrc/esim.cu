@@ -49,7 +49,7 @@ __global__ void __launch_bounds__(kThreads) esim_kernel(const EsimArgs a) {
   const int N = d.N;
   const int64_t clip_pix = static_cast<int64_t>(b) * HW + pix0;   // offset in [B,H,W] maps
   const uint64_t clip_id = d.clip_index_base + static_cast<uint64_t>(b);
-  const NoiseKey nkey = make_noise_key(d.seed, clip_id);
+  const NoiseKey nkey = make_noise_key(clip_id);
   const float nc2 = noise_c2(static_cast<float>((NOISE != V2V_NOISE_NONE && d.base_noise_std) ? d.base_noise_std[b] : 0.0));
 
   // ---- per-pixel / per-clip constants ----
@@ -85,7 +85,7 @@ __global__ void __launch_bounds__(kThreads) esim_kernel(const EsimArgs a) {
     hot[k] = 0.0;
     double u = -1.0;
     if (NOISE == V2V_NOISE_PHILOX) {
-      philox_init_pixel(static_cast<uint64_t>(pix0 + k), nkey, d.hot_pixel_fraction[b],
+      philox_init_pixel(static_cast<uint64_t>(pix0 + k), nkey, a.rk, d.hot_pixel_fraction[b],
                         static_cast<float>(d.hot_pixel_std[b]), &u, &hot[k]);
     } else if (NOISE == V2V_NOISE_EXPLICIT) {
       if (d.hot_noise) hot[k] = d.hot_noise[clip_pix + k];
@@ -169,11 +169,11 @@ __global__ void __launch_bounds__(kThreads) esim_kernel(const EsimArgs a) {
         } else if (NOISE == V2V_NOISE_PHILOX) {
           if (P == 4) {
             float ev[4], od[4];
-            philox_noise8(static_cast<uint64_t>(pix0) >> 2, static_cast<uint32_t>(i - 1) >> 1, nkey, nc2, trig_s, ev, od);
+            philox_noise8(static_cast<uint64_t>(pix0) >> 2, static_cast<uint32_t>(i - 1) >> 1, nkey, a.rk, nc2, trig_s, ev, od);
 #pragma unroll
             for (int k = 0; k < P; ++k) bn[k] = static_cast<double>(((i - 1) & 1) ? od[k % 4] : ev[k % 4]);
           } else {
-            bn[0] = static_cast<double>(philox_noise1(static_cast<uint64_t>(pix0), static_cast<uint32_t>(i - 1), nkey, nc2, trig_s));
+            bn[0] = static_cast<double>(philox_noise1(static_cast<uint64_t>(pix0), static_cast<uint32_t>(i - 1), nkey, a.rk, nc2, trig_s));
           }
         }
 
@@ -307,17 +307,17 @@ __global__ void esim_philox_fields_kernel(const EsimArgs a, double* u0, double* 
   const int b = blockIdx.y;
   const int64_t pix = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (pix >= a.HW) return;
-  const NoiseKey nkey = make_noise_key(d.seed, d.clip_index_base + static_cast<uint64_t>(b));
+  const NoiseKey nkey = make_noise_key(d.clip_index_base + static_cast<uint64_t>(b));
   const int64_t o = static_cast<int64_t>(b) * a.HW + pix;
   double u, h;
-  philox_init_pixel(static_cast<uint64_t>(pix), nkey, d.hot_pixel_fraction[b], static_cast<float>(d.hot_pixel_std[b]), &u, &h);
+  philox_init_pixel(static_cast<uint64_t>(pix), nkey, a.rk, d.hot_pixel_fraction[b], static_cast<float>(d.hot_pixel_std[b]), &u, &h);
   if (u0) u0[o] = u;
   if (hot) hot[o] = h;
   if (bn) {
     const float nc2 = noise_c2(static_cast<float>(d.base_noise_std[b]));
     for (int i = 0; i < d.N - 1; ++i) {
       bn[(static_cast<int64_t>(b) * (d.N - 1) + i) * a.HW + pix] =
-          static_cast<double>(philox_noise1(static_cast<uint64_t>(pix), static_cast<uint32_t>(i), nkey, nc2, trig_s));
+          static_cast<double>(philox_noise1(static_cast<uint64_t>(pix), static_cast<uint32_t>(i), nkey, a.rk, nc2, trig_s));
     }
   }
 }
@@ -360,6 +360,7 @@ extern "C" int v2v_esim_frames_to_voxel(const v2v_esim_desc* desc, void* stream)
   V2V_REQUIRE(a.row_stride >= d.W && a.plane_stride >= a.row_stride * (d.H - 1) + d.W, V2V_ERR_SHAPE,
               "voxel strides too small");
   a.padded = a.row_stride != d.W;
+  Philox::round_keys(d.seed, a.rk);
   a.Tf = d.frame_out_mode == 2 ? a.T + 1 : a.T;
   if (!d.frame_out) a.d.frame_out_mode = 0;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
@@ -391,6 +392,7 @@ extern "C" int v2v_esim_philox_fields(const v2v_esim_desc* desc, double* u0, dou
   EsimArgs a;
   a.d = d;
   a.HW = static_cast<int64_t>(d.H) * d.W;
+  Philox::round_keys(d.seed, a.rk);
   if (d.B == 0 || a.HW == 0) return V2V_OK;
   dim3 grid(static_cast<unsigned int>((a.HW + 255) / 256), static_cast<unsigned int>(d.B));
   esim_philox_fields_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(a, u0, hot_noise, base_noise);

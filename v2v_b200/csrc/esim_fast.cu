@@ -80,7 +80,7 @@ __global__ void __launch_bounds__(kEsimThreads, MINB) esim_fast_kernel(const Esi
   if (pix0 < HW) {          // (no early return: every thread reaches the stats barrier at the end)
   const int N = d.N;
   const int64_t clip_pix = static_cast<int64_t>(b) * HW + pix0;
-  const NoiseKey nkey = make_noise_key(d.seed, d.clip_index_base + static_cast<uint64_t>(b));
+  const NoiseKey nkey = make_noise_key(d.clip_index_base + static_cast<uint64_t>(b));
   const uint64_t g4 = static_cast<uint64_t>(pix0) >> 2;
 
   const double pos = d.pos_thres[b], neg = d.neg_thres[b];
@@ -112,7 +112,7 @@ __global__ void __launch_bounds__(kEsimThreads, MINB) esim_fast_kernel(const Esi
     double u = -1.0;
     if (NOISE == V2V_NOISE_PHILOX) {
       double hk;
-      philox_init_pixel(static_cast<uint64_t>(pix0 + k), nkey, d.hot_pixel_fraction[b], static_cast<float>(d.hot_pixel_std[b]), &u, &hk);
+      philox_init_pixel(static_cast<uint64_t>(pix0 + k), nkey, a.rk, d.hot_pixel_fraction[b], static_cast<float>(d.hot_pixel_std[b]), &u, &hk);
       hotf[k] = static_cast<float>(hk);     // exact: hk was produced from a float
     }
     if (d.u0) u = d.u0[clip_pix + k];
@@ -137,9 +137,11 @@ __global__ void __launch_bounds__(kEsimThreads, MINB) esim_fast_kernel(const Esi
   unsigned int npos = 0, nneg = 0;      // multi-threshold events (exact integers)
   float net = 0.f, tot = 0.f;           // single-threshold events: net = #pos - #neg, tot = #pos + #neg
 
-  bool any_hot = false;
+  bool lane_hot = false;
 #pragma unroll
-  for (int k = 0; k < 4; ++k) any_hot = any_hot || hotf[k] != 0.f;
+  for (int k = 0; k < 4; ++k) lane_hot = lane_hot || hotf[k] != 0.f;
+  // warp-uniform: a real branch that 94 % of the warps never take (hot_pixel_fraction <= 1e-3)
+  const bool any_hot = __any_sync(__activemask(), lane_hot);
 
   auto step = [&](const uint32_t w, const float (&bnf)[4]) {
     float o[4];
@@ -208,10 +210,10 @@ __global__ void __launch_bounds__(kEsimThreads, MINB) esim_fast_kernel(const Esi
     if (NOISE == V2V_NOISE_PHILOX) {
       // intervals i-1 .. i+2 = 4t .. 4t+3: two Philox calls, 8 normals each
       float e0[4], o0[4], e1[4], o1[4];
-      philox_noise8(g4, static_cast<uint32_t>(2 * t), nkey, nc2, trig_s, e0, o0);
+      philox_noise8(g4, static_cast<uint32_t>(2 * t), nkey, a.rk, nc2, trig_s, e0, o0);
       step(cur[0], e0);
       step(cur[1], o0);
-      philox_noise8(g4, static_cast<uint32_t>(2 * t + 1), nkey, nc2, trig_s, e1, o1);
+      philox_noise8(g4, static_cast<uint32_t>(2 * t + 1), nkey, a.rk, nc2, trig_s, e1, o1);
       step(cur[2], e1);
       step(cur[3], o1);
     } else {
@@ -226,7 +228,7 @@ __global__ void __launch_bounds__(kEsimThreads, MINB) esim_fast_kernel(const Esi
     float bn1[4] = {0.f, 0.f, 0.f, 0.f};
     if (NOISE == V2V_NOISE_PHILOX) {
       float ev[4], od[4];
-      philox_noise8(g4, static_cast<uint32_t>(i - 1) >> 1, nkey, nc2, trig_s, ev, od);
+      philox_noise8(g4, static_cast<uint32_t>(i - 1) >> 1, nkey, a.rk, nc2, trig_s, ev, od);
 #pragma unroll
       for (int k = 0; k < 4; ++k) bn1[k] = ((i - 1) & 1) ? od[k] : ev[k];
     }

@@ -41,7 +41,9 @@ class HostPipeline:
     def run(self, host_frames: torch.Tensor, params: Sequence[dict], host_out: torch.Tensor,
             clip_index_base: int = 0, stats: Optional[torch.Tensor] = None):
         """host_frames: pinned uint8 [B,N,H,W]; host_out: pinned float32 [B,T,bins,H,W] (filled on return
-        of ``torch.cuda.synchronize`` / ``self.s_out.synchronize()``).  Returns the per-clip stats tensor."""
+        of ``torch.cuda.synchronize`` / ``self.s_out.synchronize()``), or None to keep the voxels on the
+        device (read them from ``self.device_voxels`` chunk by chunk via ``on_chunk``).  Returns the
+        per-clip stats tensor."""
         B, n, h, w = host_frames.shape
         self._alloc(n, h, w)
         bins, fpb = self.vz.num_bins, self.vz.frames_per_bin
@@ -74,7 +76,8 @@ class HostPipeline:
                 ev_k.record(self.s_k)
             with torch.cuda.stream(self.s_out):
                 self.s_out.wait_event(ev_k)
-                host_out[b0:b1].copy_(slot["fout"][:nb], non_blocking=True)
+                if host_out is not None:
+                    host_out[b0:b1].copy_(slot["fout"][:nb], non_blocking=True)
                 slot["done"] = torch.cuda.Event()
                 slot["done"].record(self.s_out)
         cur.wait_stream(self.s_out)
