@@ -32,6 +32,7 @@ void count_launch(int n = 1);
   } while (0)
 
 static inline bool aligned(const void* p, size_t a) { return (reinterpret_cast<uintptr_t>(p) % a) == 0; }
+__device__ __forceinline__ bool aligned_dev(const void* p, size_t a) { return (reinterpret_cast<uintptr_t>(p) % a) == 0; }
 
 // ---- streaming loads / stores ----------------------------------------------
 // Inputs are read exactly once and outputs written exactly once: keep them out

@@ -27,52 +27,72 @@ struct V2eArgs {
   float leak_hz_f32;   // leak_rate_hz as the float32 it becomes in `leak_rate_hz*noise_rate_array`
 };
 
-__device__ __forceinline__ double count_floor(double a, double thr, double rthr) {
-  // np.floor_divide(max(diff,0), thr) for a >= 0, thr > 0
-  if (a < thr) return 0.0;
+__device__ __forceinline__ double count_floor(double a, double thr) {
+  // np.floor_divide(max(diff,0), thr) for a >= thr > 0 (the caller filters a < thr); the reciprocal is only
+  // needed on the rare multi-threshold path
   if (a < __dadd_rn(thr, thr)) return 1.0;
-  return floor_div_exact(a, thr, rthr);
+  return floor_div_exact(a, thr, __drcp_rn(thr));
 }
 
-__device__ __forceinline__ int poisson_small(double lam, double u) {
-  // inversion; lam is a fraction of an event per frame in every shipped preset
-  if (!(lam > 0.0)) return 0;
-  double p = exp(-lam), cdf = p;
+// Poisson(lam) by inversion from one uniform; lam is a fraction of an event per frame in every shipped preset,
+// so the first comparison (k = 0) settles ~90 % of the draws.  float32: statistical mode only (the audit hook
+// dumps exactly what this function returns).
+__device__ __forceinline__ int poisson_small(float lam, float u) {
+  if (!(lam > 0.f)) return 0;
+  float p = __expf(-lam), cdf = p;
+  if (u < cdf) return 0;
   int k = 0;
-  while (u > cdf && k < 64) {
+  while (u >= cdf && k < 64) {
     ++k;
-    p *= lam / k;
+    p *= lam / static_cast<float>(k);
     cdf += p;
   }
   return k;
 }
 
-
-// Per pixel / interval Philox draws of the v2e model: leak jitter normal and the two Poisson uniforms.
-__device__ __forceinline__ void v2e_philox_draw(uint64_t px, uint32_t interval, uint64_t clip_id, uint2 key,
-                                                float* leak_z, double* u_pos, double* u_neg) {
-  const uint4 r = Philox::run(make_uint4(static_cast<uint32_t>(px), interval, static_cast<uint32_t>(clip_id),
-                                         0x40000000u | (static_cast<uint32_t>(px >> 32) & 0x3fffu) << 16 |
-                                             static_cast<uint32_t>((clip_id >> 32) & 0xffffu)),
-                              key);
-  *leak_z = box_muller(r.x, r.y).x;
-  *u_pos = static_cast<double>(r.z) * (1.0 / 4294967296.0);
-  *u_neg = static_cast<double>(r.w) * (1.0 / 4294967296.0);
-}
-
-__device__ __forceinline__ double v2e_shot_lambda(uint32_t v, double pre_prob, double scale) {
-  const double inten = __ddiv_rn(__dadd_rn(static_cast<double>(v), 20.0), 275.0);     // :190
-  const double fac = __dsub_rn(1.0, __dmul_rn(0.75, inten));                          // :90
-  return fac * pre_prob * scale;                                                      // :91-99
+// Philox draws of the v2e model for one aligned group of 4 pixels and one interval:
+//   call A (tag 1): word k -> pixel k: low 16 bits = shot-noise uniform ON, high 16 bits = OFF  (bin centres)
+//   call B (tag 3): two Box-Muller pairs -> leak jitter normals of pixels 0..3
+__device__ __forceinline__ void v2e_group_draw(uint64_t g4, uint32_t interval, uint64_t clip_id, uint2 key, bool leak, bool shot,
+                                               float (&lz)[4], float (&up)[4], float (&un)[4]) {
+  const uint32_t hi = (static_cast<uint32_t>(g4 >> 32) & 0x3fffu) << 16 | static_cast<uint32_t>((clip_id >> 32) & 0xffffu);
+  if (shot) {
+    const uint4 r = Philox::run(make_uint4(static_cast<uint32_t>(g4), interval, static_cast<uint32_t>(clip_id), 0x40000000u | hi), key);
+    const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      up[k] = (static_cast<float>(w[k] & 0xffffu) + 0.5f) * (1.0f / 65536.0f);
+      un[k] = (static_cast<float>(w[k] >> 16) + 0.5f) * (1.0f / 65536.0f);
+    }
+  }
+  if (leak) {
+    const uint4 r = Philox::run(make_uint4(static_cast<uint32_t>(g4), interval, static_cast<uint32_t>(clip_id), 0xC0000000u | hi), key);
+    const float2 p0 = box_muller(r.x, r.y), p1 = box_muller(r.z, r.w);
+    lz[0] = p0.x; lz[1] = p0.y; lz[2] = p1.x; lz[3] = p1.y;
+  }
 }
 
 __device__ __forceinline__ uint32_t load_pix4(const uint8_t* p) { return ld_stream_u32(p); }
 
-template <int P, bool F32STATE>
+struct V2eLuts {
+  float logv[256];     // float32(log(v/255+0.01)), from the host          (:120-137)
+  double inten[256];   // (v+20)/275                                       (:190)
+  float facf[256];     // 1 - 0.75*inten as float (shot-noise rate factor) (:90)
+};
+
+// shot-noise Poisson rate of one pixel (float32, statistical mode): fac(v) * nominal/thres * per-frame scale (:90-99)
+__device__ __forceinline__ float v2e_shot_lambda(float facf, float pre_prob, float scale) { return facf * pre_prob * scale; }
+
+template <int P, bool F32STATE, bool CUTOFF, bool LEAK, bool SHOT>
 __global__ void __launch_bounds__(kV2eThreads) v2e_kernel(const V2eArgs a) {
-  __shared__ float lut_s[256];
+  __shared__ V2eLuts L;
   const v2v_v2e_desc& d = a.d;
-  for (int i = threadIdx.x; i < 256; i += kV2eThreads) lut_s[i] = d.lut[i];
+  for (int i = threadIdx.x; i < 256; i += kV2eThreads) {
+    L.logv[i] = d.lut[i];
+    const double it = __ddiv_rn(__dadd_rn(static_cast<double>(i), 20.0), 275.0);
+    L.inten[i] = it;
+    L.facf[i] = static_cast<float>(__dsub_rn(1.0, __dmul_rn(0.75, it)));
+  }
   __syncthreads();
   const int b = blockIdx.y;
   const int64_t pix0 = (static_cast<int64_t>(blockIdx.x) * kV2eThreads + threadIdx.x) * P;
@@ -80,22 +100,21 @@ __global__ void __launch_bounds__(kV2eThreads) v2e_kernel(const V2eArgs a) {
   if (pix0 >= HW) return;
   const int N = d.N;
   const int64_t mp = static_cast<int64_t>(b) * HW + pix0;
-  const bool cutoff = d.cutoff_hz > 0.0, leak = d.leak_rate_hz > 0.0, shot = d.shot_noise_rate_hz > 0.0;
-  const bool need_inten = cutoff || shot;
   const uint64_t clip_id = d.clip_index_base + static_cast<uint64_t>(b);
   const uint2 key = make_uint2(static_cast<uint32_t>(d.seed), static_cast<uint32_t>(d.seed >> 32));
+  const bool philox = d.noise_mode == V2V_NOISE_PHILOX, explicit_noise = d.noise_mode == V2V_NOISE_EXPLICIT;
 
-  double pth[P], nth[P], rp[P], rn[P], lp[P], base[P], ppp[P], npp[P];
-  float nrate[P];
+  double pth[P], nth[P], lp[P], base[P];
+  float nrate[LEAK ? P : 1], ppf[SHOT ? P : 1], npf[SHOT ? P : 1];
 #pragma unroll
   for (int k = 0; k < P; ++k) {
     pth[k] = d.pos_thres[mp + k];
     nth[k] = d.neg_thres[mp + k];
-    rp[k] = __drcp_rn(pth[k]);
-    rn[k] = __drcp_rn(nth[k]);
-    nrate[k] = (leak && d.noise_rate) ? d.noise_rate[mp + k] : 1.0f;
-    ppp[k] = __ddiv_rn(d.pos_thres_nominal, pth[k]);     // :396-399
-    npp[k] = __ddiv_rn(d.neg_thres_nominal, nth[k]);
+    if (LEAK) nrate[LEAK ? k : 0] = d.noise_rate ? d.noise_rate[mp + k] : 1.0f;
+    if (SHOT) {                                                                    // :396-399
+      ppf[SHOT ? k : 0] = static_cast<float>(__ddiv_rn(d.pos_thres_nominal, pth[k]));
+      npf[SHOT ? k : 0] = static_cast<float>(__ddiv_rn(d.neg_thres_nominal, nth[k]));
+    }
   }
 
   const uint8_t* fr = d.frames + static_cast<int64_t>(b) * N * HW + pix0;
@@ -106,8 +125,8 @@ __global__ void __launch_bounds__(kV2eThreads) v2e_kernel(const V2eArgs a) {
     const uint32_t w0 = load(0);
 #pragma unroll
     for (int k = 0; k < P; ++k) {
-      const double l0 = static_cast<double>(lut_s[(w0 >> (8 * k)) & 0xffu]);
-      lp[k] = cutoff ? __dadd_rn(__dmul_rn(1.0, l0), __dmul_rn(0.0, l0)) : l0;
+      const double l0 = static_cast<double>(L.logv[(w0 >> (8 * k)) & 0xffu]);
+      lp[k] = CUTOFF ? __dadd_rn(__dmul_rn(1.0, l0), __dmul_rn(0.0, l0)) : l0;
       base[k] = lp[k];
     }
   }
@@ -131,24 +150,48 @@ __global__ void __launch_bounds__(kV2eThreads) v2e_kernel(const V2eArgs a) {
       if (i >= N) break;
       const uint32_t w = ring[u];
       if (i + kPF < N) ring[u] = load(i + kPF);
+      // per-interval quantities shared by all pixels
       const double t_k = __ddiv_rn(static_cast<double>(i), d.fps);     // :577
       const double dt = __dsub_rn(t_k, t_prev);                         // :442
       t_prev = t_k;
+      const double qdt = CUTOFF ? __ddiv_rn(dt, a.tau) : 0.0;           // :167
       const int64_t fo = (static_cast<int64_t>(b) * (N - 1) + (i - 1)) * HW + pix0;
+      float sps = 0.f, sns = 0.f;
+      if (SHOT && philox) {
+        const int64_t si = static_cast<int64_t>(b) * (N - 1) + (i - 1);
+        sps = static_cast<float>(d.shot_pos_scale[si]);
+        sns = static_cast<float>(d.shot_neg_scale[si]);
+      }
 
       // per-interval random fields
       double lr[P];
       int sp[P], sn[P];
 #pragma unroll
       for (int k = 0; k < P; ++k) { lr[k] = 0.0; sp[k] = 0; sn[k] = 0; }
-      if (d.noise_mode == V2V_NOISE_EXPLICIT) {
-        if (leak && d.leak_randn) {
+      if (explicit_noise) {
+        if (LEAK && d.leak_randn) {
 #pragma unroll
           for (int k = 0; k < P; ++k) lr[k] = d.leak_randn[fo + k];
         }
-        if (shot && d.pos_shot && d.neg_shot) {
+        if (SHOT && d.pos_shot && d.neg_shot) {
 #pragma unroll
           for (int k = 0; k < P; ++k) { sp[k] = d.pos_shot[fo + k]; sn[k] = d.neg_shot[fo + k]; }
+        }
+      } else if (philox && (LEAK || SHOT)) {
+        float lz[4] = {0.f, 0.f, 0.f, 0.f}, up[4] = {1.f, 1.f, 1.f, 1.f}, un[4] = {1.f, 1.f, 1.f, 1.f};
+        v2e_group_draw(static_cast<uint64_t>(pix0) >> 2, static_cast<uint32_t>(i - 1), clip_id, key, LEAK, SHOT, lz, up, un);
+#pragma unroll
+        for (int k = 0; k < P; ++k) {
+          const int j = P == 4 ? k : static_cast<int>(pix0 & 3);
+          const float lzj = j == 0 ? lz[0] : j == 1 ? lz[1] : j == 2 ? lz[2] : lz[3];
+          const float upj = j == 0 ? up[0] : j == 1 ? up[1] : j == 2 ? up[2] : up[3];
+          const float unj = j == 0 ? un[0] : j == 1 ? un[1] : j == 2 ? un[2] : un[3];
+          if (LEAK) lr[k] = static_cast<double>(lzj);
+          if (SHOT) {
+            const float fac = L.facf[(w >> (8 * k)) & 0xffu];
+            sp[k] = poisson_small(v2e_shot_lambda(fac, ppf[SHOT ? k : 0], sps), upj);
+            sn[k] = poisson_small(v2e_shot_lambda(fac, npf[SHOT ? k : 0], sns), unj);
+          }
         }
       }
 
@@ -156,29 +199,16 @@ __global__ void __launch_bounds__(kV2eThreads) v2e_kernel(const V2eArgs a) {
 #pragma unroll
       for (int k = 0; k < P; ++k) {
         const uint32_t v = (w >> (8 * k)) & 0xffu;
-        const float lognew = lut_s[v];                                              // :447
-        double inten = 0.0;
-        if (need_inten) inten = __ddiv_rn(__dadd_rn(static_cast<double>(v), 20.0), 275.0);   // :190
-        if (cutoff) {                                                               // :157-173
-          double eps = __dmul_rn(inten, __ddiv_rn(dt, a.tau));
+        const float lognew = L.logv[v];                                             // :447
+        if (CUTOFF) {                                                               // :157-173
+          double eps = __dmul_rn(L.inten[v], qdt);
           eps = fmin(eps, 1.0);
           lp[k] = __dadd_rn(__dmul_rn(__dsub_rn(1.0, eps), lp[k]), __dmul_rn(eps, static_cast<double>(lognew)));
         } else {
           lp[k] = static_cast<double>(lognew);
         }
-        if (d.noise_mode == V2V_NOISE_PHILOX && (leak || shot)) {
-          float lz;
-          double up, un;
-          v2e_philox_draw(static_cast<uint64_t>(pix0 + k), static_cast<uint32_t>(i - 1), clip_id, key, &lz, &up, &un);
-          if (leak) lr[k] = static_cast<double>(lz);
-          if (shot) {
-            const int64_t si = static_cast<int64_t>(b) * (N - 1) + (i - 1);
-            sp[k] = poisson_small(v2e_shot_lambda(v, ppp[k], d.shot_pos_scale[si]), up);
-            sn[k] = poisson_small(v2e_shot_lambda(v, npp[k], d.shot_neg_scale[si]), un);
-          }
-        }
-        if (leak) {                                                                 // :192-211
-          const float r32 = __fmul_rn(a.leak_hz_f32, nrate[k]);
+        if (LEAK) {                                                                 // :192-211
+          const float r32 = __fmul_rn(a.leak_hz_f32, nrate[LEAK ? k : 0]);
           const double rate = __dmul_rn(static_cast<double>(r32), __dsub_rn(1.0, __dmul_rn(d.leak_jitter_fraction, lr[k])));
           base[k] = __dsub_rn(base[k], __dmul_rn(__dmul_rn(dt, rate), pth[k]));
         }
@@ -186,19 +216,23 @@ __global__ void __launch_bounds__(kV2eThreads) v2e_kernel(const V2eArgs a) {
         if (F32STATE) diff = static_cast<double>(__fsub_rn(static_cast<float>(lp[k]), static_cast<float>(base[k])));
         else diff = __dsub_rn(lp[k], base[k]);
         double pe = 0.0, ne = 0.0;                                                  // :55-60
-        if (diff > 0.0) pe = count_floor(diff, pth[k], rp[k]);
-        else if (diff < 0.0) ne = count_floor(-diff, nth[k], rn[k]);
-        pe += static_cast<double>(sp[k]);                                           // :530-531
-        ne += static_cast<double>(sn[k]);
-        // :547-548 — in place: the float64 sum is cast back to the state dtype after each line
-        double nb = __dadd_rn(base[k], __dmul_rn(pe, pth[k]));
-        if (F32STATE) nb = static_cast<double>(__double2float_rn(nb));
-        nb = __dsub_rn(nb, __dmul_rn(ne, nth[k]));
-        if (F32STATE) nb = static_cast<double>(__double2float_rn(nb));
-        base[k] = nb;
-        npos += static_cast<unsigned int>(pe);
-        nneg += static_cast<unsigned int>(ne);
-        acc[k] += static_cast<int>(pe) - static_cast<int>(ne);                      // :579-580
+        if (diff >= pth[k]) pe = count_floor(diff, pth[k]);
+        else if (-diff >= nth[k]) ne = count_floor(-diff, nth[k]);
+        if (SHOT) {                                                                 // :530-531
+          pe += static_cast<double>(sp[k]);
+          ne += static_cast<double>(sn[k]);
+        }
+        if (pe != 0.0 || ne != 0.0) {
+          // :547-548 — in place: the float64 sum is cast back to the state dtype after each line
+          double nb = __dadd_rn(base[k], __dmul_rn(pe, pth[k]));
+          if (F32STATE) nb = static_cast<double>(__double2float_rn(nb));
+          nb = __dsub_rn(nb, __dmul_rn(ne, nth[k]));
+          if (F32STATE) nb = static_cast<double>(__double2float_rn(nb));
+          base[k] = nb;
+          npos += static_cast<unsigned int>(pe);
+          nneg += static_cast<unsigned int>(ne);
+          acc[k] += static_cast<int>(pe) - static_cast<int>(ne);                    // :579-580
+        }
         outv[k] = static_cast<float>(acc[k]);
       }
       if (++sub == d.frames_per_bin) {
@@ -219,38 +253,67 @@ __global__ void __launch_bounds__(kV2eThreads) v2e_kernel(const V2eArgs a) {
 }
 
 // Full-frame means of generate_shot_noise (:90-96) -> per-frame Poisson scales.
-__global__ void __launch_bounds__(256) v2e_shot_scale_kernel(const V2eArgs a, double* pos_scale, double* neg_scale) {
+// One pass over the clip: a thread keeps nominal/thres of its 4 pixels in registers, walks the frames and adds
+// fac(v)*pre_prob to per-frame sums.  The sums are accumulated as 2^-36 fixed point in int64 (exact and order
+// independent, so the scales - and with them the Poisson draws - are run-to-run deterministic); the accumulators
+// live in the output arrays, which a second tiny kernel converts in place to (rate/2*dt) / mean.
+constexpr double kShotFix = 68719476736.0;   // 2^36
+
+__global__ void __launch_bounds__(256) v2e_shot_accum_kernel(const V2eArgs a, long long* pos_acc, long long* neg_acc) {
+  __shared__ double fac_s[256];
   const v2v_v2e_desc& d = a.d;
-  const int k = blockIdx.x + 1, b = blockIdx.y;
-  const uint8_t* fr = d.frames + (static_cast<int64_t>(b) * d.N + k) * a.HW;
-  const double* pt = d.pos_thres + static_cast<int64_t>(b) * a.HW;
-  const double* nt = d.neg_thres + static_cast<int64_t>(b) * a.HW;
-  double sp = 0.0, sn = 0.0;
-  for (int64_t i = threadIdx.x; i < a.HW; i += 256) {
-    const double inten = (static_cast<double>(fr[i]) + 20.0) / 275.0;
-    const double fac = 1.0 - 0.75 * inten;
-    sp += fac * (d.pos_thres_nominal / pt[i]);
-    sn += fac * (d.neg_thres_nominal / nt[i]);
-  }
-  __shared__ double red[2][8];
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    sp += __shfl_xor_sync(0xffffffffu, sp, o);
-    sn += __shfl_xor_sync(0xffffffffu, sn, o);
-  }
-  if ((threadIdx.x & 31) == 0) { red[0][threadIdx.x >> 5] = sp; red[1][threadIdx.x >> 5] = sn; }
+  for (int i = threadIdx.x; i < 256; i += 256) fac_s[i] = 1.0 - 0.75 * ((static_cast<double>(i) + 20.0) / 275.0);
   __syncthreads();
-  if (threadIdx.x == 0) {
-    double tp = 0.0, tn = 0.0;
-    for (int i = 0; i < 8; ++i) { tp += red[0][i]; tn += red[1][i]; }
-    const double dt = static_cast<double>(k) / d.fps - static_cast<double>(k - 1) / d.fps;
-    const double sf = (d.shot_noise_rate_hz / 2) * dt;
-    const int64_t o = static_cast<int64_t>(b) * (d.N - 1) + (k - 1);
-    pos_scale[o] = sf / (tp / static_cast<double>(a.HW));
-    neg_scale[o] = sf / (tn / static_cast<double>(a.HW));
+  const int b = blockIdx.y;
+  const int64_t pix0 = (static_cast<int64_t>(blockIdx.x) * 256 + threadIdx.x) * 4;
+  double pp[4], np_[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const bool ok = pix0 + k < a.HW;
+    pp[k] = ok ? d.pos_thres_nominal / d.pos_thres[static_cast<int64_t>(b) * a.HW + pix0 + k] : 0.0;
+    np_[k] = ok ? d.neg_thres_nominal / d.neg_thres[static_cast<int64_t>(b) * a.HW + pix0 + k] : 0.0;
+  }
+  const bool vec = (a.HW % 4 == 0) && aligned_dev(d.frames, 4);
+  for (int f = 1; f < d.N; ++f) {
+    const uint8_t* fr = d.frames + (static_cast<int64_t>(b) * d.N + f) * a.HW + pix0;
+    uint32_t w = 0;
+    if (pix0 < a.HW) {
+      if (vec) w = ld_stream_u32(fr);
+      else {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) if (pix0 + k < a.HW) w |= static_cast<uint32_t>(fr[k]) << (8 * k);
+      }
+    }
+    long long sp = 0, sn = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const double fc = fac_s[(w >> (8 * k)) & 0xffu];
+      sp += __double2ll_rn(fc * pp[k] * kShotFix);
+      sn += __double2ll_rn(fc * np_[k] * kShotFix);
+    }
+    sp = warp_sum(sp);
+    sn = warp_sum(sn);
+    if ((threadIdx.x & 31) == 0) {
+      const int64_t o = static_cast<int64_t>(b) * (d.N - 1) + (f - 1);
+      atomicAdd(reinterpret_cast<unsigned long long*>(pos_acc + o), static_cast<unsigned long long>(sp));
+      atomicAdd(reinterpret_cast<unsigned long long*>(neg_acc + o), static_cast<unsigned long long>(sn));
+    }
   }
 }
 
+__global__ void v2e_shot_finalize_kernel(const V2eArgs a, double* pos_scale, double* neg_scale) {
+  const v2v_v2e_desc& d = a.d;
+  const int64_t n = static_cast<int64_t>(d.B) * (d.N - 1);
+  const int64_t o = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (o >= n) return;
+  const int k = static_cast<int>(o % (d.N - 1)) + 1;
+  const double dt = static_cast<double>(k) / d.fps - static_cast<double>(k - 1) / d.fps;
+  const double sf = (d.shot_noise_rate_hz / 2) * dt;
+  const double tp = static_cast<double>(reinterpret_cast<long long*>(pos_scale)[o]) / kShotFix;
+  const double tn = static_cast<double>(reinterpret_cast<long long*>(neg_scale)[o]) / kShotFix;
+  pos_scale[o] = sf / (tp / static_cast<double>(a.HW));
+  neg_scale[o] = sf / (tn / static_cast<double>(a.HW));
+}
 
 // Audit hook: the random fields a PHILOX run draws, for explicit replay / oracle checks.
 __global__ void v2e_philox_fields_kernel(const V2eArgs a, double* leak_randn, int32_t* pos_shot, int32_t* neg_shot) {
@@ -260,20 +323,23 @@ __global__ void v2e_philox_fields_kernel(const V2eArgs a, double* leak_randn, in
   if (pix >= a.HW) return;
   const uint64_t clip_id = d.clip_index_base + static_cast<uint64_t>(b);
   const uint2 key = make_uint2(static_cast<uint32_t>(d.seed), static_cast<uint32_t>(d.seed >> 32));
-  const bool shot = d.shot_noise_rate_hz > 0.0;
+  const bool shot = d.shot_noise_rate_hz > 0.0, leak = d.leak_rate_hz > 0.0;
   const int64_t mp = static_cast<int64_t>(b) * a.HW + pix;
-  const double ppp = __ddiv_rn(d.pos_thres_nominal, d.pos_thres[mp]), npp = __ddiv_rn(d.neg_thres_nominal, d.neg_thres[mp]);
+  const float ppf = static_cast<float>(__ddiv_rn(d.pos_thres_nominal, d.pos_thres[mp]));
+  const float npf = static_cast<float>(__ddiv_rn(d.neg_thres_nominal, d.neg_thres[mp]));
+  const int j = static_cast<int>(pix & 3);
   for (int i = 1; i < d.N; ++i) {
-    float lz;
-    double up, un;
-    v2e_philox_draw(static_cast<uint64_t>(pix), static_cast<uint32_t>(i - 1), clip_id, key, &lz, &up, &un);
+    float lz[4] = {0.f, 0.f, 0.f, 0.f}, up[4] = {1.f, 1.f, 1.f, 1.f}, un[4] = {1.f, 1.f, 1.f, 1.f};
+    v2e_group_draw(static_cast<uint64_t>(pix) >> 2, static_cast<uint32_t>(i - 1), clip_id, key, leak, shot, lz, up, un);
     const int64_t o = (static_cast<int64_t>(b) * (d.N - 1) + (i - 1)) * a.HW + pix;
-    if (leak_randn) leak_randn[o] = static_cast<double>(lz);
+    if (leak_randn) leak_randn[o] = static_cast<double>(lz[j]);
     if (shot && pos_shot && neg_shot) {
       const uint32_t v = d.frames[(static_cast<int64_t>(b) * d.N + i) * a.HW + pix];
+      const double it = __ddiv_rn(__dadd_rn(static_cast<double>(v), 20.0), 275.0);
+      const float fac = static_cast<float>(__dsub_rn(1.0, __dmul_rn(0.75, it)));
       const int64_t si = static_cast<int64_t>(b) * (d.N - 1) + (i - 1);
-      pos_shot[o] = poisson_small(v2e_shot_lambda(v, ppp, d.shot_pos_scale[si]), up);
-      neg_shot[o] = poisson_small(v2e_shot_lambda(v, npp, d.shot_neg_scale[si]), un);
+      pos_shot[o] = poisson_small(v2e_shot_lambda(fac, ppf, static_cast<float>(d.shot_pos_scale[si])), up[j]);
+      neg_shot[o] = poisson_small(v2e_shot_lambda(fac, npf, static_cast<float>(d.shot_neg_scale[si])), un[j]);
     }
   }
 }
@@ -316,13 +382,18 @@ extern "C" int v2v_v2e_frames_to_voxel(const v2v_v2e_desc* desc, void* stream) {
                     static_cast<int64_t>(d.B) * a.HW >= 148LL * 2048;
   const int P = vec4 ? 4 : 1;
   dim3 grid(static_cast<unsigned int>(((a.HW + P - 1) / P + kV2eThreads - 1) / kV2eThreads), static_cast<unsigned int>(d.B));
-  if (vec4) {
-    if (d.state_f32) v2e_kernel<4, true><<<grid, kV2eThreads, 0, s>>>(a);
-    else v2e_kernel<4, false><<<grid, kV2eThreads, 0, s>>>(a);
-  } else {
-    if (d.state_f32) v2e_kernel<1, true><<<grid, kV2eThreads, 0, s>>>(a);
-    else v2e_kernel<1, false><<<grid, kV2eThreads, 0, s>>>(a);
-  }
+  const bool cut = d.cutoff_hz > 0.0, lk = d.leak_rate_hz > 0.0, sh = d.shot_noise_rate_hz > 0.0 && d.noise_mode != V2V_NOISE_NONE;
+#define V2V_V2E(PP, F32, CU, LK, SH) v2e_kernel<PP, F32, CU, LK, SH><<<grid, kV2eThreads, 0, s>>>(a)
+#define V2V_V2E_P(PP)                                                                   \
+  do {                                                                                  \
+    if (d.state_f32) { if (sh) V2V_V2E(PP, true, false, false, true); else V2V_V2E(PP, true, false, false, false); } \
+    else if (cut && lk) { if (sh) V2V_V2E(PP, false, true, true, true); else V2V_V2E(PP, false, true, true, false); } \
+    else if (cut) { if (sh) V2V_V2E(PP, false, true, false, true); else V2V_V2E(PP, false, true, false, false); }     \
+    else { if (sh) V2V_V2E(PP, false, false, true, true); else V2V_V2E(PP, false, false, true, false); }              \
+  } while (0)
+  if (vec4) V2V_V2E_P(4); else V2V_V2E_P(1);
+#undef V2V_V2E_P
+#undef V2V_V2E
   count_launch();
   V2V_CUDA(cudaGetLastError());
   return V2V_OK;
@@ -337,9 +408,16 @@ extern "C" int v2v_v2e_shot_scales(const v2v_v2e_desc* desc, double* shot_pos_sc
   const v2v_v2e_desc& d = *desc;
   if (d.B == 0 || a.HW == 0 || d.N == 1) return V2V_OK;
   V2V_REQUIRE(d.frames && d.pos_thres && d.neg_thres, V2V_ERR_INVALID_ARG, "frames and threshold maps must be non-NULL");
-  dim3 grid(static_cast<unsigned int>(d.N - 1), static_cast<unsigned int>(d.B));
-  v2e_shot_scale_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(a, shot_pos_scale, shot_neg_scale);
-  count_launch();
+  V2V_REQUIRE(aligned(shot_pos_scale, 8) && aligned(shot_neg_scale, 8), V2V_ERR_ALIGNMENT, "misaligned scale arrays");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const size_t nbytes = static_cast<size_t>(d.B) * (d.N - 1) * sizeof(double);
+  V2V_CUDA(cudaMemsetAsync(shot_pos_scale, 0, nbytes, s));
+  V2V_CUDA(cudaMemsetAsync(shot_neg_scale, 0, nbytes, s));
+  dim3 grid(static_cast<unsigned int>((a.HW + 1023) / 1024), static_cast<unsigned int>(d.B));
+  v2e_shot_accum_kernel<<<grid, 256, 0, s>>>(a, reinterpret_cast<long long*>(shot_pos_scale), reinterpret_cast<long long*>(shot_neg_scale));
+  const int64_t n = static_cast<int64_t>(d.B) * (d.N - 1);
+  v2e_shot_finalize_kernel<<<static_cast<unsigned int>((n + 255) / 256), 256, 0, s>>>(a, shot_pos_scale, shot_neg_scale);
+  count_launch(2);
   V2V_CUDA(cudaGetLastError());
   return V2V_OK;
 }
