@@ -127,8 +127,8 @@ constexpr int kTrigEntries = 4096;
 
 __device__ __forceinline__ void fill_trig_table(float2* tab) {      // call with the whole CTA, then __syncthreads()
   for (int k = threadIdx.x; k < kTrigEntries; k += blockDim.x) {
-    float s, c;
-    sincospif(static_cast<float>(2 * k + 1) * (1.0f / kTrigEntries), &s, &c);
+    float s, c;      // SFU approximations (abs error ~1e-6): directions of statistical noise, cheap enough to refill per CTA
+    __sincosf(static_cast<float>(2 * k + 1) * (3.14159265358979323846f / kTrigEntries), &s, &c);
     tab[k] = make_float2(c, s);
   }
 }

@@ -280,6 +280,8 @@ class EventEmulator(object):
         self.hot_pixel_std = hot_pixel_std
         self.put_noise_external = put_noise_external
         self.seed = seed
+        if not (pos_thres > 0 and neg_thres > 0):
+            raise ValueError("pos_thres and neg_thres must be positive")
         self.rng = rng or default_rng_mode()
         if self.rng not in ("numpy", "philox"):
             raise ValueError("rng must be 'numpy' or 'philox'")
