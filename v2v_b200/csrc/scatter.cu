@@ -36,6 +36,8 @@ struct ScatterArgs {
   v2v_scatter_desc d;
   int rows_per_strip, num_strips;
   int packed16;        // h5 discrete: strips are sized for 2-byte cells
+  int num_splits;      // >1: each (window, bin, strip) is shared by this many CTAs, each scanning a slice of the bin's events
+                       //     into a private tile and adding it to the (pre-zeroed) output with global atomics
   int64_t* bounds;     // [Wn, bins+2]: first event with bin_floor >= k for k = -1 .. bins (from the pre-pass), or NULL
   struct WinConst* wcs; // [Wn] window constants from the pre-pass (valid when bounds != NULL)
 };
@@ -212,11 +214,14 @@ __global__ void __launch_bounds__(kScatterThreads, 2) scatter_kernel(const Scatt
   int* acc_lo = acc_i + R * W;                  // second word of the fixed-point pair (h5 interp only)
 
   // work item = (window, bin, strip of rows); items of one window are adjacent so its events stay in L2
-  const int64_t per_win = static_cast<int64_t>(B) * a.num_strips;
+  const int K = a.num_splits;
+  const int64_t per_win = static_cast<int64_t>(B) * a.num_strips * K;
   const int64_t items = static_cast<int64_t>(d.num_windows) * per_win;
   for (int64_t item = blockIdx.x; item < items; item += gridDim.x) {
     const int win = static_cast<int>(item / per_win);
-    const int rem = static_cast<int>(item - static_cast<int64_t>(win) * per_win);
+    int rem = static_cast<int>(item - static_cast<int64_t>(win) * per_win);
+    const int split = rem % K;
+    rem /= K;
     const int bin = rem / a.num_strips, strip = rem - bin * a.num_strips;
     const int r0 = strip * R;
     const int rows = min(R, H - r0);
@@ -240,12 +245,18 @@ __global__ void __launch_bounds__(kScatterThreads, 2) scatter_kernel(const Scatt
         }
         if (lane == 0) s_wc = wc;
         // events whose bin falls outside [0, B) are dropped: counted once per window
-        if (lane == 0 && strip == 0 && d.dropped) {
+        if (lane == 0 && strip == 0 && split == 0 && d.dropped) {
           long long nd = 0;
           if (bin == 0 && !kTwoTap) nd += lo - e0;                    // bin < 0 (unsorted / negative timestamps)
           if (bin == B - 1) nd += e1 - hi;                            // bin >= B
           if (nd) atomicAdd(reinterpret_cast<unsigned long long*>(d.dropped), static_cast<unsigned long long>(nd));
         }
+      }
+      if (K > 1) {                                   // this CTA's slice of the bin's events
+        const int64_t n = hi - lo, per = (n + K - 1) / K;
+        const int64_t slo = lo + split * per;
+        hi = min(hi, slo + per);
+        lo = min(slo, hi);
       }
       if (lane == 0) { s_range[0] = lo; s_range[1] = hi; }
     }
@@ -364,7 +375,17 @@ __global__ void __launch_bounds__(kScatterThreads, 2) scatter_kernel(const Scatt
         if (packed) return static_cast<float>(static_cast<int>((static_cast<unsigned int>(acc_i[i >> 1]) >> ((i & 1) * 16)) & 0xffffu) - 32768);
         return kTorch ? acc_f[i] : static_cast<float>(acc_i[i]);
       };
-      if (d.out_dtype == V2V_F64) {
+      if (K > 1) {                                   // partial tile: add the non-zero cells to the pre-zeroed output
+        if (hi > lo) {
+          for (int i = threadIdx.x; i < cells; i += kScatterThreads) {
+            const double v = value(i);
+            if (v != 0.0) {
+              if (d.out_dtype == V2V_F64) atomicAdd(static_cast<double*>(d.voxel) + out_base + i, v);
+              else atomicAdd(static_cast<float*>(d.voxel) + out_base + i, static_cast<float>(v));
+            }
+          }
+        }
+      } else if (d.out_dtype == V2V_F64) {
         double* o = static_cast<double*>(d.voxel) + out_base;
         for (int i = threadIdx.x; i < cells; i += kScatterThreads) o[i] = value(i);
       } else {
@@ -466,10 +487,23 @@ extern "C" int v2v_events_to_voxel(const v2v_scatter_desc* desc, void* stream) {
   a.rows_per_strip = (d.H + a.num_strips - 1) / a.num_strips;                 // balance the strips
   // (the 32-bit fallback of a packed strip uses two passes of ceil(R/2) rows: one extra row of slack)
   const size_t smem = (static_cast<size_t>(a.rows_per_strip + (a.packed16 ? 1 : 0)) * row_bytes + 31) / 16 * 16;
-  const int64_t items = static_cast<int64_t>(d.num_windows) * d.num_bins * a.num_strips;
+  int64_t items = static_cast<int64_t>(d.num_windows) * d.num_bins * a.num_strips;
   int dev = 0, sms = 148;
   V2V_CUDA(cudaGetDevice(&dev));
   V2V_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  // few, large windows (e.g. the offline cache builder: one window of millions of events) cannot fill the GPU with
+  // one CTA per (window, bin, strip): split every bin's event range over several CTAs
+  a.num_splits = 1;
+  const int64_t ev_per_item = d.num_events / (static_cast<int64_t>(d.num_windows) * d.num_bins > 0 ? static_cast<int64_t>(d.num_windows) * d.num_bins : 1);
+  if (items < 2LL * sms && ev_per_item > 16384) {
+    int64_t k = (4LL * sms + items - 1) / items;
+    const int64_t kmax = ev_per_item / 8192;
+    if (k > kmax) k = kmax;
+    if (k > 64) k = 64;
+    if (k > 1) a.num_splits = static_cast<int>(k);
+  }
+  if (const char* e = getenv("V2V_SCATTER_SPLITS")) a.num_splits = atoi(e) > 0 ? atoi(e) : 1;
+  items *= a.num_splits;
   const int grid = static_cast<int>(items < 4LL * sms ? items : 4LL * sms);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   a.bounds = nullptr;
@@ -480,6 +514,8 @@ extern "C" int v2v_events_to_voxel(const v2v_scatter_desc* desc, void* stream) {
     a.bounds = static_cast<int64_t*>(d.workspace);
     a.wcs = reinterpret_cast<WinConst*>(static_cast<char*>(d.workspace) + nb);
   }
+  if (a.num_splits > 1)
+    V2V_CUDA(cudaMemsetAsync(d.voxel, 0, static_cast<size_t>(d.num_windows) * d.num_bins * d.H * d.W * (d.out_dtype == V2V_F64 ? 8 : 4), s));
 #define V2V_LAUNCH(M)                                                                                      \
   do {                                                                                                     \
     if (a.bounds) {                                                                                        \
