@@ -36,6 +36,7 @@ struct ScatterArgs {
   v2v_scatter_desc d;
   int rows_per_strip, num_strips;
   int packed16;        // h5 discrete: strips are sized for 2-byte cells
+  int tile_bytes;      // bytes of the accumulator tile in dynamic shared memory (the two-tap hit list follows it)
   int num_splits;      // >1: each (window, bin, strip) is shared by this many CTAs, each scanning a slice of the bin's events
                        //     into a private tile and adding it to the (pre-zeroed) output with global atomics
   int64_t* bounds;     // [Wn, bins+2]: first event with bin_floor >= k for k = -1 .. bins (from the pre-pass), or NULL
@@ -200,6 +201,7 @@ __global__ void __launch_bounds__(kScatterThreads, 2) scatter_kernel(const Scatt
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ int64_t s_range[2];
   __shared__ WinConst s_wc;
+  __shared__ int s_hits;
   const v2v_scatter_desc& d = a.d;
   const int W = d.W, H = d.H, B = d.num_bins;
   const int R = a.rows_per_strip;
@@ -212,6 +214,8 @@ __global__ void __launch_bounds__(kScatterThreads, 2) scatter_kernel(const Scatt
   int* acc_i = reinterpret_cast<int*>(smem_raw);
   float* acc_f = reinterpret_cast<float*>(smem_raw);
   int* acc_lo = acc_i + R * W;                  // second word of the fixed-point pair (h5 interp only)
+  // two-tap modes: hit list of one scan trip ((event offset in the trip) << 16 | cell), behind the tile
+  int* hit_list = reinterpret_cast<int*>(smem_raw + a.tile_bytes);
 
   // work item = (window, bin, strip of rows); items of one window are adjacent so its events stay in L2
   const int K = a.num_splits;
@@ -289,6 +293,10 @@ __global__ void __launch_bounds__(kScatterThreads, 2) scatter_kernel(const Scatt
       long long yv[kU], xv[kU];
       float pv[kU];
       bool okv[kU];
+      if (kTwoTap) {
+        if (threadIdx.x == 0) s_hits = 0;
+        __syncthreads();
+      }
 #pragma unroll
       for (int u = 0; u < kU; ++u) {
         const int64_t e = eb + u * kScatterThreads + threadIdx.x;
@@ -296,7 +304,7 @@ __global__ void __launch_bounds__(kScatterThreads, 2) scatter_kernel(const Scatt
         bool ok = true;
         yv[u] = okv[u] ? load_int(d.ys, d.ys_dtype, e, &ok) : -1;
         xv[u] = okv[u] ? load_int(d.xs, d.xs_dtype, e, &ok) : -1;
-        pv[u] = okv[u] ? load_f32(d.ps, d.ps_dtype, e) : 0.f;
+        pv[u] = (okv[u] && !kTwoTap) ? load_f32(d.ps, d.ps_dtype, e) : 0.f;
         if (!ok) yv[u] = xv[u] = -1;
       }
 #pragma unroll
@@ -321,6 +329,12 @@ __global__ void __launch_bounds__(kScatterThreads, 2) scatter_kernel(const Scatt
           continue;
         }
         const int cell = static_cast<int>(ry) * W + static_cast<int>(x);
+        if (kTwoTap) {
+          // the weight needs double-precision division: do it densely in a second phase instead of in this
+          // sparsely active branch (only rows/H of the lanes get here)
+          hit_list[atomicAdd(&s_hits, 1)] = (static_cast<int>(e - eb) << 16) | cell;
+          continue;
+        }
         float pw;                                                                     // polarity -> weight
         {
           const float p = pv[u];
@@ -331,27 +345,43 @@ __global__ void __launch_bounds__(kScatterThreads, 2) scatter_kernel(const Scatt
         if (MODE == V2V_SCATTER_H5_DISCRETE) {                                        // testh5.py:73
           if (packed) atomicAdd(&acc_i[cell >> 1], static_cast<int>(pw) * ((cell & 1) ? 65536 : 1));
           else atomicAdd(&acc_i[cell], static_cast<int>(pw));
-        } else if (MODE == V2V_SCATTER_TORCH_DISCRETE) {
+        } else {
           atomicAdd(&acc_f[cell], pw);                                                // event_utils.py:505
-        } else if (MODE == V2V_SCATTER_H5_INTERP) {
-          double tn;
-          bin_floor<MODE>(d, wc, e, &tn);
-          const double wgt = fmax(0.0, __dsub_rn(1.0, fabs(__dsub_rn(tn, static_cast<double>(bin)))));   // testh5.py:79
-          const long long fx = __double2ll_rn(__dmul_rn(wgt * static_cast<double>(pw), 1073741824.0));
-          if (fx != 0) {
-            const int hiw = static_cast<int>(fx >> kLoBits);
-            const unsigned int low = static_cast<unsigned int>(fx & ((1 << kLoBits) - 1));
-            if (hiw) atomicAdd(&acc_i[cell], hiw);
-            if (low) atomicAdd(reinterpret_cast<unsigned int*>(&acc_lo[cell]), low);
+        }
+      }
+      if (kTwoTap) {
+        __syncthreads();
+        const int nh = s_hits;
+        for (int h = threadIdx.x; h < nh; h += kScatterThreads) {
+          const int ent = hit_list[h];
+          const int cell = ent & 0xffff;
+          const int64_t e = eb + (ent >> 16);
+          float pw;
+          {
+            const float p = load_f32(d.ps, d.ps_dtype, e);
+            if (d.polarity_mode == V2V_POL_POS_ONLY) pw = p > 0.f ? 1.f : 0.f;
+            else if (d.polarity_mode == V2V_POL_NEG_ONLY) pw = p <= 0.f ? 1.f : 0.f;
+            else pw = kH5 ? (2.f * p - 1.f) : p;
           }
-        } else {   // TORCH_BILINEAR
           double tnd;
           bin_floor<MODE>(d, wc, e, &tnd);
-          const float tn = static_cast<float>(tnd);
-          const float wgt = fmaxf(0.f, __fsub_rn(1.0f, fabsf(__fsub_rn(tn, static_cast<float>(bin)))));  // event_utils.py:494
-          const float v = __fmul_rn(pw, wgt);                                                            // :495
-          if (v != 0.f) atomicAdd(&acc_f[cell], v);
+          if (MODE == V2V_SCATTER_H5_INTERP) {
+            const double wgt = fmax(0.0, __dsub_rn(1.0, fabs(__dsub_rn(tnd, static_cast<double>(bin)))));   // testh5.py:79
+            const long long fx = __double2ll_rn(__dmul_rn(wgt * static_cast<double>(pw), 1073741824.0));
+            if (fx != 0) {
+              const int hiw = static_cast<int>(fx >> kLoBits);
+              const unsigned int low = static_cast<unsigned int>(fx & ((1 << kLoBits) - 1));
+              if (hiw) atomicAdd(&acc_i[cell], hiw);
+              if (low) atomicAdd(reinterpret_cast<unsigned int*>(&acc_lo[cell]), low);
+            }
+          } else {   // TORCH_BILINEAR
+            const float tn = static_cast<float>(tnd);
+            const float wgt = fmaxf(0.f, __fsub_rn(1.0f, fabsf(__fsub_rn(tn, static_cast<float>(bin)))));  // event_utils.py:494
+            const float v = __fmul_rn(pw, wgt);                                                            // :495
+            if (v != 0.f) atomicAdd(&acc_f[cell], v);
+          }
         }
+        __syncthreads();
       }
     }
     if (d.dropped && ndrop) atomicAdd(reinterpret_cast<unsigned long long*>(d.dropped), static_cast<unsigned long long>(ndrop));
@@ -480,13 +510,18 @@ extern "C" int v2v_events_to_voxel(const v2v_scatter_desc* desc, void* stream) {
   const int64_t row_bytes = static_cast<int64_t>(d.W) * cell_bytes;
   int budget = kSmemBudget;
   if (const char* e = getenv("V2V_SCATTER_SMEM_KB")) budget = atoi(e) * 1024;
+  const bool two_tap = d.mode == V2V_SCATTER_H5_INTERP || d.mode == V2V_SCATTER_TORCH_BILINEAR;
+  const int list_bytes = two_tap ? 8 * kScatterThreads * 4 : 0;        // one scan trip: 8 events per thread, 4 bytes each
+  budget -= list_bytes;
+  if (two_tap && budget > 65535 * cell_bytes) budget = 65535 * cell_bytes;   // hit-list entries hold 16-bit cell indices
   V2V_REQUIRE(row_bytes <= budget, V2V_ERR_UNSUPPORTED, "W=%d does not fit one shared-memory row tile", d.W);
   a.rows_per_strip = static_cast<int>(budget / row_bytes);
   if (a.rows_per_strip > d.H) a.rows_per_strip = d.H;
   a.num_strips = (d.H + a.rows_per_strip - 1) / a.rows_per_strip;
   a.rows_per_strip = (d.H + a.num_strips - 1) / a.num_strips;                 // balance the strips
   // (the 32-bit fallback of a packed strip uses two passes of ceil(R/2) rows: one extra row of slack)
-  const size_t smem = (static_cast<size_t>(a.rows_per_strip + (a.packed16 ? 1 : 0)) * row_bytes + 31) / 16 * 16;
+  a.tile_bytes = static_cast<int>((static_cast<size_t>(a.rows_per_strip + (a.packed16 ? 1 : 0)) * row_bytes + 31) / 16 * 16);
+  const size_t smem = static_cast<size_t>(a.tile_bytes) + list_bytes;
   int64_t items = static_cast<int64_t>(d.num_windows) * d.num_bins * a.num_strips;
   int dev = 0, sms = 148;
   V2V_CUDA(cudaGetDevice(&dev));
