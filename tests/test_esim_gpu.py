@@ -363,3 +363,26 @@ def test_host_pipeline_and_batch_api(cuda_device):
     # sharding invariance: clips simulated one by one with their global index give the same noise streams
     one = vz.batch_to_tensors(fr[3:4], params[3:4], seed=9, clip_index_base=43)
     assert torch.equal(one["events"][0], ref["events"][3])
+
+
+def test_full_size_clip_bit_exact_vs_c_oracle(cuda_device):
+    """BASELINE config 2 clip (121x480x640) in the production mode (Philox noise, fast kernel): every one of the
+    36.9 M pixel-intervals equals the C oracle fed with the dumped noise fields; potential and stats too."""
+    import v2v_b200 as v2v
+    import v2v_oracle_c as orcc
+    lut = orc.esim_log_lut()
+    n, h, w = 121, 480, 640
+    vid = synth_video("walk", n, h, w, 1234)
+    fr = torch.from_numpy(vid).to(cuda_device)
+    pos, neg, std, frac, hstd = 0.21, 0.29, 0.06, 0.0007, 8.0
+    o = v2v.frames_to_voxel(fr, pos, neg, num_bins=5, noise="philox", base_noise_std=std, hot_pixel_fraction=frac,
+                            hot_pixel_std=hstd, seed=5, clip_index_base=17, with_stats=True, return_potential=True)
+    u0, hot, bn = v2v.philox_fields(n, h, w, base_noise_std=std, hot_pixel_fraction=frac, hot_pixel_std=hstd, seed=5,
+                                    clip_index_base=17)
+    ref, pot = orcc.esim_video_to_voxel(vid, pos, neg, 1.0, u0[0].cpu().numpy(), hot[0].cpu().numpy(), bn[0].cpu().numpy(),
+                                        False, lut, return_state=True)
+    got = o.voxel[0].cpu().numpy().reshape(n - 1, h, w)
+    assert np.array_equal(got.astype(np.float64), ref)
+    assert np.array_equal(o.potential[0].cpu().numpy(), pot)
+    st = o.stats[0].cpu().numpy()
+    assert st[0] == int(np.maximum(ref, 0).sum()) and st[1] == int(np.maximum(-ref, 0).sum())

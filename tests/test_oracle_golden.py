@@ -136,3 +136,22 @@ def test_esim_properties():
     total = pot0 + lut[vid[-1]] - lut[vid[0]]
     assert np.allclose(pot + pe * pos - ne * neg, total, atol=1e-9)
     assert np.all((pot < pos) & (pot > -neg))
+
+
+# ---- the C restatement (oracle/v2v_oracle_c.c) is pinned to the same golden vectors ----
+
+@pytest.mark.parametrize("name", golden("esim").names("esim_"))
+def test_c_oracle_esim(name):
+    import v2v_oracle_c as orcc
+    c = golden("esim").case(name)
+    out = orcc.esim_video_to_voxel(c["video"], float(c["pos"]), float(c["neg"]), float(c["base_noise_std"]),
+                                   c["u0"], c["hot"], c["g"], bool(c["external"]), lut=c["lut"])
+    assert same(out, c["ref"])
+
+
+@pytest.mark.parametrize("name", golden("scatter").names("scat_mv_"))
+def test_c_oracle_make_voxel(name):
+    import v2v_oracle_c as orcc
+    c = golden("scatter").case(name)
+    out = orcc.make_voxel(c["ts"], c["xs"], c["ys"], c["ps"], int(c["bins"]), int(c["H"]), int(c["W"]), bool(c["interp"]))
+    assert same(out, c["ref"])

@@ -191,3 +191,21 @@ def test_split_bins_across_ctas(cuda_device, mode):
         assert np.array_equal(split[0], orc.make_voxel(tsx, xs, ys, ps, 5, h, w, False).astype(np.float32))
     if mode == "h5_interp":
         assert np.allclose(split[0], orc.make_voxel(tsx, xs, ys, ps, 5, h, w, True), **TOL)
+
+
+def test_full_size_stream_vs_c_oracle(cuda_device):
+    """BASELINE config 4 (10 M events, 260x346, 400 windows): every window against the C oracle."""
+    import v2v_b200 as v2v
+    import v2v_oracle_c as orcc
+    h, w, wn, ne = 260, 346, 400, 10_000_000
+    ts, xs, ys, ps, off = synth_stream(ne, h, w, wn, 29, hot_frac=0.01)
+    vd = v2v.voxelize_windows(xs, ys, ts, ps, off, 5, h, w, mode="h5_discrete").cpu().numpy()
+    vi = v2v.voxelize_windows(xs, ys, ts, ps, off, 5, h, w, mode="h5_interp", out_dtype=torch.float64).cpu().numpy()
+    worst = 0.0
+    for k in range(wn):
+        s = slice(off[k], off[k + 1])
+        assert np.array_equal(vd[k], orcc.make_voxel(ts[s], xs[s], ys[s], ps[s], 5, h, w, False).astype(np.float32)), k
+        ri = orcc.make_voxel(ts[s], xs[s], ys[s], ps[s], 5, h, w, True)
+        worst = max(worst, float(np.max(np.abs(vi[k] - ri) / np.maximum(1.0, np.abs(ri)))))
+    assert worst <= 1e-5, worst
+    assert worst < 1e-6          # in practice the fixed-point accumulation is ~1e-8
