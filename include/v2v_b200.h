@@ -221,6 +221,31 @@ typedef struct v2v_image_desc {
 
 int v2v_events_to_image(const v2v_image_desc* desc, void* stream);
 
+/* ======================================================================= *
+ * 5. Either side of the scatter
+ *    replaces  np.searchsorted(events/ts, border_timestamps)   data/testh5.py:468-474 (FPS_H5Dataset windows)
+ *              raw [N,5] float64 events [x, y, t, 2p-1, 0]     data/testh5.py:329-339 (TestH5EventDataset, NER-Net)
+ * ======================================================================= */
+/* out[i] = first index e with sorted[e] >= values[i] (np.searchsorted, side='left'); all device pointers. */
+int v2v_searchsorted_f64(const double* sorted, int64_t n, const double* values, int64_t num_values, int64_t* out, void* stream);
+/* out [N,5] float64; dtypes are enum v2v_dtype of the stored arrays. */
+int v2v_pack_events_n5(const void* xs, int xs_dtype, const void* ys, int ys_dtype, const void* ts, int ts_dtype,
+                       const void* ps, int ps_dtype, int64_t num_events, double* out, void* stream);
+
+/* ======================================================================= *
+ * 6. Voxel-space noise augmentation of cached voxels
+ *    replaces  add_noise_to_voxel        data/esim_dataset.py:33-46
+ *              add_hot_pixels_to_voxels  data/esim_dataset.py:7-30 (broadcast add of the [H,W] hot-pixel map;
+ *                                        the map itself is an event image: v2v_events_to_image with weights)
+ * ======================================================================= */
+/* voxel [n] float32 in place.  philox=0: noise [n] float64 (already scaled) and optional mask_u [n] uniforms are the
+ * reference's fields (element keeps its noise iff mask_u < noise_fraction).  philox=1: generated in the kernel:
+ * Gaussian noise_std*z, or (integer_noise) Poisson((-1+sqrt(1+4 std^2))/2) * random sign. */
+int v2v_voxel_add_noise(float* voxel, int64_t n, const double* noise, const double* mask_u, double noise_std,
+                        double noise_fraction, int integer_noise, int philox, uint64_t seed, uint64_t stream_id, void* stream);
+/* voxel [planes, hw] float32 += map [hw] float64 for every plane. */
+int v2v_voxel_add_map(float* voxel, int64_t planes, int64_t hw, const double* map, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -209,3 +209,33 @@ def test_full_size_stream_vs_c_oracle(cuda_device):
         worst = max(worst, float(np.max(np.abs(vi[k] - ri) / np.maximum(1.0, np.abs(ri)))))
     assert worst <= 1e-5, worst
     assert worst < 1e-6          # in practice the fixed-point accumulation is ~1e-8
+
+
+def test_fps_windows_and_raw_event_packing(cuda_device):
+    """FPS_H5Dataset window segmentation (data/testh5.py:468-474) and the NER-Net raw event tensor
+    (:329-339), both exact against NumPy."""
+    import v2v_b200 as v2v
+    g = np.random.Generator(np.random.PCG64(77))
+    ne, h, w = 200_000, 180, 240
+    ts = np.sort(g.random(ne)) * 2.37 + 11.0
+    ts[1000:1010] = ts[1000]                                  # ties
+    xs = g.integers(0, w, ne).astype(np.uint16)
+    ys = g.integers(0, h, ne).astype(np.uint16)
+    ps = (g.random(ne) < 0.5).astype(np.uint8)
+    fps = 100
+    total = int((ts[-1] - ts[0]) * fps)
+    borders = np.linspace(ts[0], ts[-1], total + 1)
+    ref_idx = np.searchsorted(ts, borders)
+    idx, b2 = v2v.fps_window_offsets(ts, fps)
+    assert np.array_equal(b2, borders) and np.array_equal(idx.cpu().numpy(), ref_idx)
+    # the windows feed the scatter directly: whole sequence in one launch == per-window reference voxels
+    vox = v2v.voxelize_windows(xs, ys, ts, ps, idx, 5, h, w, mode="h5_discrete").cpu().numpy()
+    for k in (0, total // 2, total - 1):
+        s = slice(ref_idx[k], ref_idx[k + 1])
+        assert np.array_equal(vox[k], orc.make_voxel(ts[s], xs[s], ys[s], ps[s], 5, h, w, False).astype(np.float32))
+    s = slice(ref_idx[3], ref_idx[4])
+    ref = np.stack([xs[s].astype(np.float64), ys[s].astype(np.float64), ts[s].astype(np.float64),
+                    ps[s].astype(np.float64) * 2 - 1, np.zeros(s.stop - s.start)], axis=1)
+    got = v2v.pack_events_n5(xs[s], ys[s], ts[s], ps[s])
+    assert got.dtype == torch.float64 and np.array_equal(got.cpu().numpy(), ref)
+    assert v2v.pack_events_n5(xs[:0], ys[:0], ts[:0], ps[:0]).shape == (1, 5)

@@ -98,6 +98,10 @@ SYMBOLS = {
     "v2v_v2e_philox_fields": (C.c_int, [C.POINTER(V2eDesc), _p, _p, _p, _p]),
     "v2v_events_to_voxel": (C.c_int, [C.POINTER(ScatterDesc), _p]),
     "v2v_events_to_image": (C.c_int, [C.POINTER(ImageDesc), _p]),
+    "v2v_voxel_add_noise": (C.c_int, [_p, C.c_int64, _p, _p, C.c_double, C.c_double, C.c_int, C.c_int, C.c_uint64, C.c_uint64, _p]),
+    "v2v_voxel_add_map": (C.c_int, [_p, C.c_int64, C.c_int64, _p, _p]),
+    "v2v_searchsorted_f64": (C.c_int, [_p, C.c_int64, _p, C.c_int64, _p, _p]),
+    "v2v_pack_events_n5": (C.c_int, [_p, C.c_int, _p, C.c_int, _p, C.c_int, _p, C.c_int, C.c_int64, _p, _p]),
 }
 
 _lib = None

@@ -1,0 +1,216 @@
+// Small helpers either side of the scatter path: window segmentation of an event stream by
+// time borders and the raw [N,5] event packing the NER-Net loader hands to its model.
+//
+// Replaces  np.searchsorted(f["events/ts"], border_timestamps)     data/testh5.py:468-474 (FPS_H5Dataset.__init__)
+//           np.stack([xs, ys, ts, ps*2-1, 0], axis=1) as float64   data/testh5.py:329-339 (TestH5EventDataset.__getitem__)
+#include "common.cuh"
+
+namespace v2v {
+namespace {
+
+// out[i] = first index e in [0, n) with ts[e] >= borders[i]   (np.searchsorted side='left' on a sorted array)
+__global__ void searchsorted_kernel(const double* __restrict__ ts, int64_t n, const double* __restrict__ borders, int64_t nb,
+                                    int64_t* __restrict__ out) {
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= nb) return;
+  const double b = borders[i];
+  int64_t lo = 0, hi = n;
+  while (lo < hi) {
+    const int64_t mid = lo + ((hi - lo) >> 1);
+    if (ts[mid] < b) lo = mid + 1; else hi = mid;
+  }
+  out[i] = lo;
+}
+
+__device__ __forceinline__ double load_as_f64(const void* p, int dtype, int64_t i) {
+  switch (dtype) {
+    case V2V_U8: return static_cast<double>(static_cast<const uint8_t*>(p)[i]);
+    case V2V_I8: return static_cast<double>(static_cast<const int8_t*>(p)[i]);
+    case V2V_U16: return static_cast<double>(static_cast<const uint16_t*>(p)[i]);
+    case V2V_I16: return static_cast<double>(static_cast<const int16_t*>(p)[i]);
+    case V2V_I32: return static_cast<double>(static_cast<const int32_t*>(p)[i]);
+    case V2V_I64: return static_cast<double>(static_cast<const int64_t*>(p)[i]);
+    case V2V_F32: return static_cast<double>(static_cast<const float*>(p)[i]);
+    case V2V_F64: return static_cast<const double*>(p)[i];
+  }
+  return 0.0;
+}
+
+struct PackArgs {
+  const void *xs, *ys, *ts, *ps;
+  int xs_dtype, ys_dtype, ts_dtype, ps_dtype;
+  int64_t n;
+  double* out;
+};
+
+// out[e] = [x, y, t, 2p-1, 0] as float64; 40 bytes out per event, written as 5 coalesced-ish doubles per thread
+__global__ void pack_events_kernel(const PackArgs a) {
+  for (int64_t e = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; e < a.n;
+       e += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    double* o = a.out + 5 * e;
+    o[0] = load_as_f64(a.xs, a.xs_dtype, e);
+    o[1] = load_as_f64(a.ys, a.ys_dtype, e);
+    o[2] = load_as_f64(a.ts, a.ts_dtype, e);
+    o[3] = load_as_f64(a.ps, a.ps_dtype, e) * 2 - 1;          // ps * 2 - 1   (data/testh5.py:334)
+    o[4] = 0.0;                                               // batch index (asserted batch size 1, :337)
+  }
+}
+
+}  // namespace
+}  // namespace v2v
+
+extern "C" int v2v_searchsorted_f64(const double* sorted, int64_t n, const double* values, int64_t num_values, int64_t* out,
+                                    void* stream) {
+  using namespace v2v;
+  V2V_REQUIRE(n >= 0 && num_values >= 0, V2V_ERR_INVALID_ARG, "negative size");
+  if (num_values == 0) return V2V_OK;
+  V2V_REQUIRE((sorted || n == 0) && values && out, V2V_ERR_INVALID_ARG, "NULL pointer");
+  searchsorted_kernel<<<static_cast<unsigned int>((num_values + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      sorted, n, values, num_values, out);
+  count_launch();
+  V2V_CUDA(cudaGetLastError());
+  return V2V_OK;
+}
+
+extern "C" int v2v_pack_events_n5(const void* xs, int xs_dtype, const void* ys, int ys_dtype, const void* ts, int ts_dtype,
+                                  const void* ps, int ps_dtype, int64_t num_events, double* out, void* stream) {
+  using namespace v2v;
+  V2V_REQUIRE(num_events >= 0, V2V_ERR_INVALID_ARG, "negative size");
+  if (num_events == 0) return V2V_OK;
+  V2V_REQUIRE(xs && ys && ts && ps && out, V2V_ERR_INVALID_ARG, "NULL pointer");
+  for (int t : {xs_dtype, ys_dtype, ts_dtype, ps_dtype}) V2V_REQUIRE(t >= V2V_U8 && t <= V2V_F64, V2V_ERR_INVALID_ARG, "bad dtype %d", t);
+  PackArgs a{xs, ys, ts, ps, xs_dtype, ys_dtype, ts_dtype, ps_dtype, num_events, out};
+  int64_t blocks = (num_events + 255) / 256;
+  if (blocks > 148 * 32) blocks = 148 * 32;
+  pack_events_kernel<<<static_cast<unsigned int>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(a);
+  count_launch();
+  V2V_CUDA(cudaGetLastError());
+  return V2V_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Voxel-space noise augmentation of the cached-voxel loader
+//   replaces  add_noise_to_voxel          data/esim_dataset.py:33-46
+//             add_hot_pixels_to_voxels    data/esim_dataset.py:7-30 (the broadcast add of the [H,W] noise map)
+// ---------------------------------------------------------------------------------------------
+namespace v2v {
+namespace {
+
+struct VoxNoiseArgs {
+  float* voxel;            // [n] in/out
+  int64_t n;
+  const double* noise;     // explicit: [n] noise values (already scaled), or NULL
+  const double* mask_u;    // explicit: [n] uniforms; element keeps its noise iff mask_u < noise_fraction (NULL: keep all)
+  double noise_std, noise_fraction, lambda;
+  int integer_noise, philox;
+  uint32_t rk[20];
+  uint64_t stream_id;
+};
+
+__device__ __forceinline__ int poisson_knuth(float lam, uint32_t w0, uint32_t w1) {
+  // inversion on a 32-bit uniform, second word continues the search for large counts
+  const float u = (static_cast<float>(w0 >> 8) + 0.5f) * (1.0f / 16777216.0f);
+  float p = __expf(-lam), cdf = p;
+  int k = 0;
+  while (u >= cdf && k < 256) {
+    ++k;
+    p *= lam / static_cast<float>(k);
+    cdf += p;
+    if (p < 1e-12f) break;
+  }
+  (void)w1;
+  return k;
+}
+
+__global__ void voxel_noise_kernel(const VoxNoiseArgs a) {
+  // 4 elements per thread and Philox call
+  const int64_t g = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const int64_t e0 = g * 4;
+  if (e0 >= a.n) return;
+  uint4 r = make_uint4(0, 0, 0, 0), r2 = make_uint4(0, 0, 0, 0);
+  if (a.philox) {
+    r = Philox::run_rk(make_uint4(static_cast<uint32_t>(g), static_cast<uint32_t>(g >> 32), static_cast<uint32_t>(a.stream_id), 0x51u), a.rk);
+    r2 = Philox::run_rk(make_uint4(static_cast<uint32_t>(g), static_cast<uint32_t>(g >> 32), static_cast<uint32_t>(a.stream_id), 0x52u), a.rk);
+  }
+  const uint32_t w[4] = {r.x, r.y, r.z, r.w}, w2[4] = {r2.x, r2.y, r2.z, r2.w};
+  float2 n01 = make_float2(0.f, 0.f), n23 = make_float2(0.f, 0.f);
+  if (a.philox && !a.integer_noise) {
+    n01 = box_muller(r.x, r.y);
+    n23 = box_muller(r.z, r.w);
+  }
+  const float z[4] = {n01.x, n01.y, n23.x, n23.y};
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int64_t e = e0 + k;
+    if (e >= a.n) break;
+    double noise;
+    bool keep = true;
+    if (a.philox) {
+      if (a.integer_noise) {      // y ~ Poisson(lambda), sign +-1 with equal probability   (:36-39)
+        const int y = poisson_knuth(static_cast<float>(a.lambda), w[k], 0u);
+        noise = static_cast<double>((w2[k] & 1u) ? y : -y);
+      } else {
+        noise = a.noise_std * static_cast<double>(z[k]);                                   // :41
+      }
+      if (a.noise_fraction < 1.0) keep = (static_cast<double>(w2[k] >> 8) * (1.0 / 16777216.0)) < a.noise_fraction;   // :43-45
+    } else {
+      noise = a.noise ? a.noise[e] : 0.0;
+      if (a.mask_u && a.noise_fraction < 1.0) keep = a.mask_u[e] < a.noise_fraction;       // mask = rand >= fraction -> 0
+    }
+    if (keep) a.voxel[e] = static_cast<float>(static_cast<double>(a.voxel[e]) + noise);    // voxel + noise in float64 (:46)
+  }
+}
+
+// voxel[p, i] += map[i] for every plane p (hot-pixel map broadcast over T and C, data/esim_dataset.py:27-29)
+__global__ void voxel_add_map_kernel(float* voxel, const double* map, int64_t planes, int64_t hw) {
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= hw) return;
+  const double m = map[i];
+  if (m == 0.0) return;
+  for (int64_t p = blockIdx.y; p < planes; p += gridDim.y) {
+    float* v = voxel + p * hw + i;
+    *v = static_cast<float>(static_cast<double>(*v) + m);
+  }
+}
+
+}  // namespace
+}  // namespace v2v
+
+extern "C" int v2v_voxel_add_noise(float* voxel, int64_t n, const double* noise, const double* mask_u, double noise_std,
+                                   double noise_fraction, int integer_noise, int philox, uint64_t seed, uint64_t stream_id,
+                                   void* stream) {
+  using namespace v2v;
+  V2V_REQUIRE(n >= 0, V2V_ERR_INVALID_ARG, "negative size");
+  if (n == 0) return V2V_OK;
+  V2V_REQUIRE(voxel != nullptr, V2V_ERR_INVALID_ARG, "voxel is NULL");
+  V2V_REQUIRE(philox || noise, V2V_ERR_INVALID_ARG, "explicit mode needs the noise field");
+  VoxNoiseArgs a;
+  a.voxel = voxel;
+  a.n = n;
+  a.noise = noise;
+  a.mask_u = mask_u;
+  a.noise_std = noise_std;
+  a.noise_fraction = noise_fraction;
+  a.lambda = (-1.0 + sqrt(1.0 + 4.0 * noise_std * noise_std)) / 2.0;       // data/esim_dataset.py:36
+  a.integer_noise = integer_noise;
+  a.philox = philox;
+  a.stream_id = stream_id;
+  Philox::round_keys(seed, a.rk);
+  const int64_t groups = (n + 3) / 4;
+  voxel_noise_kernel<<<static_cast<unsigned int>((groups + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(a);
+  count_launch();
+  V2V_CUDA(cudaGetLastError());
+  return V2V_OK;
+}
+
+extern "C" int v2v_voxel_add_map(float* voxel, int64_t planes, int64_t hw, const double* map, void* stream) {
+  using namespace v2v;
+  V2V_REQUIRE(planes >= 0 && hw >= 0, V2V_ERR_INVALID_ARG, "negative size");
+  if (planes == 0 || hw == 0) return V2V_OK;
+  V2V_REQUIRE(voxel && map, V2V_ERR_INVALID_ARG, "NULL pointer");
+  dim3 grid(static_cast<unsigned int>((hw + 255) / 256), static_cast<unsigned int>(planes < 64 ? planes : 64));
+  voxel_add_map_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(voxel, map, planes, hw);
+  count_launch();
+  V2V_CUDA(cudaGetLastError());
+  return V2V_OK;
+}

@@ -238,3 +238,42 @@ def events_to_voxel(xs, ys, ts, ps, B, sensor_size=(180, 240), temporal_bilinear
 def event_count_map(xs, ys, height, width, device="cuda") -> torch.Tensor:
     """Per-pixel int64 event counts (scripts/testset_evcnt_maps.py:19-25)."""
     return _image(xs, ys, None, (height, width), False, False, False, torch.int64, device)
+
+
+def fps_window_offsets(ts, fps: float, device="cuda"):
+    """Event offsets of fixed-rate windows, as ``FPS_H5Dataset.__init__`` computes them (data/testh5.py:468-474):
+    ``total = int((ts[-1]-ts[0])*FPS)``, ``borders = np.linspace(ts[0], ts[-1], total+1)``,
+    ``event_idx = np.searchsorted(ts, borders)``.  ``ts`` float64 seconds (sorted), host or device.
+    Returns (event_idx int64 [total+1] on the device, borders float64 numpy)."""
+    dev = torch.device(device)
+    ts_t = _to_dev(ts, dev)
+    if ts_t.dtype != torch.float64:
+        ts_t = ts_t.to(torch.float64)
+    n = ts_t.numel()
+    if n == 0:
+        return torch.zeros(1, dtype=torch.int64, device=dev), np.zeros(1)
+    lo_hi = ts_t[[0, n - 1]].cpu().numpy()
+    total = int((lo_hi[1] - lo_hi[0]) * fps)
+    borders = np.linspace(lo_hi[0], lo_hi[1], total + 1)            # the 2-number host step keeps numpy's exact linspace
+    b_t = torch.from_numpy(borders).to(dev)
+    out = torch.empty(total + 1, dtype=torch.int64, device=dev)
+    s = torch.cuda.current_stream(dev)
+    with torch.cuda.device(dev):
+        _lib.check(_lib.load().v2v_searchsorted_f64(_ptr(ts_t), n, _ptr(b_t), total + 1, _ptr(out), C.c_void_p(s.cuda_stream)))
+    return out, borders
+
+
+def pack_events_n5(xs, ys, ts, ps, device="cuda") -> torch.Tensor:
+    """Raw event tensor of the NER-Net loader (data/testh5.py:329-339): float64 ``[N,5]`` = [x, y, t, 2p-1, 0];
+    an empty window gives ``zeros((1,5))`` like the reference (:341-342)."""
+    dev = torch.device(device)
+    xs_t, ys_t, ts_t, ps_t = (_to_dev(a, dev) for a in (xs, ys, ts, ps))
+    n = xs_t.numel()
+    if n == 0:
+        return torch.zeros((1, 5), dtype=torch.float64, device=dev)
+    out = torch.empty((n, 5), dtype=torch.float64, device=dev)
+    s = torch.cuda.current_stream(dev)
+    with torch.cuda.device(dev):
+        _lib.check(_lib.load().v2v_pack_events_n5(_ptr(xs_t), _dt(xs_t), _ptr(ys_t), _dt(ys_t), _ptr(ts_t), _dt(ts_t),
+                                                  _ptr(ps_t), _dt(ps_t), n, _ptr(out), C.c_void_p(s.cuda_stream)))
+    return out
