@@ -123,7 +123,7 @@ struct Philox {
 // `c2` = -2 ln2 * scale^2 folds the noise standard deviation into the radius.  The in-kernel generator is a statistical
 // stand-in for the reference's MT19937 + polar method, which cannot be reproduced on a GPU; bit-parity runs use
 // EXPLICIT noise fields instead, and the audit hooks dump exactly what this function produced.
-constexpr int kTrigEntries = 4096;
+constexpr int kTrigEntries = 2048;
 
 __device__ __forceinline__ void fill_trig_table(float2* tab) {      // call with the whole CTA, then __syncthreads()
   for (int k = threadIdx.x; k < kTrigEntries; k += blockDim.x) {
@@ -135,12 +135,12 @@ __device__ __forceinline__ void fill_trig_table(float2* tab) {      // call with
 
 __device__ __forceinline__ float2 box_muller16(uint32_t w, float c2, const float2* trig) {
   // mantissa trick: a float in [1,2) straight from the random bits, no int->float conversion
-  const float f1 = __uint_as_float(((w << 3) & 0x007ffff8u) | 0x3f800000u);
+  const float f1 = __uint_as_float(((w << 2) & 0x007ffffcu) | 0x3f800000u);
   const float u1 = 2.0f - f1;                                  // (0,1], 20 bits
   float l, r;
   asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l) : "f"(u1));
   asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(l * c2));  // scale * sqrt(-2 ln u1)
-  const float2 cs = trig[w >> 20];
+  const float2 cs = trig[w >> 21];
   return make_float2(r * cs.x, r * cs.y);
 }
 

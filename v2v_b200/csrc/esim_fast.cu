@@ -21,7 +21,8 @@ namespace v2v {
 namespace {
 
 constexpr int kPF = 4;        // frames per loop trip; 2*kPF frames in flight
-constexpr int kLutCopies = 16;
+constexpr int kLutCopies = 8;
+constexpr int kFastThreads = 128;
 
 __device__ __forceinline__ int hi32(double x) { return __double2hiint(x); }
 
@@ -59,7 +60,7 @@ __device__ __forceinline__ void single_cross(double& x, float& ov, float& net, f
 }
 
 template <int NOISE, bool FRAMES, bool STATS, int MINB>
-__global__ void __launch_bounds__(kEsimThreads, MINB) esim_fast_kernel(const EsimArgs a) {
+__global__ void __launch_bounds__(kFastThreads, 2 * MINB) esim_fast_kernel(const EsimArgs a) {
   extern __shared__ __align__(16) unsigned char dyn_smem[];     // [LUT copies 32 KB][trig table 32 KB, Philox only]
   double* lut_s = reinterpret_cast<double*>(dyn_smem);
   float2* trig_s = reinterpret_cast<float2*>(dyn_smem + 256 * kLutCopies * sizeof(double));
@@ -68,14 +69,16 @@ __global__ void __launch_bounds__(kEsimThreads, MINB) esim_fast_kernel(const Esi
   const v2v_esim_desc& d = a.d;
   if (STATS && threadIdx.x < 2) cta_stats[threadIdx.x] = 0ull;
   {
-    const double v = d.lut[threadIdx.x];                    // kEsimThreads == 256
+    for (int e = threadIdx.x; e < 256; e += kFastThreads) {
+      const double v = d.lut[e];
 #pragma unroll
-    for (int c = 0; c < kLutCopies; ++c) lut_s[threadIdx.x * kLutCopies + c] = v;
+      for (int c = 0; c < kLutCopies; ++c) lut_s[e * kLutCopies + c] = v;
+    }
   }
   __syncthreads();
 
   const int b = blockIdx.y;
-  const int64_t pix0 = (static_cast<int64_t>(blockIdx.x) * kEsimThreads + threadIdx.x) * 4;
+  const int64_t pix0 = (static_cast<int64_t>(blockIdx.x) * kFastThreads + threadIdx.x) * 4;
   const int64_t HW = a.HW;
   if (pix0 < HW) {          // (no early return: every thread reaches the stats barrier at the end)
   const int N = d.N;
@@ -275,7 +278,7 @@ bool esim_fast_eligible(const EsimArgs& a) {
 
 int launch_esim_fast(const EsimArgs& a, cudaStream_t s) {
   const int64_t groups = a.HW / 4;
-  dim3 grid(static_cast<unsigned int>((groups + kEsimThreads - 1) / kEsimThreads), static_cast<unsigned int>(a.d.B));
+  dim3 grid(static_cast<unsigned int>((groups + kFastThreads - 1) / kFastThreads), static_cast<unsigned int>(a.d.B));
   const bool ph = a.d.noise_mode == V2V_NOISE_PHILOX, fr = a.d.frame_out_mode != 0, st = a.d.stats != nullptr;
   // occupancy knob (CTAs per SM the register allocator must allow), from a same-box sweep on B200
   // (profiles/r01_esim_minb_sweep.txt); V2V_ESIM_MINB overrides for tuning
@@ -286,13 +289,13 @@ int launch_esim_fast(const EsimArgs& a, cudaStream_t s) {
   do {                                                                                                           \
     if (minb <= 2) {                                                                                             \
       V2V_CUDA(cudaFuncSetAttribute(esim_fast_kernel<NM, FR, ST, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem))); \
-      esim_fast_kernel<NM, FR, ST, 2><<<grid, kEsimThreads, smem, s>>>(a);                                       \
+      esim_fast_kernel<NM, FR, ST, 2><<<grid, kFastThreads, smem, s>>>(a);                                       \
     } else if (minb >= 4) {                                                                                      \
       V2V_CUDA(cudaFuncSetAttribute(esim_fast_kernel<NM, FR, ST, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem))); \
-      esim_fast_kernel<NM, FR, ST, 4><<<grid, kEsimThreads, smem, s>>>(a);                                       \
+      esim_fast_kernel<NM, FR, ST, 4><<<grid, kFastThreads, smem, s>>>(a);                                       \
     } else {                                                                                                     \
       V2V_CUDA(cudaFuncSetAttribute(esim_fast_kernel<NM, FR, ST, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem))); \
-      esim_fast_kernel<NM, FR, ST, 3><<<grid, kEsimThreads, smem, s>>>(a);                                       \
+      esim_fast_kernel<NM, FR, ST, 3><<<grid, kFastThreads, smem, s>>>(a);                                       \
     }                                                                                                            \
   } while (0)
   if (ph) {
