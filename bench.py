@@ -454,7 +454,7 @@ def main():
     ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--clips", type=int, default=16, help="clips per step per GPU")
+    ap.add_argument("--clips", type=int, default=32, help="clips per step per GPU")
     ap.add_argument("--seed", type=int, default=2026)
     ap.add_argument("--e2e-clips", type=int, default=16)
     ap.add_argument("--e2e-chunk", type=int, default=2)
