@@ -156,7 +156,7 @@ def workload_config(clips_per_step, note=""):
                         "base_noise_std U[0,0.1], hot_pixel_fraction U[0,0.001], hot_pixel_std U[0,10], in-kernel Philox noise",
             "clips_per_step_per_gpu": clips_per_step, "frames": N_FRAMES, "height": H, "width": W, "num_bins": BINS,
             "l2": "inputs+outputs per step exceed the 126 MB L2 (no flush needed)", "note": note,
-            "launch": "timed steps replayed from CUDA graphs of 10 steps (each step = one C-ABI kernel launch + stats reduction)"}
+            "launch": "timed steps replayed from one CUDA graph (each step = one C-ABI kernel launch + stats reduction)"}
 
 
 # ----------------------------------------------------------------------------------------------
@@ -279,7 +279,19 @@ def run_ours(args):
     dist = None
     if world > 1:
         import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=dev)
+        # NCCL prints its version banner on stdout when NCCL_DEBUG is set on the host: keep stdout to the one JSON line
+        # by pointing fd 1 at stderr while the communicator is created (first collective)
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=dev)
+            dist.barrier()
+            torch.cuda.synchronize(dev)
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved, 1)
+            os.close(saved)
     B = args.clips
     vz = v2v.V2VVoxelizer(TRAIN_CFG, device=dev)
     rs = np.random.RandomState(1234 + rank)
@@ -353,8 +365,12 @@ def run_ours(args):
     t_wall1 = time.perf_counter()
     launches = (v2v.launch_count() - launches0) if graph is None else args.steps      # one kernel of ours per step (graph replays are not re-counted by the library)
     ms = ev0.elapsed_time(ev1)
+    per_rank = [ms / args.steps]
     if dist is not None:
         t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        allt = [torch.zeros_like(t) for _ in range(world)]
+        dist.all_gather(allt, t)
+        per_rank = [float(x.item()) / args.steps for x in allt]
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
     clocks = (sampler.stop(t_wall0, t_wall1) if not args.no_clocks else sampler._smi_once()) if rank == 0 else None
@@ -441,6 +457,7 @@ def run_ours(args):
                          "noise_free_launch_ms": clean_ms,
                          "noise_free_frac": B * ALGO_BYTES_PER_CLIP / (clean_ms * 1e-3) / 1e9 / peak},
             "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+            "ms_per_step_per_rank": per_rank,
             "event_stats": vdist.stats_dict(job),
         }
         print(json.dumps(line))
@@ -461,7 +478,7 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="launch every timed step from Python instead of replaying CUDA graphs")
-    ap.add_argument("--graph-steps", type=int, default=10)
+    ap.add_argument("--graph-steps", type=int, default=100)
     ap.add_argument("--no-clocks", action="store_true", help="(experiments) do not sample clocks during the timed region")
     ap.add_argument("--clock-period", type=float, default=0.1)
     args = ap.parse_args()
