@@ -155,3 +155,35 @@ def test_c_oracle_make_voxel(name):
     c = golden("scatter").case(name)
     out = orcc.make_voxel(c["ts"], c["xs"], c["ys"], c["ps"], int(c["bins"]), int(c["H"]), int(c["W"]), bool(c["interp"]))
     assert same(out, c["ref"])
+
+
+def test_c_and_numpy_oracles_agree_on_random_inputs():
+    """The two restatements are independent (vectorised NumPy vs scalar C with numpy's divmod spelled out):
+    they must agree bit for bit on random clips, thresholds incl. near-multiples, noise on/off/external."""
+    import v2v_oracle_c as orcc
+    from conftest import synth_video
+    g = np.random.Generator(np.random.PCG64(99))
+    lut = orc.esim_log_lut()
+    for trial in range(12):
+        n, h, w = int(g.integers(2, 9)), int(g.integers(1, 20)), int(g.integers(1, 20))
+        vid = synth_video("iid" if trial % 2 else "walk", n, h, w, trial)
+        pos = float(g.choice([0.05, 0.1, 0.2, 1 / 3, 0.7, 1.9]))
+        neg = pos * float(g.choice([1.0, 1.25, 1.5, 1 / 1.5]))
+        std = float(g.choice([0.0, 0.03, 0.1]))
+        u0 = g.random((h, w))
+        hot = np.where(g.random((h, w)) < 0.1, g.standard_normal((h, w)) * 5, 0.0)
+        gs = g.standard_normal((n - 1, h, w))
+        for ext in (False, True):
+            a, pa = orc.esim_video_to_voxel(vid, pos, neg, std, u0, hot, gs, ext, lut, return_state=True)
+            b, pb = orcc.esim_video_to_voxel(vid, pos, neg, std, u0, hot, gs, ext, lut, return_state=True)
+            assert same(a, b) and same(pa, pb), (trial, ext)
+    for trial in range(8):
+        ne, h, w, bins = int(g.integers(1, 400)), int(g.integers(2, 30)), int(g.integers(2, 30)), int(g.choice([1, 3, 5, 15]))
+        ts = np.sort(g.random(ne)) * float(g.choice([1e-3, 0.04, 2.0])) + float(g.choice([0.0, 17.3, 1.6e9]))
+        if trial % 3 == 0:
+            ts = ts.astype(np.float32)
+        xs = g.integers(0, w, ne).astype(np.uint16)
+        ys = g.integers(0, h, ne).astype(np.uint16)
+        ps = (g.random(ne) < 0.5).astype(np.uint8)
+        for interp in (False, True):
+            assert same(orc.make_voxel(ts, xs, ys, ps, bins, h, w, interp), orcc.make_voxel(ts, xs, ys, ps, bins, h, w, interp)), (trial, interp)

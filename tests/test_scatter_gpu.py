@@ -239,3 +239,15 @@ def test_fps_windows_and_raw_event_packing(cuda_device):
     got = v2v.pack_events_n5(xs[s], ys[s], ts[s], ps[s])
     assert got.dtype == torch.float64 and np.array_equal(got.cpu().numpy(), ref)
     assert v2v.pack_events_n5(xs[:0], ys[:0], ts[:0], ps[:0]).shape == (1, 5)
+
+
+def test_validate_flag_rejects_unsorted_windows(cuda_device):
+    import v2v_b200 as v2v
+    ts = np.array([0.0, 0.1, 0.2, 0.05, 0.06, 0.07])          # decrease at index 3 = window boundary: allowed
+    xs = np.arange(6, dtype=np.int16)
+    ys = np.zeros(6, dtype=np.int16)
+    ps = np.ones(6, dtype=np.uint8)
+    v = v2v.voxelize_windows(xs, ys, ts, ps, [0, 3, 6], 2, 4, 8, validate=True)
+    assert float(v.sum()) == 6.0
+    with pytest.raises(ValueError):
+        v2v.voxelize_windows(xs, ys, ts, ps, [0, 6], 2, 4, 8, validate=True)

@@ -57,7 +57,7 @@ def _dt(t: torch.Tensor) -> int:
 def voxelize_windows(xs, ys, ts, ps, window_offsets, num_bins: int, height: int, width: int, *,
                      mode: str = "h5_discrete", polarity: str = "signed", out_dtype=torch.float32,
                      device="cuda", out: Optional[torch.Tensor] = None, return_dropped: bool = False,
-                     stream: Optional[torch.cuda.Stream] = None):
+                     validate: bool = False, stream: Optional[torch.cuda.Stream] = None):
     """Scatter ``Wn`` windows of one event stream into ``[Wn,bins,H,W]`` in one launch.
 
     window_offsets: ``[Wn+1]`` ascending event indices (e.g. the ``event_idx``
@@ -65,6 +65,9 @@ def voxelize_windows(xs, ys, ts, ps, window_offsets, num_bins: int, height: int,
     "h5_discrete" | "h5_interp" (data/testh5.py:70-80; ts in seconds, float64
     or float32, ps in {0,1}) | "torch_discrete" | "torch_bilinear"
     (utils/event_utils.py:490-505; float32 arithmetic, ps = signed weights).
+
+    Precondition (include/v2v_b200.h): timestamps are non-decreasing inside every window, as in every h5 file the
+    reference's converters write.  ``validate=True`` checks it (one extra pass, a device->host sync) and raises.
     """
     dev = torch.device(device)
     modes = {"h5_discrete": _lib.SCATTER_H5_DISCRETE, "h5_interp": _lib.SCATTER_H5_INTERP,
@@ -83,6 +86,14 @@ def voxelize_windows(xs, ys, ts, ps, window_offsets, num_bins: int, height: int,
     wn = off_t.numel() - 1
     if wn < 0:
         raise ValueError("window_offsets needs at least one entry")
+    if validate and ne > 1:
+        bad = ts_t[1:] < ts_t[:-1]
+        if wn > 0:                                   # a decrease exactly at a window boundary is fine
+            edges = off_t[1:-1]
+            edges = edges[(edges > 0) & (edges < ne)]
+            bad[edges - 1] = False
+        if bool(bad.any()):
+            raise ValueError("timestamps must be non-decreasing inside every window")
     if out is None:
         out = torch.empty((wn, num_bins, height, width), dtype=out_dtype, device=dev)
     elif tuple(out.shape) != (wn, num_bins, height, width) or not out.is_contiguous() or not out.is_cuda:
