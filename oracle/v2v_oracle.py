@@ -458,6 +458,21 @@ def events_to_image_np(xs, ys, ps, sensor_size=(180, 240)):
     return np.bincount(flat, weights=ps, minlength=sensor_size[0] * sensor_size[1]).reshape(sensor_size)
 
 
+def events_to_voxel_np(xs, ys, ts, ps, num_bins, sensor_size=(180, 240)):
+    """NumPy float64 voxel with temporal bilinear weights (events_to_voxel, utils/event_utils.py:692-728, the
+    ``temporal_bilinear=True`` branch; the other branch reads ``weights`` before assignment in the reference).
+    ``ts``/``ps`` may be ``[N]`` or the ``[N,1]`` columns the reference needs."""
+    ts = np.asarray(ts, dtype=np.float64).reshape(-1)
+    ps = np.asarray(ps, dtype=np.float64).reshape(-1)
+    span = ts[-1] - ts[0]                                            # :711
+    tn = (ts - ts[0]) / span * (num_bins - 1)                        # :712
+    planes = []
+    for bi in range(num_bins):                                       # :714-726
+        wgt = ps * np.maximum(0.0, 1.0 - np.abs(tn - bi))
+        planes.append(events_to_image_np(xs, ys, wgt, sensor_size))
+    return np.stack(planes)
+
+
 def event_count_map(xs, ys, height, width):
     """Per-pixel event count (scripts/testset_evcnt_maps.py:19-25)."""
     cnt = np.zeros((height, width), dtype=np.int64)

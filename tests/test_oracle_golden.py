@@ -187,3 +187,9 @@ def test_c_and_numpy_oracles_agree_on_random_inputs():
         ps = (g.random(ne) < 0.5).astype(np.uint8)
         for interp in (False, True):
             assert same(orc.make_voxel(ts, xs, ys, ps, bins, h, w, interp), orcc.make_voxel(ts, xs, ys, ps, bins, h, w, interp)), (trial, interp)
+
+
+def test_events_to_voxel_np():
+    c = golden("scatter").case("scat_voxel_np")
+    out = orc.events_to_voxel_np(c["xs"], c["ys"], c["ts"], c["ps"], int(c["bins"]), (int(c["H"]), int(c["W"])))
+    assert same(out, c["ref"])

@@ -251,3 +251,13 @@ def test_validate_flag_rejects_unsorted_windows(cuda_device):
     assert float(v.sum()) == 6.0
     with pytest.raises(ValueError):
         v2v.voxelize_windows(xs, ys, ts, ps, [0, 6], 2, 4, 8, validate=True)
+
+
+def test_numpy_events_to_voxel_golden(cuda_device):
+    import v2v_b200 as v2v
+    c = golden("scatter").case("scat_voxel_np")
+    got = v2v.events_to_voxel(c["xs"], c["ys"], c["ts"][:, None], c["ps"][:, None], int(c["bins"]),
+                              sensor_size=(int(c["H"]), int(c["W"])))
+    assert got.dtype == np.float64 and np.allclose(got, c["ref"], rtol=1e-9, atol=1e-9)
+    with pytest.raises(NotImplementedError):
+        v2v.events_to_voxel(c["xs"], c["ys"], c["ts"], c["ps"], 5, temporal_bilinear=False)
