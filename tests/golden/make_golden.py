@@ -308,10 +308,9 @@ def gen_scatter(testh5, eu, out):
     xs2, ys2 = g.integers(0, w, ne2), g.integers(0, h, ne2)
     ts2 = np.sort(g.random(ne2)) * 0.3 + 2.0
     ps2 = (g.integers(0, 2, ne2) * 2 - 1).astype(np.float64)
-    ref = eu.events_to_voxel(xs2, ys2, ts2[:, None], ps2[:, None], 5, sensor_size=(h, w), temporal_bilinear=True)
-    mine = orc.events_to_voxel_np(xs2, ys2, ts2, ps2, 5, (h, w))
-    assert same(ref, mine)
-    out["scat_voxel_np"] = dict(xs=xs2, ys=ys2, ts=ts2, ps=ps2, bins=5, H=h, W=w, ref=ref)
+    ref_v = eu.events_to_voxel(xs2, ys2, ts2[:, None], ps2[:, None], 5, sensor_size=(h, w), temporal_bilinear=True)
+    assert same(ref_v, orc.events_to_voxel_np(xs2, ys2, ts2, ps2, 5, (h, w)))
+    out["scat_voxel_np"] = dict(xs=xs2, ys=ys2, ts=ts2, ps=ps2, bins=5, H=h, W=w, ref=ref_v)
     out["scat_img_np"] = dict(xs=xi.astype(np.int64), ys=yi.astype(np.int64), ps=pf.astype(np.float64), H=h, W=w,
                               ref=ref)
 
