@@ -59,8 +59,8 @@ __device__ __forceinline__ void single_cross(double& x, float& ov, float& net, f
   }
 }
 
-template <int NOISE, bool FRAMES, bool STATS, int MINB>
-__global__ void __launch_bounds__(kFastThreads, 2 * MINB) esim_fast_kernel(const EsimArgs a) {
+template <int NOISE, bool FRAMES, bool STATS, int CTAS>
+__global__ void __launch_bounds__(kFastThreads, CTAS) esim_fast_kernel(const EsimArgs a) {
   extern __shared__ __align__(16) unsigned char dyn_smem[];     // [LUT copies 32 KB][trig table 32 KB, Philox only]
   double* lut_s = reinterpret_cast<double*>(dyn_smem);
   float2* trig_s = reinterpret_cast<float2*>(dyn_smem + 256 * kLutCopies * sizeof(double));
@@ -280,23 +280,21 @@ int launch_esim_fast(const EsimArgs& a, cudaStream_t s) {
   const int64_t groups = a.HW / 4;
   dim3 grid(static_cast<unsigned int>((groups + kFastThreads - 1) / kFastThreads), static_cast<unsigned int>(a.d.B));
   const bool ph = a.d.noise_mode == V2V_NOISE_PHILOX, fr = a.d.frame_out_mode != 0, st = a.d.stats != nullptr;
-  // occupancy knob (CTAs per SM the register allocator must allow), from a same-box sweep on B200
-  // (profiles/r01_esim_minb_sweep.txt); V2V_ESIM_MINB overrides for tuning
-  int minb = ph ? (st ? 2 : 3) : (st ? 3 : 4);
-  if (const char* e = getenv("V2V_ESIM_MINB")) minb = atoi(e);
+  // resident CTAs per SM the register allocator must allow (4 -> 128 regs, 6 -> 80, 8 -> 64), chosen per
+  // variant from same-box sweeps on B200 (profiles/r01_esim_minb_sweep.txt); V2V_ESIM_CTAS overrides for tuning
+  int ctas = ph ? (st ? 4 : 6) : (st ? 6 : 8);
+  if (const char* e = getenv("V2V_ESIM_CTAS")) ctas = atoi(e);
   const size_t smem = 256 * kLutCopies * sizeof(double) + (ph ? kTrigEntries * sizeof(float2) : 0);
-#define V2V_F(NM, FR, ST)                                                                                        \
-  do {                                                                                                           \
-    if (minb <= 2) {                                                                                             \
-      V2V_CUDA(cudaFuncSetAttribute(esim_fast_kernel<NM, FR, ST, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem))); \
-      esim_fast_kernel<NM, FR, ST, 2><<<grid, kFastThreads, smem, s>>>(a);                                       \
-    } else if (minb >= 4) {                                                                                      \
-      V2V_CUDA(cudaFuncSetAttribute(esim_fast_kernel<NM, FR, ST, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem))); \
-      esim_fast_kernel<NM, FR, ST, 4><<<grid, kFastThreads, smem, s>>>(a);                                       \
-    } else {                                                                                                     \
-      V2V_CUDA(cudaFuncSetAttribute(esim_fast_kernel<NM, FR, ST, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem))); \
-      esim_fast_kernel<NM, FR, ST, 3><<<grid, kFastThreads, smem, s>>>(a);                                       \
-    }                                                                                                            \
+#define V2V_G(NM, FR, ST, CT)                                                                                     \
+  do {                                                                                                            \
+    V2V_CUDA(cudaFuncSetAttribute(esim_fast_kernel<NM, FR, ST, CT>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem))); \
+    esim_fast_kernel<NM, FR, ST, CT><<<grid, kFastThreads, smem, s>>>(a);                                        \
+  } while (0)
+#define V2V_F(NM, FR, ST)                       \
+  do {                                          \
+    if (ctas <= 4) V2V_G(NM, FR, ST, 4);        \
+    else if (ctas <= 7) V2V_G(NM, FR, ST, 6);   \
+    else V2V_G(NM, FR, ST, 8);                  \
   } while (0)
   if (ph) {
     if (fr) { if (st) V2V_F(V2V_NOISE_PHILOX, true, true); else V2V_F(V2V_NOISE_PHILOX, true, false); }
@@ -306,6 +304,7 @@ int launch_esim_fast(const EsimArgs& a, cudaStream_t s) {
     else    { if (st) V2V_F(V2V_NOISE_NONE, false, true); else V2V_F(V2V_NOISE_NONE, false, false); }
   }
 #undef V2V_F
+#undef V2V_G
   count_launch();
   V2V_CUDA(cudaGetLastError());
   return V2V_OK;
