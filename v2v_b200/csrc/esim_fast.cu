@@ -23,8 +23,7 @@ namespace {
 constexpr int kPF = 4;        // frames per loop trip; 2*kPF frames in flight
 constexpr int kLutCopies = 8;
 constexpr int kFastThreads = 128;
-
-__device__ __forceinline__ int hi32(double x) { return __double2hiint(x); }
+constexpr int kFlushTrips = 8;  // statistics: float partial sums cover 4*kPF*kFlushTrips pixel-intervals (exact for counts < 2^17 each)
 
 // Exact multi-threshold crossing on the ORIGINAL potential x (data/v2v_core_esim.py:51-58).
 // Also correct for |x| below the threshold (count 0), so the caller's trigger may be conservative.
@@ -42,21 +41,28 @@ __device__ __forceinline__ double multi_cross(double x, double pos, double neg, 
 }
 
 // The common case, branch-free: at most one threshold is crossed, so q*thr == thr exactly and
-// x - q*pos == fma(-pos, q, x) with q in {0.0, 1.0} (one rounding, same value as the reference's
-// separately rounded product and difference because the product is exact).
-template <bool STATS>
-__device__ __forceinline__ void single_cross(double& x, float& ov, float& net, float& tot, double pos, double mneg, double neg) {
+// x - q*pos is one rounded subtraction (same value as the reference's separately rounded product
+// and difference because the product is exact).  Written as two predicated FP64 adds: the FP64 pipe
+// has slack, the ALU pipe (selects) does not.
+__device__ __forceinline__ void single_cross(double& x, float& ov, double pos, double mneg) {
   const bool up = x >= pos, dn = x <= mneg;                                 // :52,55
-  // x + sel with sel in {-pos, +neg, 0}: one rounded add, equal to x - 1*pos / x + 1*neg  (:57-58)
+  // qu in {0.0, 1.0}, qd in {0.0, -1.0}: q*thr is exact, so fma(-thr, q, x) rounds once exactly like x -/+ q*thr (:57-58),
+  // and a zero q adds -0.0, which leaves every x untouched.  Only the high words are selected (the low words are 0).
+  const int hu = up ? 0x3ff00000 : 0, hd = dn ? static_cast<int>(0xbff00000u) : 0;
+  x = __fma_rn(-pos, __hiloint2double(hu, 0), x);
+  x = __fma_rn(mneg, __hiloint2double(hd, 0), x);
+  ov = __int_as_float((hu | hd) & static_cast<int>(0xbf800000u));           // +1.0f, -1.0f or 0.0f from the same words
+}
+
+// Select form of the same update (one FP64 add of {-pos, +neg, 0}): fewer registers; used by the noise-free
+// variants, which run at 64 registers / 8 CTAs per SM and are closer to the HBM limit than to the ALU pipe's.
+__device__ __forceinline__ void single_cross_sel(double& x, float& ov, double pos, double mneg, double neg) {
+  const bool up = x >= pos, dn = x <= mneg;
   double sel = up ? -pos : 0.0;
   sel = dn ? neg : sel;
   x = __dadd_rn(x, sel);
   ov = up ? 1.0f : 0.0f;
   ov = dn ? -1.0f : ov;
-  if (STATS) {            // float accumulators are exact below 2^24 events per thread; flushed by the caller
-    net += ov;
-    tot += fabsf(ov);
-  }
 }
 
 template <int NOISE, bool FRAMES, bool STATS, int CTAS>
@@ -65,9 +71,12 @@ __global__ void __launch_bounds__(kFastThreads, CTAS) esim_fast_kernel(const Esi
   double* lut_s = reinterpret_cast<double*>(dyn_smem);
   float2* trig_s = reinterpret_cast<float2*>(dyn_smem + 256 * kLutCopies * sizeof(double));
   __shared__ unsigned long long cta_stats[2];
+  __shared__ double cta_rcp[2];                                    // 1/pos, 1/neg of this CTA's clip: only the rare path reads them
+  __shared__ float4 hot_s[NOISE == V2V_NOISE_PHILOX ? kFastThreads : 1];   // per-lane hot-pixel noise: read by the ~6 % of warps that own one
   if (NOISE == V2V_NOISE_PHILOX) fill_trig_table(trig_s);
   const v2v_esim_desc& d = a.d;
   if (STATS && threadIdx.x < 2) cta_stats[threadIdx.x] = 0ull;
+  if (threadIdx.x < 2) cta_rcp[threadIdx.x] = __drcp_rn(threadIdx.x ? d.neg_thres[blockIdx.y] : d.pos_thres[blockIdx.y]);
   {
     for (int e = threadIdx.x; e < 256; e += kFastThreads) {
       const double v = d.lut[e];
@@ -88,8 +97,9 @@ __global__ void __launch_bounds__(kFastThreads, CTAS) esim_fast_kernel(const Esi
 
   const double pos = d.pos_thres[b], neg = d.neg_thres[b];
   const double mneg = -neg;
-  const double rpos = __drcp_rn(pos), rneg = __drcp_rn(neg);
-  const int hibig = hi32(__dadd_rn(fmin(pos, neg), fmin(pos, neg)));
+  const double thr2 = __dadd_rn(fmin(pos, neg), fmin(pos, neg));   // below 2*min(pos,neg) at most one threshold is crossed
+  const int hibig = __double2hiint(thr2);
+  constexpr bool kFp64Trigger = NOISE == V2V_NOISE_PHILOX;         // which pipe pays for the trigger / the update (see single_cross*)
   const float nc2 = NOISE == V2V_NOISE_PHILOX ? noise_c2(static_cast<float>(d.base_noise_std[b])) : 0.f;
   // byte offset of this lane's LUT copy
   const uint32_t lut_base = static_cast<uint32_t>(__cvta_generic_to_shared(dyn_smem)) + (threadIdx.x & (kLutCopies - 1)) * 8u;
@@ -106,7 +116,7 @@ __global__ void __launch_bounds__(kFastThreads, CTAS) esim_fast_kernel(const Esi
 
   const uint8_t* fr = d.frames + (static_cast<int64_t>(b) * N) * HW + pix0;
   double pot[4], lprev[4];
-  float hotf[4];            // Philox hot-pixel noise is double(float) by construction: keep the float
+  float hotf[4];            // Philox hot-pixel noise is double(float) by construction: keep the float (parked in smem)
   const uint32_t w0 = ld_stream_u32(fr);
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
@@ -137,14 +147,24 @@ __global__ void __launch_bounds__(kFastThreads, CTAS) esim_fast_kernel(const Esi
                     __fdiv_rn(static_cast<float>((w0 >> 16) & 0xffu), 255.0f), __fdiv_rn(static_cast<float>(w0 >> 24), 255.0f));
     fout += HW;
   }
-  unsigned int npos = 0, nneg = 0;      // multi-threshold events (exact integers)
-  float net = 0.f, tot = 0.f;           // single-threshold events: net = #pos - #neg, tot = #pos + #neg
+  float net = 0.f, tot = 0.f;             // since the last flush: net = #pos - #neg, tot = #pos + #neg
+  auto flush_stats = [&]() {              // warp REDUX -> shared atomics; all active lanes of a warp run the same trip count
+    const unsigned int m = __activemask();
+    const unsigned int sp = __reduce_add_sync(m, static_cast<unsigned int>((tot + net) * 0.5f));
+    const unsigned int sn = __reduce_add_sync(m, static_cast<unsigned int>((tot - net) * 0.5f));
+    if ((threadIdx.x & 31) == (__ffs(m) - 1)) {
+      atomicAdd(&cta_stats[0], static_cast<unsigned long long>(sp));
+      atomicAdd(&cta_stats[1], static_cast<unsigned long long>(sn));
+    }
+    net = tot = 0.f;
+  };
 
   bool lane_hot = false;
 #pragma unroll
   for (int k = 0; k < 4; ++k) lane_hot = lane_hot || hotf[k] != 0.f;
   // warp-uniform: a real branch that 94 % of the warps never take (hot_pixel_fraction <= 1e-3)
   const bool any_hot = __any_sync(__activemask(), lane_hot);
+  if (NOISE == V2V_NOISE_PHILOX) hot_s[threadIdx.x] = make_float4(hotf[0], hotf[1], hotf[2], hotf[3]);   // own slot: no barrier needed
 
   auto step = [&](const uint32_t w, const float (&bnf)[4]) {
     float o[4];
@@ -155,33 +175,55 @@ __global__ void __launch_bounds__(kFastThreads, CTAS) esim_fast_kernel(const Esi
       const double L = lut_at(byte_of(w, k));
       double x = __dadd_rn(pot[k], __dsub_rn(L, lprev[k]));          // :42-43
       lprev[k] = L;
-      if (NOISE == V2V_NOISE_PHILOX) {                                // :46-49
-        x = __dadd_rn(x, static_cast<double>(bnf[k]));
-        if (any_hot) x = __dadd_rn(x, static_cast<double>(hotf[k]));                        // x + 0.0 == x: skipped for the 99.8 % of threads without a hot pixel
-      }
+      if (NOISE == V2V_NOISE_PHILOX) x = __dadd_rn(x, static_cast<double>(bnf[k]));   // :46-48
       x0[k] = x;
-      // trigger of the exact multi-threshold path: |x| >= 2*min(pos,neg), tested on the high word
-      rare = rare || ((hi32(x) & 0x7fffffff) >= hibig);
-      single_cross<STATS>(x, o[k], net, tot, pos, mneg, neg);      // :51-58 with q in {0,1}
+    }
+    if (NOISE == V2V_NOISE_PHILOX && any_hot) {                       // :49; x + 0.0 == x: skipped by the warps without a hot pixel
+      asm volatile("" ::: "memory");                                  // keep this a (warp-uniform) branch
+      const float4 h = hot_s[threadIdx.x];
+      x0[0] = __dadd_rn(x0[0], static_cast<double>(h.x));
+      x0[1] = __dadd_rn(x0[1], static_cast<double>(h.y));
+      x0[2] = __dadd_rn(x0[2], static_cast<double>(h.z));
+      x0[3] = __dadd_rn(x0[3], static_cast<double>(h.w));
+    }
+    if (kFp64Trigger) {   // trigger of the exact multi-threshold path: four FP64 compares chained through one predicate
+      unsigned int r;
+      asm("{\n"
+          " .reg .pred p;\n"
+          " .reg .f64 t;\n"
+          " abs.f64 t, %1;\n setp.ge.f64 p, t, %5;\n"
+          " abs.f64 t, %2;\n setp.ge.or.f64 p, t, %5, p;\n"
+          " abs.f64 t, %3;\n setp.ge.or.f64 p, t, %5, p;\n"
+          " abs.f64 t, %4;\n setp.ge.or.f64 p, t, %5, p;\n"
+          " selp.u32 %0, 1, 0, p;\n"
+          "}"
+          : "=r"(r)
+          : "d"(x0[0]), "d"(x0[1]), "d"(x0[2]), "d"(x0[3]), "d"(thr2));
+      rare = r != 0;
+    } else {              // same test on the high words (conservative: may also fire just below 2*min, which multi_cross handles)
+#pragma unroll
+      for (int k = 0; k < 4; ++k) rare = rare || ((__double2hiint(x0[k]) & 0x7fffffff) >= hibig);
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      double x = x0[k];
+      if (kFp64Trigger) single_cross(x, o[k], pos, mneg);
+      else single_cross_sel(x, o[k], pos, mneg, neg);                        // :51-58 with q in {0,1}
       pot[k] = x;
     }
     if (rare) {                                                       // a few % of warp-steps on natural video
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
-        if ((hi32(x0[k]) & 0x7fffffff) >= hibig) {
-          if (STATS) {                                                // undo what single_cross counted
-            net -= o[k];
-            tot -= fabsf(o[k]);
-          }
+        if (kFp64Trigger ? fabs(x0[k]) >= thr2 : (__double2hiint(x0[k]) & 0x7fffffff) >= hibig) {
           int cnt;
-          pot[k] = multi_cross(x0[k], pos, neg, rpos, rneg, &cnt);   // conservative trigger: correct for any x
+          pot[k] = multi_cross(x0[k], pos, neg, cta_rcp[0], cta_rcp[1], &cnt);   // conservative trigger: correct for any x
           o[k] = static_cast<float>(cnt);
-          if (STATS) {
-            if (cnt > 0) npos += static_cast<unsigned int>(cnt);
-            else nneg += static_cast<unsigned int>(-cnt);
-          }
         }
       }
+    }
+    if (STATS) {            // from the final counts; float sums are exact while below 2^24 (flushed every kFlushTrips trips)
+      net += (o[0] + o[1]) + (o[2] + o[3]);
+      tot += (fabsf(o[0]) + fabsf(o[1])) + (fabsf(o[2]) + fabsf(o[3]));
     }
     st_stream_f32x4(vox, o[0], o[1], o[2], o[3]);
     vox += a.plane_stride;
@@ -226,6 +268,7 @@ __global__ void __launch_bounds__(kFastThreads, CTAS) esim_fast_kernel(const Esi
     i += kPF;
 #pragma unroll
     for (int u = 0; u < kPF; ++u) cur[u] = nxt[u];
+    if (STATS && (t & (kFlushTrips - 1)) == kFlushTrips - 1) flush_stats();
   }
   for (; i < N; ++i) {                                                // ragged tail (< kPF intervals)
     float bn1[4] = {0.f, 0.f, 0.f, 0.f};
@@ -242,22 +285,7 @@ __global__ void __launch_bounds__(kFastThreads, CTAS) esim_fast_kernel(const Esi
 #pragma unroll
     for (int k = 0; k < 4; ++k) d.potential_out[clip_pix + k] = pot[k];
   }
-  if (STATS) {
-    // warp shuffle -> shared atomics -> one pair of global atomics per CTA (the whole CTA belongs to clip b)
-    npos += static_cast<unsigned int>((tot + net) * 0.5f);
-    nneg += static_cast<unsigned int>((tot - net) * 0.5f);
-    const unsigned int m = __activemask();
-    if (m == 0xffffffffu) {
-      const long long sp = warp_sum(static_cast<long long>(npos)), sn = warp_sum(static_cast<long long>(nneg));
-      if ((threadIdx.x & 31) == 0) {
-        atomicAdd(&cta_stats[0], static_cast<unsigned long long>(sp));
-        atomicAdd(&cta_stats[1], static_cast<unsigned long long>(sn));
-      }
-    } else {
-      atomicAdd(&cta_stats[0], static_cast<unsigned long long>(npos));
-      atomicAdd(&cta_stats[1], static_cast<unsigned long long>(nneg));
-    }
-  }
+  if (STATS) flush_stats();               // one pair of global atomics per CTA follows (the whole CTA belongs to clip b)
   }  // valid
   if (STATS) {
     __syncthreads();
@@ -282,7 +310,7 @@ int launch_esim_fast(const EsimArgs& a, cudaStream_t s) {
   const bool ph = a.d.noise_mode == V2V_NOISE_PHILOX, fr = a.d.frame_out_mode != 0, st = a.d.stats != nullptr;
   // resident CTAs per SM the register allocator must allow (4 -> 128 regs, 6 -> 80, 8 -> 64), chosen per
   // variant from same-box sweeps on B200 (profiles/r01_esim_minb_sweep.txt); V2V_ESIM_CTAS overrides for tuning
-  int ctas = ph ? (st ? 4 : 6) : (st ? 6 : 8);
+  int ctas = ph ? 4 : (st ? 6 : 8);
   if (const char* e = getenv("V2V_ESIM_CTAS")) ctas = atoi(e);
   const size_t smem = 256 * kLutCopies * sizeof(double) + (ph ? kTrigEntries * sizeof(float2) : 0);
 #define V2V_G(NM, FR, ST, CT)                                                                                     \
