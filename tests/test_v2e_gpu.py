@@ -114,3 +114,120 @@ def test_v2e_philox_statistics(cuda_device):
                             leak_jitter_fraction=0.1, noise_rate=nrate[None], noise="explicit",
                             leak_randn=f["leak_randn"][None], pos_shot=f["pos_shot"][None], neg_shot=f["neg_shot"][None])
     assert torch.equal(e["voxel"], a["voxel"])
+
+
+# ---- throughput kernel (csrc/v2e_fast.cu): forced on small shapes with V2V_V2E_FAST=1 ---------------------------
+
+_FAST_NONE = {
+    "clean_f32state": dict(cutoff_hz=0.0, leak_rate_hz=0.0),
+    "cutoff": dict(cutoff_hz=30.0, leak_rate_hz=0.0),
+    "leak": dict(cutoff_hz=0.0, leak_rate_hz=0.3),
+    "cutoff_leak": dict(cutoff_hz=15.0, leak_rate_hz=0.2),
+}
+
+
+@pytest.mark.parametrize("preset", sorted(_FAST_NONE))
+@pytest.mark.parametrize("shape", [(13, 64, 96, 1, 1), (8, 40, 52, 1, 1), (13, 32, 36, 3, 2), (2, 16, 16, 1, 1)])
+def test_v2e_fast_kernel_noise_free_vs_oracle(cuda_device, monkeypatch, preset, shape):
+    """Low-pass / leak / float32-state arithmetic of the throughput kernel == NumPy oracle, counts bit-exact
+    (ragged interval counts, frames_per_bin > 1, hard HDR-degraded contrast so that multi-threshold crossings occur)."""
+    from v2v_b200.v2e import frames_to_voxel_v2e
+    monkeypatch.setenv("V2V_V2E_FAST", "1")
+    n, h, w, bins, fpb = shape
+    kw = _FAST_NONE[preset]
+    vid = synth_video("walk", n, h, w, 31)
+    vid = np.clip((vid - 127.5) * 2.6 + 127.5, 0, 255).astype(np.uint8)
+    p = dict(threshold_model="pn_related", thres_mean_mean=0.2, thres_mean_std=0.05, thres_diff_mean=0.0, thres_diff_std=0.05,
+             shot_noise_rate_hz=0.0, leak_jitter_fraction=0.0, noise_rate_cov_decades=0.1, **kw)
+    rec = {}
+    np.random.seed(11)
+    ref = orc.v2e_video_to_voxel(vid.astype(np.float64), 24, p, np.random, record=rec)          # [n-1,h,w]
+    fr = torch.from_numpy(vid).to(cuda_device)
+    before = _launches()
+    out = frames_to_voxel_v2e(fr, rec["pos_thres"][None], rec["neg_thres"][None], fps=24, num_bins=bins, frames_per_bin=fpb,
+                              noise_rate=rec["noise_rate"][None], pos_thres_nominal=0.2, neg_thres_nominal=0.2, noise="none",
+                              with_stats=True, **kw)
+    assert _launches() == before + 1
+    got = out["voxel"][0].cpu().numpy().astype(np.float64)                                       # [T,bins,h,w]
+    T = (n - 1) // (bins * fpb)
+    assert np.array_equal(got, ref.reshape(T, bins, fpb, h, w).sum(axis=2))
+    # generic kernel on the same input: same voxels and the same event totals
+    monkeypatch.delenv("V2V_V2E_FAST")
+    monkeypatch.setenv("V2V_V2E_GENERIC", "1")
+    gen = frames_to_voxel_v2e(fr, rec["pos_thres"][None], rec["neg_thres"][None], fps=24, num_bins=bins, frames_per_bin=fpb,
+                              noise_rate=rec["noise_rate"][None], pos_thres_nominal=0.2, neg_thres_nominal=0.2, noise="none",
+                              with_stats=True, **kw)
+    assert torch.equal(gen["voxel"], out["voxel"]) and torch.equal(gen["stats"], out["stats"])
+    if fpb == 1:
+        assert int(out["stats"].sum()) == int(np.abs(ref).sum())
+
+
+def _launches():
+    from v2v_b200 import _lib
+    return int(_lib.load().v2v_launch_count())
+
+
+_FAST_PHILOX = {
+    "noisy": dict(cutoff_hz=30.0, leak_rate_hz=0.1, shot_noise_rate_hz=5.0, leak_jitter_fraction=0.1),
+    "leak_jitter": dict(cutoff_hz=0.0, leak_rate_hz=0.5, shot_noise_rate_hz=0.0, leak_jitter_fraction=0.3),
+    "cutoff_shot": dict(cutoff_hz=20.0, leak_rate_hz=0.0, shot_noise_rate_hz=40.0, leak_jitter_fraction=0.0),
+    "leak_shot_heavy": dict(cutoff_hz=0.0, leak_rate_hz=0.2, shot_noise_rate_hz=400.0, leak_jitter_fraction=0.1),
+}
+
+
+@pytest.mark.parametrize("preset", sorted(_FAST_PHILOX))
+@pytest.mark.parametrize("n", [13, 8])
+def test_v2e_fast_kernel_philox_equals_generic_and_replay(cuda_device, monkeypatch, preset, n):
+    """Philox mode: throughput kernel == generic kernel == explicit replay of the dumped fields (bit for bit);
+    `leak_shot_heavy` pushes the Poisson rate to ~8 events per frame so the k >= 3 tail loop runs everywhere."""
+    from v2v_b200.v2e import frames_to_voxel_v2e
+    h, w = 48, 64
+    kw = _FAST_PHILOX[preset]
+    vid = synth_video("walk", n, h, w, 5)
+    vid = np.clip((vid - 127.5) * 2.0 + 127.5, 0, 255).astype(np.uint8)
+    fr = torch.from_numpy(np.stack([vid, vid[::-1].copy()])).to(cuda_device)                    # B = 2
+    g = np.random.Generator(np.random.PCG64(2))
+    pos = np.clip(g.normal(0.2, 0.05, (2, h, w)), 0.01, None)
+    neg = np.clip(g.normal(0.2, 0.05, (2, h, w)), 0.01, None)
+    nrate = np.exp(np.log(10) * 0.1 * g.standard_normal((2, h, w)).astype(np.float32)).astype(np.float32)
+    common = dict(fps=24, noise_rate=nrate, with_stats=True, **kw)
+    monkeypatch.setenv("V2V_V2E_FAST", "1")
+    fast = frames_to_voxel_v2e(fr, pos, neg, noise="philox", seed=9, clip_index_base=3, return_fields=True, **common)
+    monkeypatch.delenv("V2V_V2E_FAST")
+    monkeypatch.setenv("V2V_V2E_GENERIC", "1")
+    gen = frames_to_voxel_v2e(fr, pos, neg, noise="philox", seed=9, clip_index_base=3, **common)
+    assert torch.equal(fast["voxel"], gen["voxel"]) and torch.equal(fast["stats"], gen["stats"])
+    f = fast["fields"]
+    rep = frames_to_voxel_v2e(fr, pos, neg, noise="explicit",
+                              leak_randn=f["leak_randn"] if kw["leak_rate_hz"] > 0 else None,
+                              pos_shot=f["pos_shot"] if kw["shot_noise_rate_hz"] > 0 else None,
+                              neg_shot=f["neg_shot"] if kw["shot_noise_rate_hz"] > 0 else None, **common)
+    assert torch.equal(fast["voxel"], rep["voxel"]) and torch.equal(fast["stats"], rep["stats"])
+    if kw["shot_noise_rate_hz"] > 0:
+        lam = kw["shot_noise_rate_hz"] / 2 / 24
+        m = float(f["pos_shot"].double().mean())
+        assert abs(m - lam) / lam < 0.05
+        if preset == "leak_shot_heavy":
+            assert int(f["pos_shot"].max()) >= 12
+
+
+def test_v2e_fast_kernel_full_size_philox_replay(cuda_device):
+    """Config-3 shape (one HDR-degraded 480x640 clip, noisy preset): the throughput kernel is the default path;
+    its run equals the explicit replay of the fields it drew through the generic kernel."""
+    from v2v_b200.v2e import frames_to_voxel_v2e
+    n, h, w = 21, 480, 640
+    vid = synth_video("walk", n, h, w, 77)
+    vid = np.clip((vid - 127.5) * 2.3 + 127.5, 0, 255).astype(np.uint8)
+    fr = torch.from_numpy(vid).to(cuda_device)
+    g = np.random.Generator(np.random.PCG64(4))
+    pos = np.clip(g.normal(0.2, 0.05, (1, h, w)), 0.01, None)
+    neg = np.clip(g.normal(0.2, 0.05, (1, h, w)), 0.01, None)
+    nrate = np.exp(np.log(10) * 0.1 * g.standard_normal((1, h, w)).astype(np.float32)).astype(np.float32)
+    common = dict(fps=24, num_bins=5, cutoff_hz=30.0, leak_rate_hz=0.1, shot_noise_rate_hz=5.0, leak_jitter_fraction=0.1,
+                  noise_rate=nrate, with_stats=True)
+    a = frames_to_voxel_v2e(fr, pos, neg, noise="philox", seed=21, return_fields=True, **common)
+    f = a["fields"]
+    e = frames_to_voxel_v2e(fr, pos, neg, noise="explicit", leak_randn=f["leak_randn"], pos_shot=f["pos_shot"],
+                            neg_shot=f["neg_shot"], **common)
+    assert torch.equal(a["voxel"], e["voxel"]) and torch.equal(a["stats"], e["stats"])
+    assert int(a["stats"].sum()) > 0

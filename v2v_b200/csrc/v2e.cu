@@ -11,66 +11,15 @@
 // brightness `base` and `diff` are float32 only when neither the low-pass nor
 // the leak runs (state_f32), float64 otherwise; every float64 step is a single
 // correctly rounded operation (no FMA contraction).
-#include "common.cuh"
+#include "v2e_common.cuh"
+
+#include <cstdlib>
 
 namespace v2v {
 namespace {
 
 constexpr int kV2eThreads = 256;
 constexpr int kPF = 4;
-
-struct V2eArgs {
-  v2v_v2e_desc d;
-  int64_t HW;
-  int32_t T, G;
-  double tau;          // 1/(2*pi*cutoff)
-  float leak_hz_f32;   // leak_rate_hz as the float32 it becomes in `leak_rate_hz*noise_rate_array`
-};
-
-__device__ __forceinline__ double count_floor(double a, double thr) {
-  // np.floor_divide(max(diff,0), thr) for a >= thr > 0 (the caller filters a < thr); the reciprocal is only
-  // needed on the rare multi-threshold path
-  if (a < __dadd_rn(thr, thr)) return 1.0;
-  return floor_div_exact(a, thr, __drcp_rn(thr));
-}
-
-// Poisson(lam) by inversion from one uniform; lam is a fraction of an event per frame in every shipped preset,
-// so the first comparison (k = 0) settles ~90 % of the draws.  float32: statistical mode only (the audit hook
-// dumps exactly what this function returns).
-__device__ __forceinline__ int poisson_small(float lam, float u) {
-  if (!(lam > 0.f)) return 0;
-  float p = __expf(-lam), cdf = p;
-  if (u < cdf) return 0;
-  int k = 0;
-  while (u >= cdf && k < 64) {
-    ++k;
-    p *= lam / static_cast<float>(k);
-    cdf += p;
-  }
-  return k;
-}
-
-// Philox draws of the v2e model for one aligned group of 4 pixels and one interval:
-//   call A (tag 1): word k -> pixel k: low 16 bits = shot-noise uniform ON, high 16 bits = OFF  (bin centres)
-//   call B (tag 3): two Box-Muller pairs -> leak jitter normals of pixels 0..3
-__device__ __forceinline__ void v2e_group_draw(uint64_t g4, uint32_t interval, uint64_t clip_id, uint2 key, bool leak, bool shot,
-                                               float (&lz)[4], float (&up)[4], float (&un)[4]) {
-  const uint32_t hi = (static_cast<uint32_t>(g4 >> 32) & 0x3fffu) << 16 | static_cast<uint32_t>((clip_id >> 32) & 0xffffu);
-  if (shot) {
-    const uint4 r = Philox::run(make_uint4(static_cast<uint32_t>(g4), interval, static_cast<uint32_t>(clip_id), 0x40000000u | hi), key);
-    const uint32_t w[4] = {r.x, r.y, r.z, r.w};
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      up[k] = (static_cast<float>(w[k] & 0xffffu) + 0.5f) * (1.0f / 65536.0f);
-      un[k] = (static_cast<float>(w[k] >> 16) + 0.5f) * (1.0f / 65536.0f);
-    }
-  }
-  if (leak) {
-    const uint4 r = Philox::run(make_uint4(static_cast<uint32_t>(g4), interval, static_cast<uint32_t>(clip_id), 0xC0000000u | hi), key);
-    const float2 p0 = box_muller(r.x, r.y), p1 = box_muller(r.z, r.w);
-    lz[0] = p0.x; lz[1] = p0.y; lz[2] = p1.x; lz[3] = p1.y;
-  }
-}
 
 __device__ __forceinline__ uint32_t load_pix4(const uint8_t* p) { return ld_stream_u32(p); }
 
@@ -80,13 +29,12 @@ struct V2eLuts {
   float facf[256];     // 1 - 0.75*inten as float (shot-noise rate factor) (:90)
 };
 
-// shot-noise Poisson rate of one pixel (float32, statistical mode): fac(v) * nominal/thres * per-frame scale (:90-99)
-__device__ __forceinline__ float v2e_shot_lambda(float facf, float pre_prob, float scale) { return facf * pre_prob * scale; }
-
 template <int P, bool F32STATE, bool CUTOFF, bool LEAK, bool SHOT>
 __global__ void __launch_bounds__(kV2eThreads) v2e_kernel(const V2eArgs a) {
   __shared__ V2eLuts L;
+  __shared__ float2 trig_s[LEAK ? kTrigEntries : 1];
   const v2v_v2e_desc& d = a.d;
+  if (LEAK && d.noise_mode == V2V_NOISE_PHILOX) fill_trig_table(trig_s);
   for (int i = threadIdx.x; i < 256; i += kV2eThreads) {
     L.logv[i] = d.lut[i];
     const double it = __ddiv_rn(__dadd_rn(static_cast<double>(i), 20.0), 275.0);
@@ -101,7 +49,6 @@ __global__ void __launch_bounds__(kV2eThreads) v2e_kernel(const V2eArgs a) {
   const int N = d.N;
   const int64_t mp = static_cast<int64_t>(b) * HW + pix0;
   const uint64_t clip_id = d.clip_index_base + static_cast<uint64_t>(b);
-  const uint2 key = make_uint2(static_cast<uint32_t>(d.seed), static_cast<uint32_t>(d.seed >> 32));
   const bool philox = d.noise_mode == V2V_NOISE_PHILOX, explicit_noise = d.noise_mode == V2V_NOISE_EXPLICIT;
 
   double pth[P], nth[P], lp[P], base[P];
@@ -178,8 +125,16 @@ __global__ void __launch_bounds__(kV2eThreads) v2e_kernel(const V2eArgs a) {
           for (int k = 0; k < P; ++k) { sp[k] = d.pos_shot[fo + k]; sn[k] = d.neg_shot[fo + k]; }
         }
       } else if (philox && (LEAK || SHOT)) {
-        float lz[4] = {0.f, 0.f, 0.f, 0.f}, up[4] = {1.f, 1.f, 1.f, 1.f}, un[4] = {1.f, 1.f, 1.f, 1.f};
-        v2e_group_draw(static_cast<uint64_t>(pix0) >> 2, static_cast<uint32_t>(i - 1), clip_id, key, LEAK, SHOT, lz, up, un);
+        float lz[4] = {0.f, 0.f, 0.f, 0.f}, lo[4] = {0.f, 0.f, 0.f, 0.f}, up[4] = {1.f, 1.f, 1.f, 1.f}, un[4] = {1.f, 1.f, 1.f, 1.f};
+        const uint64_t g4 = static_cast<uint64_t>(pix0) >> 2;
+        if (SHOT) v2e_shot_uniforms(g4, static_cast<uint32_t>(i - 1), clip_id, a.rk, up, un);
+        if (LEAK) {
+          v2e_leak_normals(g4, static_cast<uint32_t>(i - 1) >> 1, clip_id, a.rk, trig_s, lz, lo);
+          if ((i - 1) & 1) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) lz[k] = lo[k];
+          }
+        }
 #pragma unroll
         for (int k = 0; k < P; ++k) {
           const int j = P == 4 ? k : static_cast<int>(pix0 & 3);
@@ -317,20 +272,29 @@ __global__ void v2e_shot_finalize_kernel(const V2eArgs a, double* pos_scale, dou
 
 // Audit hook: the random fields a PHILOX run draws, for explicit replay / oracle checks.
 __global__ void v2e_philox_fields_kernel(const V2eArgs a, double* leak_randn, int32_t* pos_shot, int32_t* neg_shot) {
+  __shared__ float2 trig_s[kTrigEntries];
+  fill_trig_table(trig_s);
+  __syncthreads();
   const v2v_v2e_desc& d = a.d;
   const int b = blockIdx.y;
   const int64_t pix = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (pix >= a.HW) return;
   const uint64_t clip_id = d.clip_index_base + static_cast<uint64_t>(b);
-  const uint2 key = make_uint2(static_cast<uint32_t>(d.seed), static_cast<uint32_t>(d.seed >> 32));
   const bool shot = d.shot_noise_rate_hz > 0.0, leak = d.leak_rate_hz > 0.0;
   const int64_t mp = static_cast<int64_t>(b) * a.HW + pix;
   const float ppf = static_cast<float>(__ddiv_rn(d.pos_thres_nominal, d.pos_thres[mp]));
   const float npf = static_cast<float>(__ddiv_rn(d.neg_thres_nominal, d.neg_thres[mp]));
   const int j = static_cast<int>(pix & 3);
   for (int i = 1; i < d.N; ++i) {
-    float lz[4] = {0.f, 0.f, 0.f, 0.f}, up[4] = {1.f, 1.f, 1.f, 1.f}, un[4] = {1.f, 1.f, 1.f, 1.f};
-    v2e_group_draw(static_cast<uint64_t>(pix) >> 2, static_cast<uint32_t>(i - 1), clip_id, key, leak, shot, lz, up, un);
+    float lz[4] = {0.f, 0.f, 0.f, 0.f}, lo[4] = {0.f, 0.f, 0.f, 0.f}, up[4] = {1.f, 1.f, 1.f, 1.f}, un[4] = {1.f, 1.f, 1.f, 1.f};
+    const uint64_t g4 = static_cast<uint64_t>(pix) >> 2;
+    if (shot) v2e_shot_uniforms(g4, static_cast<uint32_t>(i - 1), clip_id, a.rk, up, un);
+    if (leak) {
+      v2e_leak_normals(g4, static_cast<uint32_t>(i - 1) >> 1, clip_id, a.rk, trig_s, lz, lo);
+      if ((i - 1) & 1) {
+        for (int k = 0; k < 4; ++k) lz[k] = lo[k];
+      }
+    }
     const int64_t o = (static_cast<int64_t>(b) * (d.N - 1) + (i - 1)) * a.HW + pix;
     if (leak_randn) leak_randn[o] = static_cast<double>(lz[j]);
     if (shot && pos_shot && neg_shot) {
@@ -357,6 +321,7 @@ int validate(const v2v_v2e_desc& d, V2eArgs* a) {
   a->T = (d.N - 1) / a->G;
   a->tau = d.cutoff_hz > 0.0 ? 1.0 / (3.141592653589793 * 2 * d.cutoff_hz) : 0.0;    // :162
   a->leak_hz_f32 = static_cast<float>(d.leak_rate_hz);
+  Philox::round_keys(d.seed, a->rk);
   return V2V_OK;
 }
 
@@ -378,6 +343,7 @@ extern "C" int v2v_v2e_frames_to_voxel(const v2v_v2e_desc* desc, void* stream) {
   if (d.noise_mode == V2V_NOISE_PHILOX && d.shot_noise_rate_hz > 0.0)
     V2V_REQUIRE(d.shot_pos_scale && d.shot_neg_scale, V2V_ERR_INVALID_ARG, "PHILOX shot noise needs the scales from v2v_v2e_shot_scales");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (v2e_fast_eligible(a) && !getenv("V2V_V2E_GENERIC")) return launch_v2e_fast(a, s);
   const bool vec4 = (a.HW % 4 == 0) && aligned(d.frames, 4) && aligned(d.voxel, 16) &&
                     static_cast<int64_t>(d.B) * a.HW >= 148LL * 2048;
   const int P = vec4 ? 4 : 1;

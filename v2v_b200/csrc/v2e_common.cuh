@@ -1,0 +1,107 @@
+// Shared pieces of the v2e kernels: launch arguments, the counter-based random draws and the exact count helper.
+#pragma once
+#include "common.cuh"
+
+namespace v2v {
+
+struct V2eArgs {
+  v2v_v2e_desc d;
+  int64_t HW;
+  int32_t T, G;
+  double tau;          // 1/(2*pi*cutoff)
+  float leak_hz_f32;   // leak_rate_hz as the float32 it becomes in `leak_rate_hz*noise_rate_array`
+  uint32_t rk[20];     // Philox round keys of d.seed (host-precomputed)
+};
+
+// np.floor_divide(max(diff,0), thr) for a >= thr > 0 (the caller filters a < thr); the reciprocal is only
+// needed on the multi-threshold path
+__device__ __forceinline__ double count_floor(double a, double thr) {
+  if (a < __dadd_rn(thr, thr)) return 1.0;
+  return floor_div_exact(a, thr, __drcp_rn(thr));
+}
+
+// ---- Philox draws of the v2e model -------------------------------------------------------------------------
+// Every kernel (generic, fast, field dump) draws the same values for the same (seed, clip, pixel, interval),
+// independent of launch geometry.  Per aligned group of 4 pixels:
+//   shot noise : one call per interval, counter (group lo32, interval, clip lo32, tag1|group hi|clip hi16);
+//                word k -> pixel k: low 16 bits = uniform of the ON draw, high 16 bits = OFF draw (bin centres)
+//   leak jitter: one call per PAIR of intervals, counter (group lo32, interval/2, clip lo32, tag3|...);
+//                word k -> pixel k: one Box-Muller pair, .x for the even interval, .y for the odd one
+__device__ __forceinline__ uint32_t v2e_ctr_hi(uint64_t g4, uint64_t clip_id) {
+  return (static_cast<uint32_t>(g4 >> 32) & 0x3fffu) << 16 | static_cast<uint32_t>((clip_id >> 32) & 0xffffu);
+}
+
+// (h + 0.5) / 65536 for a 16-bit h, through the mantissa (no int->float conversion)
+__device__ __forceinline__ float v2e_u16(uint32_t h) {
+  return __uint_as_float(0x3f800000u | (h << 7)) - 0.99999237060546875f;
+}
+
+__device__ __forceinline__ void v2e_shot_uniforms(uint64_t g4, uint32_t interval, uint64_t clip_id, const uint32_t (&rk)[20],
+                                                  float (&up)[4], float (&un)[4]) {
+  const uint4 r = Philox::run_rk(make_uint4(static_cast<uint32_t>(g4), interval, static_cast<uint32_t>(clip_id),
+                                            0x40000000u | v2e_ctr_hi(g4, clip_id)), rk);
+  const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    up[k] = v2e_u16(w[k] & 0xffffu);
+    un[k] = v2e_u16(w[k] >> 16);
+  }
+}
+
+__device__ __forceinline__ void v2e_leak_normals(uint64_t g4, uint32_t pair, uint64_t clip_id, const uint32_t (&rk)[20],
+                                                 const float2* trig, float (&even)[4], float (&odd)[4]) {
+  const uint4 r = Philox::run_rk(make_uint4(static_cast<uint32_t>(g4), pair, static_cast<uint32_t>(clip_id),
+                                            0xC0000000u | v2e_ctr_hi(g4, clip_id)), rk);
+  const float c2 = -1.3862943611198906f;      // -2 ln 2: unit variance
+  const float2 p0 = box_muller16(r.x, c2, trig), p1 = box_muller16(r.y, c2, trig), p2 = box_muller16(r.z, c2, trig),
+               p3 = box_muller16(r.w, c2, trig);
+  even[0] = p0.x; odd[0] = p0.y;
+  even[1] = p1.x; odd[1] = p1.y;
+  even[2] = p2.x; odd[2] = p2.y;
+  even[3] = p3.x; odd[3] = p3.y;
+}
+
+// shot-noise Poisson rate of one pixel (float32, statistical mode): fac(v) * nominal/thres * per-frame scale (:90-99)
+// (clamped at 0: a negative or NaN rate draws no events in every kernel)
+__device__ __forceinline__ float v2e_shot_lambda(float facf, float pre_prob, float scale) {
+  return fmaxf(__fmul_rn(__fmul_rn(facf, pre_prob), scale), 0.f);
+}
+
+// Poisson(lam) by inversion from one uniform.  lam is a fraction of an event per frame in every shipped preset:
+// the first three CDF steps are straight-line code (k <= 2 covers all but ~lam^3/6 of the draws), the tail is a loop.
+// float32: statistical mode only (the audit hook dumps exactly what this function returns).
+struct PoissonCdf {
+  float c0, c1, c2, p2;
+};
+__device__ __forceinline__ PoissonCdf poisson_cdf(float lam) {
+  PoissonCdf c;
+  float p0;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(p0) : "f"(__fmul_rn(lam, -1.4426950408889634f)));
+  const float t = __fmul_rn(p0, lam);
+  c.c0 = p0;
+  c.c1 = __fadd_rn(p0, t);
+  c.p2 = __fmul_rn(t, __fmul_rn(0.5f, lam));
+  c.c2 = __fadd_rn(c.c1, c.p2);
+  return c;
+}
+static __device__ __noinline__ int poisson_tail(float lam, float u, float p2, float c2) {      // u >= c2: k >= 3 (rare)
+  int k = 2;
+  float p = p2, cdf = c2;
+  while (u >= cdf && k < 64) {
+    ++k;
+    p = __fmul_rn(p, __fdiv_rn(lam, static_cast<float>(k)));
+    cdf = __fadd_rn(cdf, p);
+  }
+  return k;
+}
+__device__ __forceinline__ int poisson_small(float lam, float u) {
+  if (!(lam > 0.f)) return 0;
+  const PoissonCdf c = poisson_cdf(lam);
+  if (u >= c.c2) return poisson_tail(lam, u, c.p2, c.c2);
+  return (u >= c.c0 ? 1 : 0) + (u >= c.c1 ? 1 : 0);
+}
+
+int launch_v2e_fast(const V2eArgs& a, cudaStream_t s);      // v2e_fast.cu
+bool v2e_fast_eligible(const V2eArgs& a);
+
+}  // namespace v2v

@@ -1,0 +1,336 @@
+// v2e-style frames -> voxel: the throughput kernel (noise none or in-kernel Philox, 4-pixel groups).
+//
+// Same arithmetic as the generic kernel in v2e.cu (reference data/v2v_core_v2e.py:401-581), restructured the way
+// esim_fast.cu is: 128-thread CTAs, 4 pixels per lane, everything that is the same for all pixels of a frame
+// (t = k/fps, dt, dt/tau, the shot-noise scales) computed once per CTA into a shared-memory table instead of
+// two float64 divisions per lane and frame, Philox with host-precomputed round keys, three generator calls per
+// two intervals (shot uniforms per interval, leak normals per interval pair), Poisson inversion as straight-line
+// code for k <= 2, and the single-threshold crossing handled without branches:
+//   pe, ne in {0,1} as float64 built from the compare predicates (high-word selects), shot counts added as float64,
+//   base += pe*pth; base -= ne*nth as separately rounded multiply and add (exact for any count, :547-548).
+// Multi-threshold crossings take the exact floor-division path (per lane, only where |diff| >= 2*min threshold).
+#include "v2e_common.cuh"
+
+#include <cstdlib>
+
+namespace v2v {
+namespace {
+
+constexpr int kThreads = 128;
+constexpr int kPF = 4;             // frames per loop trip (two interval pairs)
+constexpr int kMaxIntervals = 1024;
+
+struct __align__(16) IntervalRow {  // one row per frame interval, identical for every pixel of the clip
+  double dt;                        // t_k - t_{k-1}, t_k = k/fps                 (:442,577)
+  double qdt;                       // dt / tau                                   (:167)
+  float sps, sns;                   // float32 shot-noise scales of this frame    (:98-99)
+  float pad[2];
+};
+
+constexpr int kLutBytes = 256 * 16, kFacBytes = 256 * 4, kLogfBytes = 256 * 4, kTrigBytes = kTrigEntries * 8;
+
+__device__ __forceinline__ double hi_double(int hi) { return __hiloint2double(hi, 0); }
+
+template <bool F32STATE, bool CUTOFF, bool LEAK, bool SHOT, bool PHILOX>
+__global__ void __launch_bounds__(kThreads, 4) v2e_fast_kernel(const V2eArgs a) {
+  extern __shared__ __align__(16) unsigned char dyn[];
+  double2* lut2 = reinterpret_cast<double2*>(dyn);                                   // {double(logv), (v+20)/275}
+  float* facf_s = reinterpret_cast<float*>(dyn + kLutBytes);                        // 1 - 0.75*inten as float
+  float* logf_s = reinterpret_cast<float*>(dyn + kLutBytes + kFacBytes);            // float32 log LUT (float32-state path)
+  float2* trig_s = reinterpret_cast<float2*>(dyn + kLutBytes + kFacBytes + kLogfBytes);
+  IntervalRow* itab = reinterpret_cast<IntervalRow*>(dyn + kLutBytes + kFacBytes + kLogfBytes + (LEAK && PHILOX ? kTrigBytes : 0));
+  __shared__ unsigned long long cta_stats[2];
+
+  const v2v_v2e_desc& d = a.d;
+  const int N = d.N, b = blockIdx.y;
+  if (LEAK && PHILOX) fill_trig_table(trig_s);
+  if (threadIdx.x < 2) cta_stats[threadIdx.x] = 0ull;
+  for (int i = threadIdx.x; i < 256; i += kThreads) {
+    const double it = __ddiv_rn(__dadd_rn(static_cast<double>(i), 20.0), 275.0);       // :190
+    lut2[i] = make_double2(static_cast<double>(d.lut[i]), it);
+    facf_s[i] = static_cast<float>(__dsub_rn(1.0, __dmul_rn(0.75, it)));              // :90
+    logf_s[i] = d.lut[i];
+  }
+  for (int i = 1 + threadIdx.x; i < N; i += kThreads) {
+    IntervalRow r;
+    const double t_k = __ddiv_rn(static_cast<double>(i), d.fps);                       // :577
+    const double t_p = i == 1 ? 0.0 : __ddiv_rn(static_cast<double>(i - 1), d.fps);
+    r.dt = __dsub_rn(t_k, t_p);                                                        // :442
+    r.qdt = CUTOFF ? __ddiv_rn(r.dt, a.tau) : 0.0;                                     // :167
+    r.sps = r.sns = r.pad[0] = r.pad[1] = 0.f;
+    if (SHOT) {
+      const int64_t si = static_cast<int64_t>(b) * (N - 1) + (i - 1);
+      r.sps = static_cast<float>(d.shot_pos_scale[si]);
+      r.sns = static_cast<float>(d.shot_neg_scale[si]);
+    }
+    itab[i - 1] = r;
+  }
+  __syncthreads();
+
+  const int64_t pix0 = (static_cast<int64_t>(blockIdx.x) * kThreads + threadIdx.x) * 4;
+  const int64_t HW = a.HW;
+  const bool want_stats = d.stats != nullptr;
+  if (pix0 < HW) {
+  const int64_t mp = static_cast<int64_t>(b) * HW + pix0;
+  const uint64_t clip_id = d.clip_index_base + static_cast<uint64_t>(b);
+  const uint64_t g4 = static_cast<uint64_t>(pix0) >> 2;
+
+  double pth[4], nth[4], lp[4], base[4];
+  float basef[F32STATE ? 4 : 1], pthf[F32STATE ? 4 : 1], nthf[F32STATE ? 4 : 1];
+  double r32d[LEAK ? 4 : 1];
+  float ppf[SHOT ? 4 : 1], npf[SHOT ? 4 : 1];
+  double thr2 = 1e300;
+  {
+    const double2 p01 = ld_stream_f64x2(d.pos_thres + mp), p23 = ld_stream_f64x2(d.pos_thres + mp + 2);
+    const double2 n01 = ld_stream_f64x2(d.neg_thres + mp), n23 = ld_stream_f64x2(d.neg_thres + mp + 2);
+    pth[0] = p01.x, pth[1] = p01.y, pth[2] = p23.x, pth[3] = p23.y;
+    nth[0] = n01.x, nth[1] = n01.y, nth[2] = n23.x, nth[3] = n23.y;
+  }
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    thr2 = fmin(thr2, fmin(pth[k], nth[k]));
+    if (LEAK) r32d[LEAK ? k : 0] = static_cast<double>(__fmul_rn(a.leak_hz_f32, d.noise_rate ? d.noise_rate[mp + k] : 1.0f));   // :205
+    if (SHOT) {                                                                      // :396-399
+      ppf[SHOT ? k : 0] = static_cast<float>(__ddiv_rn(d.pos_thres_nominal, pth[k]));
+      npf[SHOT ? k : 0] = static_cast<float>(__ddiv_rn(d.neg_thres_nominal, nth[k]));
+    }
+    if (F32STATE) {      // float32 diff compared with float64 thresholds: diff >= thr  <=>  diff >= RU_f32(thr)
+      pthf[F32STATE ? k : 0] = __double2float_ru(pth[k]);
+      nthf[F32STATE ? k : 0] = __double2float_ru(nth[k]);
+    }
+  }
+  thr2 = __dadd_rn(thr2, thr2);       // below 2*min(threshold) of this lane's pixels at most one threshold is crossed
+  const float thr2f = __double2float_rd(thr2);
+
+  const uint8_t* fr = d.frames + static_cast<int64_t>(b) * N * HW + pix0;
+  {
+    // first frame: lp = log_new; the filter runs with dt = 0 (eps = 0); base = lp   (:463-478)
+    const uint32_t w0 = ld_stream_u32(fr);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const double l0 = lut2[(w0 >> (8 * k)) & 0xffu].x;
+      lp[k] = CUTOFF ? __dadd_rn(__dmul_rn(1.0, l0), __dmul_rn(0.0, l0)) : l0;
+      base[k] = lp[k];
+      if (F32STATE) basef[F32STATE ? k : 0] = static_cast<float>(l0);
+    }
+  }
+
+  float* vox = d.voxel + static_cast<int64_t>(b) * a.T * d.num_bins * HW + pix0;
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  double dpos = 0.0, dneg = 0.0;      // event totals of this lane (exact integers in float64)
+  int sub = 0;
+  const int fpb = d.frames_per_bin;
+  const double jit = d.leak_jitter_fraction;
+
+  auto byte_of = [](uint32_t w, int k) -> uint32_t {
+    uint32_t v;
+    asm("prmt.b32 %0, %1, 0, %2;" : "=r"(v) : "r"(w), "r"(0x4440u | static_cast<uint32_t>(k)));
+    return v;
+  };
+
+  // one frame interval for the lane's 4 pixels; lz = leak jitter normals, (up, un) = shot uniforms
+  auto step = [&](const uint32_t w, const int iv, const float (&lz)[4], const float (&up)[4], const float (&un)[4]) {
+    const IntervalRow row = itab[iv];
+    float outv[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const uint32_t v = byte_of(w, k);
+      double pe, ne;          // threshold-crossing counts as float64 (:55-60)
+      float of;               // pe - ne as float32 (the voxel contribution), kept beside them to stay off the conversion unit
+      if (F32STATE) {
+        const float lognew = logf_s[v];                                               // :447 (lp == log_new)
+        const float df = __fsub_rn(lognew, basef[F32STATE ? k : 0]);                    // :503 in float32
+        const bool upc = df >= pthf[F32STATE ? k : 0], dnc = -df >= nthf[F32STATE ? k : 0];
+        pe = hi_double(upc ? 0x3ff00000 : 0);
+        ne = hi_double(dnc ? 0x3ff00000 : 0);
+        of = upc ? 1.0f : 0.0f;
+        of = dnc ? -1.0f : of;
+        if (fabsf(df) >= thr2f) {                                                      // possibly several thresholds: exact path
+          const double diff = static_cast<double>(df);
+          if (diff >= pth[k]) pe = count_floor(diff, pth[k]);
+          else if (-diff >= nth[k]) ne = count_floor(-diff, nth[k]);
+          of = static_cast<float>(__dsub_rn(pe, ne));
+        }
+        // :547-548 — in place on a float32 array, the float64 sum cast back after each line.  Without shot noise at
+        // most one of pe, ne is non-zero, the other line is the identity: one add of (pe*pth - ne*nth), one cast.
+        const double s = __dsub_rn(__dmul_rn(pe, pth[k]), __dmul_rn(ne, nth[k]));
+        basef[F32STATE ? k : 0] = __double2float_rn(__dadd_rn(static_cast<double>(basef[F32STATE ? k : 0]), s));
+      } else {
+        const double2 lv = lut2[v];                                                    // {log_new, inten01}
+        if (CUTOFF) {                                                                  // :157-173
+          double eps = __dmul_rn(lv.y, row.qdt);
+          eps = fmin(eps, 1.0);
+          lp[k] = __dadd_rn(__dmul_rn(__dsub_rn(1.0, eps), lp[k]), __dmul_rn(eps, lv.x));
+        } else {
+          lp[k] = lv.x;
+        }
+        if (LEAK) {                                                                    // :192-211
+          const double lr = PHILOX ? static_cast<double>(lz[k]) : 0.0;
+          const double rate = __dmul_rn(r32d[LEAK ? k : 0], __dsub_rn(1.0, __dmul_rn(jit, lr)));
+          base[k] = __dsub_rn(base[k], __dmul_rn(__dmul_rn(row.dt, rate), pth[k]));
+        }
+        const double diff = __dsub_rn(lp[k], base[k]);                                 // :503
+        const bool upc = diff >= pth[k], dnc = -diff >= nth[k];
+        pe = hi_double(upc ? 0x3ff00000 : 0);
+        ne = hi_double(dnc ? 0x3ff00000 : 0);
+        of = upc ? 1.0f : 0.0f;
+        of = dnc ? -1.0f : of;
+        if (fabs(diff) >= thr2) {                                                      // possibly several thresholds: exact path
+          if (upc) pe = count_floor(diff, pth[k]);
+          else if (dnc) ne = count_floor(-diff, nth[k]);
+          of = static_cast<float>(__dsub_rn(pe, ne));
+        }
+      }
+      if (SHOT) {                                                                      // :90-103, 530-531
+        const float fac = facf_s[v];
+        const float lam_p = v2e_shot_lambda(fac, ppf[SHOT ? k : 0], row.sps), lam_n = v2e_shot_lambda(fac, npf[SHOT ? k : 0], row.sns);
+        const PoissonCdf cp = poisson_cdf(lam_p), cn = poisson_cdf(lam_n);
+        // k in {0,1,2} from two compares, as the high word of a float64 (0.0, 1.0, 2.0) whose exponent bits are also the
+        // float32 of the same value; k >= 3 (about lam^3/6 of the draws) takes the loop
+        const int hp = up[k] >= cp.c1 ? 0x40000000 : (up[k] >= cp.c0 ? 0x3ff00000 : 0);
+        const int hn = un[k] >= cn.c1 ? 0x40000000 : (un[k] >= cn.c0 ? 0x3ff00000 : 0);
+        double kp = hi_double(hp), kn = hi_double(hn);
+        float kpf = __int_as_float(hp & 0x7f800000), knf = __int_as_float(hn & 0x7f800000);
+        if (up[k] >= cp.c2) {
+          const int kk = poisson_tail(lam_p, up[k], cp.p2, cp.c2);
+          kp = static_cast<double>(kk);
+          kpf = static_cast<float>(kk);
+        }
+        if (un[k] >= cn.c2) {
+          const int kk = poisson_tail(lam_n, un[k], cn.p2, cn.c2);
+          kn = static_cast<double>(kk);
+          knf = static_cast<float>(kk);
+        }
+        pe = __dadd_rn(pe, kp);
+        ne = __dadd_rn(ne, kn);
+        of = __fadd_rn(of, __fsub_rn(kpf, knf));
+      }
+      if (!F32STATE) {
+        // :547-548, unconditionally: a zero count adds 0*thr = 0 and leaves base untouched
+        base[k] = __dadd_rn(base[k], __dmul_rn(pe, pth[k]));
+        base[k] = __dsub_rn(base[k], __dmul_rn(ne, nth[k]));
+      }
+      if (want_stats) {
+        dpos = __dadd_rn(dpos, pe);
+        dneg = __dadd_rn(dneg, ne);
+      }
+      acc[k] += of;                                                                     // :579-580 (integers: exact in float32)
+      outv[k] = acc[k];
+    }
+    if (++sub == fpb) {
+      sub = 0;
+      st_stream_f32x4(vox, outv[0], outv[1], outv[2], outv[3]);
+      vox += HW;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) acc[k] = 0.f;
+    }
+  };
+
+  // ---- main loop: kPF frames per trip, the next trip's words already in flight ----
+  const int M = N - 1;
+  const int trips = M / kPF;
+  uint32_t cur[kPF], nxt[kPF];
+  if (trips > 0) {
+#pragma unroll
+    for (int u = 0; u < kPF; ++u) cur[u] = ld_stream_u32(fr + static_cast<int64_t>(1 + u) * HW);
+  }
+  int i = 1;
+  for (int t = 0; t < trips; ++t) {
+    if (t + 1 < trips) {
+#pragma unroll
+      for (int u = 0; u < kPF; ++u) nxt[u] = ld_stream_u32(fr + static_cast<int64_t>(i + kPF + u) * HW);
+    }
+#pragma unroll
+    for (int h = 0; h < kPF / 2; ++h) {           // interval pairs (i-1+2h, i+2h)
+      float le[4] = {0.f, 0.f, 0.f, 0.f}, lo[4] = {0.f, 0.f, 0.f, 0.f};
+      if (LEAK && PHILOX) v2e_leak_normals(g4, static_cast<uint32_t>(i - 1 + 2 * h) >> 1, clip_id, a.rk, trig_s, le, lo);
+      float up[4] = {1.f, 1.f, 1.f, 1.f}, un[4] = {1.f, 1.f, 1.f, 1.f};
+      if (SHOT) v2e_shot_uniforms(g4, static_cast<uint32_t>(i - 1 + 2 * h), clip_id, a.rk, up, un);
+      step(cur[2 * h], i - 1 + 2 * h, le, up, un);
+      if (SHOT) v2e_shot_uniforms(g4, static_cast<uint32_t>(i + 2 * h), clip_id, a.rk, up, un);
+      step(cur[2 * h + 1], i + 2 * h, lo, up, un);
+    }
+    i += kPF;
+#pragma unroll
+    for (int u = 0; u < kPF; ++u) cur[u] = nxt[u];
+  }
+  for (; i < N; ++i) {                                                   // ragged tail (< kPF intervals)
+    float le[4] = {0.f, 0.f, 0.f, 0.f}, lo[4] = {0.f, 0.f, 0.f, 0.f}, lz[4];
+    if (LEAK && PHILOX) v2e_leak_normals(g4, static_cast<uint32_t>(i - 1) >> 1, clip_id, a.rk, trig_s, le, lo);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) lz[k] = ((i - 1) & 1) ? lo[k] : le[k];
+    float up[4] = {1.f, 1.f, 1.f, 1.f}, un[4] = {1.f, 1.f, 1.f, 1.f};
+    if (SHOT) v2e_shot_uniforms(g4, static_cast<uint32_t>(i - 1), clip_id, a.rk, up, un);
+    step(ld_stream_u32(fr + static_cast<int64_t>(i) * HW), i - 1, lz, up, un);
+  }
+
+  if (want_stats) {
+    const unsigned int m = __activemask();
+    unsigned long long sp = static_cast<unsigned long long>(dpos), sn = static_cast<unsigned long long>(dneg);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const unsigned long long op = __shfl_xor_sync(m, sp, o), on = __shfl_xor_sync(m, sn, o);
+      const bool ok = ((m >> ((threadIdx.x & 31) ^ o)) & 1u) != 0;      // partner lane is active
+      sp += ok ? op : 0ull;
+      sn += ok ? on : 0ull;
+    }
+    if ((threadIdx.x & 31) == (__ffs(m) - 1)) {
+      atomicAdd(&cta_stats[0], sp);
+      atomicAdd(&cta_stats[1], sn);
+    }
+  }
+  }  // valid
+  if (want_stats) {
+    __syncthreads();
+    if (threadIdx.x < 2 && cta_stats[threadIdx.x])
+      atomicAdd(reinterpret_cast<unsigned long long*>(d.stats + 2 * b) + threadIdx.x, cta_stats[threadIdx.x]);
+  }
+}
+
+size_t fast_smem_bytes(const V2eArgs& a, bool trig) {
+  return kLutBytes + kFacBytes + kLogfBytes + (trig ? kTrigBytes : 0) + static_cast<size_t>(a.d.N - 1) * sizeof(IntervalRow);
+}
+
+}  // namespace
+
+bool v2e_fast_eligible(const V2eArgs& a) {
+  const v2v_v2e_desc& d = a.d;
+  if (d.noise_mode == V2V_NOISE_EXPLICIT) return false;
+  if (a.HW % 4 != 0 || !aligned(d.frames, 4) || !aligned(d.voxel, 16) || !aligned(d.pos_thres, 16) || !aligned(d.neg_thres, 16)) return false;
+  if (d.N - 1 > kMaxIntervals) return false;
+  const bool sh = d.shot_noise_rate_hz > 0.0 && d.noise_mode != V2V_NOISE_NONE;
+  if (d.state_f32 && sh) return false;          // float32 state with shot noise: two float32 roundings per update, generic kernel
+  if (getenv("V2V_V2E_FAST")) return true;      // tests: force the fast kernel on small shapes
+  return static_cast<int64_t>(d.B) * a.HW >= 148LL * 2048;
+}
+
+int launch_v2e_fast(const V2eArgs& a, cudaStream_t s) {
+  const v2v_v2e_desc& d = a.d;
+  const int64_t groups = a.HW / 4;
+  dim3 grid(static_cast<unsigned int>((groups + kThreads - 1) / kThreads), static_cast<unsigned int>(d.B));
+  const bool ph = d.noise_mode == V2V_NOISE_PHILOX;
+  const bool cut = d.cutoff_hz > 0.0, lk = d.leak_rate_hz > 0.0, sh = d.shot_noise_rate_hz > 0.0 && ph;
+  const bool leak_variant = !d.state_f32 && (lk || !cut);      // the template's LEAK (a float64 state without cutoff runs the leak variant)
+  const size_t smem = fast_smem_bytes(a, leak_variant && ph);
+#define V2V_K(F32, CU, LK, SH, PH)                                                                                          \
+  do {                                                                                                                      \
+    V2V_CUDA(cudaFuncSetAttribute(v2e_fast_kernel<F32, CU, LK, SH, PH>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem))); \
+    v2e_fast_kernel<F32, CU, LK, SH, PH><<<grid, kThreads, smem, s>>>(a);                                                   \
+  } while (0)
+#define V2V_PHX(F32, CU, LK)                                                     \
+  do {                                                                           \
+    if (ph) { if (sh) V2V_K(F32, CU, LK, true, true); else V2V_K(F32, CU, LK, false, true); } \
+    else V2V_K(F32, CU, LK, false, false);                                       \
+  } while (0)
+  if (d.state_f32) V2V_K(true, false, false, false, false);
+  else if (cut && lk) V2V_PHX(false, true, true);
+  else if (cut) V2V_PHX(false, true, false);
+  else V2V_PHX(false, false, true);
+#undef V2V_PHX
+#undef V2V_K
+  count_launch();
+  V2V_CUDA(cudaGetLastError());
+  return V2V_OK;
+}
+
+}  // namespace v2v
