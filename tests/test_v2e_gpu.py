@@ -126,13 +126,15 @@ _FAST_NONE = {
 }
 
 
+@pytest.mark.parametrize("bf", ["1", "0"])
 @pytest.mark.parametrize("preset", sorted(_FAST_NONE))
 @pytest.mark.parametrize("shape", [(13, 64, 96, 1, 1), (8, 40, 52, 1, 1), (13, 32, 36, 3, 2), (2, 16, 16, 1, 1)])
-def test_v2e_fast_kernel_noise_free_vs_oracle(cuda_device, monkeypatch, preset, shape):
+def test_v2e_fast_kernel_noise_free_vs_oracle(cuda_device, monkeypatch, preset, shape, bf):
     """Low-pass / leak / float32-state arithmetic of the throughput kernel == NumPy oracle, counts bit-exact
     (ragged interval counts, frames_per_bin > 1, hard HDR-degraded contrast so that multi-threshold crossings occur)."""
     from v2v_b200.v2e import frames_to_voxel_v2e
     monkeypatch.setenv("V2V_V2E_FAST", "1")
+    monkeypatch.setenv("V2V_V2E_BF", bf)          # exact division on every pixel / single-crossing fast path + divergent exact path
     n, h, w, bins, fpb = shape
     kw = _FAST_NONE[preset]
     vid = synth_video("walk", n, h, w, 31)
@@ -175,9 +177,10 @@ _FAST_PHILOX = {
 }
 
 
+@pytest.mark.parametrize("bf", ["1", "0"])
 @pytest.mark.parametrize("preset", sorted(_FAST_PHILOX))
 @pytest.mark.parametrize("n", [13, 8])
-def test_v2e_fast_kernel_philox_equals_generic_and_replay(cuda_device, monkeypatch, preset, n):
+def test_v2e_fast_kernel_philox_equals_generic_and_replay(cuda_device, monkeypatch, preset, n, bf):
     """Philox mode: throughput kernel == generic kernel == explicit replay of the dumped fields (bit for bit);
     `leak_shot_heavy` pushes the Poisson rate to ~8 events per frame so the k >= 3 tail loop runs everywhere."""
     from v2v_b200.v2e import frames_to_voxel_v2e
@@ -192,6 +195,7 @@ def test_v2e_fast_kernel_philox_equals_generic_and_replay(cuda_device, monkeypat
     nrate = np.exp(np.log(10) * 0.1 * g.standard_normal((2, h, w)).astype(np.float32)).astype(np.float32)
     common = dict(fps=24, noise_rate=nrate, with_stats=True, **kw)
     monkeypatch.setenv("V2V_V2E_FAST", "1")
+    monkeypatch.setenv("V2V_V2E_BF", bf)
     fast = frames_to_voxel_v2e(fr, pos, neg, noise="philox", seed=9, clip_index_base=3, return_fields=True, **common)
     monkeypatch.delenv("V2V_V2E_FAST")
     monkeypatch.setenv("V2V_V2E_GENERIC", "1")
@@ -231,3 +235,28 @@ def test_v2e_fast_kernel_full_size_philox_replay(cuda_device):
                             neg_shot=f["neg_shot"], **common)
     assert torch.equal(a["voxel"], e["voxel"]) and torch.equal(a["stats"], e["stats"])
     assert int(a["stats"].sum()) > 0
+
+
+@pytest.mark.parametrize("shape", [(2, 9, 48, 64), (1, 5, 30, 34), (3, 4, 480, 640)])
+def test_v2e_shot_scales_match_numpy(cuda_device, shape):
+    """Per-frame Poisson normalisers (data/v2v_core_v2e.py:90-99): (rate/2*dt) / mean(inten_factor * nominal/thres),
+    fixed-point accumulation -> equal to the float64 NumPy means to ~1e-10 and bit-identical from run to run."""
+    from v2v_b200.v2e import frames_to_voxel_v2e
+    B, n, h, w = shape
+    g = np.random.Generator(np.random.PCG64(12))
+    vid = g.integers(0, 256, (B, n, h, w), dtype=np.uint8)
+    pos = np.clip(g.normal(0.2, 0.05, (B, h, w)), 0.01, None)
+    neg = np.clip(g.normal(0.25, 0.05, (B, h, w)), 0.01, None)
+    fr = torch.from_numpy(vid).to(cuda_device)
+    kw = dict(fps=24, cutoff_hz=10.0, shot_noise_rate_hz=5.0, pos_thres_nominal=0.2, neg_thres_nominal=0.25, noise="philox", seed=1)
+    a = frames_to_voxel_v2e(fr, pos, neg, **kw)
+    b = frames_to_voxel_v2e(fr, pos, neg, **kw)
+    assert torch.equal(a["shot_scales"], b["shot_scales"]) and torch.equal(a["voxel"], b["voxel"])
+    fac = 1 - 0.75 * ((vid[:, 1:].astype(np.float64) + 20) / 275.0)                      # [B,n-1,h,w]
+    k = np.arange(1, n, dtype=np.float64)
+    dt = k / 24 - (k - 1) / 24
+    for pol, thr, nom in ((0, pos, 0.2), (1, neg, 0.25)):
+        mean = (fac * (nom / thr)[:, None]).mean(axis=(2, 3))
+        ref = (5.0 / 2) * dt[None] / mean
+        got = a["shot_scales"][pol].cpu().numpy()
+        assert np.allclose(got, ref, rtol=1e-9, atol=0)

@@ -13,6 +13,7 @@
 // correctly rounded operation (no FMA contraction).
 #include "v2e_common.cuh"
 
+#include <algorithm>
 #include <cstdlib>
 
 namespace v2v {
@@ -59,8 +60,8 @@ __global__ void __launch_bounds__(kV2eThreads) v2e_kernel(const V2eArgs a) {
     nth[k] = d.neg_thres[mp + k];
     if (LEAK) nrate[LEAK ? k : 0] = d.noise_rate ? d.noise_rate[mp + k] : 1.0f;
     if (SHOT) {                                                                    // :396-399
-      ppf[SHOT ? k : 0] = static_cast<float>(__ddiv_rn(d.pos_thres_nominal, pth[k]));
-      npf[SHOT ? k : 0] = static_cast<float>(__ddiv_rn(d.neg_thres_nominal, nth[k]));
+      ppf[SHOT ? k : 0] = v2e_pre_prob(d.pos_thres_nominal, pth[k]);
+      npf[SHOT ? k : 0] = v2e_pre_prob(d.neg_thres_nominal, nth[k]);
     }
   }
 
@@ -106,8 +107,8 @@ __global__ void __launch_bounds__(kV2eThreads) v2e_kernel(const V2eArgs a) {
       float sps = 0.f, sns = 0.f;
       if (SHOT && philox) {
         const int64_t si = static_cast<int64_t>(b) * (N - 1) + (i - 1);
-        sps = static_cast<float>(d.shot_pos_scale[si]);
-        sns = static_cast<float>(d.shot_neg_scale[si]);
+        sps = v2e_scale_f32(d.shot_pos_scale[si]);
+        sns = v2e_scale_f32(d.shot_neg_scale[si]);
       }
 
       // per-interval random fields
@@ -210,49 +211,103 @@ __global__ void __launch_bounds__(kV2eThreads) v2e_kernel(const V2eArgs a) {
 // Full-frame means of generate_shot_noise (:90-96) -> per-frame Poisson scales.
 // One pass over the clip: a thread keeps nominal/thres of its 4 pixels in registers, walks the frames and adds
 // fac(v)*pre_prob to per-frame sums.  The sums are accumulated as 2^-36 fixed point in int64 (exact and order
-// independent, so the scales - and with them the Poisson draws - are run-to-run deterministic); the accumulators
-// live in the output arrays, which a second tiny kernel converts in place to (rate/2*dt) / mean.
+// independent, so the scales - and with them the Poisson draws - are run-to-run deterministic): per lane the four
+// products are summed in float64 in a fixed order and converted once, a warp adds its 32 integers with two REDUX
+// halves, every warp of the CTA keeps its own shared-memory accumulator row per frame (plain adds by lane 0), and the CTA
+// flushes the row sums to the output arrays at the end (one global atomic per frame, polarity and CTA); a second tiny kernel converts in place to (rate/2*dt) / mean.
 constexpr double kShotFix = 68719476736.0;   // 2^36
+constexpr int kShotChunk = 256;              // frames per shared-memory pass (8 warps x 2 x 2 KB of accumulators)
 
-__global__ void __launch_bounds__(256) v2e_shot_accum_kernel(const V2eArgs a, long long* pos_acc, long long* neg_acc) {
+__global__ void __launch_bounds__(256) v2e_shot_accum_kernel(const V2eArgs a, long long* pos_acc, long long* neg_acc, int tiles_per_cta) {
   __shared__ double fac_s[256];
+  __shared__ unsigned long long sacc[8][2][kShotChunk];      // one row per warp: lane 0 adds without atomics
   const v2v_v2e_desc& d = a.d;
   for (int i = threadIdx.x; i < 256; i += 256) fac_s[i] = 1.0 - 0.75 * ((static_cast<double>(i) + 20.0) / 275.0);
-  __syncthreads();
   const int b = blockIdx.y;
-  const int64_t pix0 = (static_cast<int64_t>(blockIdx.x) * 256 + threadIdx.x) * 4;
-  double pp[4], np_[4];
-#pragma unroll
-  for (int k = 0; k < 4; ++k) {
-    const bool ok = pix0 + k < a.HW;
-    pp[k] = ok ? d.pos_thres_nominal / d.pos_thres[static_cast<int64_t>(b) * a.HW + pix0 + k] : 0.0;
-    np_[k] = ok ? d.neg_thres_nominal / d.neg_thres[static_cast<int64_t>(b) * a.HW + pix0 + k] : 0.0;
-  }
   const bool vec = (a.HW % 4 == 0) && aligned_dev(d.frames, 4);
-  for (int f = 1; f < d.N; ++f) {
-    const uint8_t* fr = d.frames + (static_cast<int64_t>(b) * d.N + f) * a.HW + pix0;
-    uint32_t w = 0;
-    if (pix0 < a.HW) {
-      if (vec) w = ld_stream_u32(fr);
-      else {
+  const int M = d.N - 1;
+  for (int c0 = 0; c0 < M; c0 += kShotChunk) {
+    const int cn = min(kShotChunk, M - c0);
+    for (int i = threadIdx.x; i < 8 * 2 * kShotChunk; i += 256) (&sacc[0][0][0])[i] = 0ull;
+    __syncthreads();
+    for (int tile = 0; tile < tiles_per_cta; ++tile) {
+      const int64_t pix0 = ((static_cast<int64_t>(blockIdx.x) * tiles_per_cta + tile) * 256 + threadIdx.x) * 4;
+      if (pix0 - threadIdx.x * 4 >= a.HW) break;                   // whole tile past the frame (CTA-uniform)
+      double pp[4], np_[4];
 #pragma unroll
-        for (int k = 0; k < 4; ++k) if (pix0 + k < a.HW) w |= static_cast<uint32_t>(fr[k]) << (8 * k);
+      for (int k = 0; k < 4; ++k) {
+        const bool ok = pix0 + k < a.HW;
+        pp[k] = ok ? (d.pos_thres_nominal / d.pos_thres[static_cast<int64_t>(b) * a.HW + pix0 + k]) * kShotFix : 0.0;
+        np_[k] = ok ? (d.neg_thres_nominal / d.neg_thres[static_cast<int64_t>(b) * a.HW + pix0 + k]) * kShotFix : 0.0;
+      }
+      bool lane_small = true;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) lane_small = lane_small && pp[k] >= 0.0 && np_[k] >= 0.0 && pp[k] < 256.0 * kShotFix && np_[k] < 256.0 * kShotFix;
+      const bool small = __all_sync(0xffffffffu, lane_small);      // warp-uniform: the lane sums stay below 2^46
+      const uint8_t* fr0 = d.frames + (static_cast<int64_t>(b) * d.N + c0 + 1) * a.HW + pix0;
+      auto load = [&](int j) -> uint32_t {
+        uint32_t w = 0;
+        if (j < cn && pix0 < a.HW) {
+          const uint8_t* fr = fr0 + static_cast<int64_t>(j) * a.HW;
+          if (vec) w = ld_stream_u32(fr);
+          else {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) if (pix0 + k < a.HW) w |= static_cast<uint32_t>(fr[k]) << (8 * k);
+          }
+        }
+        return w;
+      };
+      constexpr int kAhead = 8;                                     // frames in flight per lane (the pass is latency bound otherwise)
+      uint32_t ring[kAhead];
+#pragma unroll
+      for (int u = 0; u < kAhead; ++u) ring[u] = load(u);
+      for (int j0 = 0; j0 < cn; j0 += kAhead) {
+#pragma unroll
+        for (int u = 0; u < kAhead; ++u) {
+          const int j = j0 + u;
+          if (j >= cn) break;                                        // CTA-uniform
+          const uint32_t w = ring[u];
+          ring[u] = load(j + kAhead);
+          double sp = 0.0, sn = 0.0;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const double fc = fac_s[(w >> (8 * k)) & 0xffu];
+            sp = __dadd_rn(sp, __dmul_rn(fc, pp[k]));
+            sn = __dadd_rn(sn, __dmul_rn(fc, np_[k]));
+          }
+          unsigned long long ps, ns;
+          unsigned int plo, nlo;
+          if (small) {
+            // RN(sp) as an integer without the conversion unit: adding 2^52+2^51 leaves it in the low mantissa bits
+            // (sp < 2^46 here); 64-bit warp sums from two 23-bit halves (32 of them stay below 2^28), one REDUX each
+            const double tp = __dadd_rn(sp, 6755399441055744.0), tn = __dadd_rn(sn, 6755399441055744.0);
+            const unsigned int pl = static_cast<unsigned int>(__double2loint(tp)), ph = static_cast<unsigned int>(__double2hiint(tp));
+            const unsigned int nl = static_cast<unsigned int>(__double2loint(tn)), nh = static_cast<unsigned int>(__double2hiint(tn));
+            plo = __reduce_add_sync(0xffffffffu, pl & 0x7fffffu);
+            nlo = __reduce_add_sync(0xffffffffu, nl & 0x7fffffu);
+            ps = static_cast<unsigned long long>(__reduce_add_sync(0xffffffffu, __funnelshift_r(pl, ph, 23) & 0x7fffffu)) << 23;
+            ns = static_cast<unsigned long long>(__reduce_add_sync(0xffffffffu, __funnelshift_r(nl, nh, 23) & 0x7fffffu)) << 23;
+          } else {                                                   // nominal/thres beyond 256: plain 64-bit shuffles
+            ps = static_cast<unsigned long long>(warp_sum(__double2ll_rn(sp)));
+            ns = static_cast<unsigned long long>(warp_sum(__double2ll_rn(sn)));
+            plo = nlo = 0u;
+          }
+          if ((threadIdx.x & 31) == 0) {
+            sacc[threadIdx.x >> 5][0][j] += ps + plo;
+            sacc[threadIdx.x >> 5][1][j] += ns + nlo;
+          }
+        }
       }
     }
-    long long sp = 0, sn = 0;
+    __syncthreads();
+    for (int i = threadIdx.x; i < 2 * cn; i += 256) {
+      const int pol = i >= cn, j = pol ? i - cn : i;
+      unsigned long long v = 0ull;
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const double fc = fac_s[(w >> (8 * k)) & 0xffu];
-      sp += __double2ll_rn(fc * pp[k] * kShotFix);
-      sn += __double2ll_rn(fc * np_[k] * kShotFix);
+      for (int wv = 0; wv < 8; ++wv) v += sacc[wv][pol][j];
+      if (v) atomicAdd(reinterpret_cast<unsigned long long*>((pol ? neg_acc : pos_acc) + static_cast<int64_t>(b) * M + c0 + j), v);
     }
-    sp = warp_sum(sp);
-    sn = warp_sum(sn);
-    if ((threadIdx.x & 31) == 0) {
-      const int64_t o = static_cast<int64_t>(b) * (d.N - 1) + (f - 1);
-      atomicAdd(reinterpret_cast<unsigned long long*>(pos_acc + o), static_cast<unsigned long long>(sp));
-      atomicAdd(reinterpret_cast<unsigned long long*>(neg_acc + o), static_cast<unsigned long long>(sn));
-    }
+    __syncthreads();
   }
 }
 
@@ -282,8 +337,8 @@ __global__ void v2e_philox_fields_kernel(const V2eArgs a, double* leak_randn, in
   const uint64_t clip_id = d.clip_index_base + static_cast<uint64_t>(b);
   const bool shot = d.shot_noise_rate_hz > 0.0, leak = d.leak_rate_hz > 0.0;
   const int64_t mp = static_cast<int64_t>(b) * a.HW + pix;
-  const float ppf = static_cast<float>(__ddiv_rn(d.pos_thres_nominal, d.pos_thres[mp]));
-  const float npf = static_cast<float>(__ddiv_rn(d.neg_thres_nominal, d.neg_thres[mp]));
+  const float ppf = v2e_pre_prob(d.pos_thres_nominal, d.pos_thres[mp]);
+  const float npf = v2e_pre_prob(d.neg_thres_nominal, d.neg_thres[mp]);
   const int j = static_cast<int>(pix & 3);
   for (int i = 1; i < d.N; ++i) {
     float lz[4] = {0.f, 0.f, 0.f, 0.f}, lo[4] = {0.f, 0.f, 0.f, 0.f}, up[4] = {1.f, 1.f, 1.f, 1.f}, un[4] = {1.f, 1.f, 1.f, 1.f};
@@ -302,8 +357,8 @@ __global__ void v2e_philox_fields_kernel(const V2eArgs a, double* leak_randn, in
       const double it = __ddiv_rn(__dadd_rn(static_cast<double>(v), 20.0), 275.0);
       const float fac = static_cast<float>(__dsub_rn(1.0, __dmul_rn(0.75, it)));
       const int64_t si = static_cast<int64_t>(b) * (d.N - 1) + (i - 1);
-      pos_shot[o] = poisson_small(v2e_shot_lambda(fac, ppf, static_cast<float>(d.shot_pos_scale[si])), up[j]);
-      neg_shot[o] = poisson_small(v2e_shot_lambda(fac, npf, static_cast<float>(d.shot_neg_scale[si])), un[j]);
+      pos_shot[o] = poisson_small(v2e_shot_lambda(fac, ppf, v2e_scale_f32(d.shot_pos_scale[si])), up[j]);
+      neg_shot[o] = poisson_small(v2e_shot_lambda(fac, npf, v2e_scale_f32(d.shot_neg_scale[si])), un[j]);
     }
   }
 }
@@ -379,8 +434,11 @@ extern "C" int v2v_v2e_shot_scales(const v2v_v2e_desc* desc, double* shot_pos_sc
   const size_t nbytes = static_cast<size_t>(d.B) * (d.N - 1) * sizeof(double);
   V2V_CUDA(cudaMemsetAsync(shot_pos_scale, 0, nbytes, s));
   V2V_CUDA(cudaMemsetAsync(shot_neg_scale, 0, nbytes, s));
-  dim3 grid(static_cast<unsigned int>((a.HW + 1023) / 1024), static_cast<unsigned int>(d.B));
-  v2e_shot_accum_kernel<<<grid, 256, 0, s>>>(a, reinterpret_cast<long long*>(shot_pos_scale), reinterpret_cast<long long*>(shot_neg_scale));
+  const int64_t tiles = (a.HW + 1023) / 1024;                       // 256 lanes x 4 pixels
+  // several tiles per CTA once the grid is a few waves deep: fewer per-frame flushes to the global accumulators
+  const int tpc = static_cast<int>(std::max<int64_t>(1, std::min<int64_t>(8, tiles * d.B / (148 * 8))));
+  dim3 grid(static_cast<unsigned int>((tiles + tpc - 1) / tpc), static_cast<unsigned int>(d.B));
+  v2e_shot_accum_kernel<<<grid, 256, 0, s>>>(a, reinterpret_cast<long long*>(shot_pos_scale), reinterpret_cast<long long*>(shot_neg_scale), tpc);
   const int64_t n = static_cast<int64_t>(d.B) * (d.N - 1);
   v2e_shot_finalize_kernel<<<static_cast<unsigned int>((n + 255) / 256), 256, 0, s>>>(a, shot_pos_scale, shot_neg_scale);
   count_launch(2);

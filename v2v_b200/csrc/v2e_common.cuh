@@ -61,11 +61,12 @@ __device__ __forceinline__ void v2e_leak_normals(uint64_t g4, uint32_t pair, uin
   even[3] = p3.x; odd[3] = p3.y;
 }
 
-// shot-noise Poisson rate of one pixel (float32, statistical mode): fac(v) * nominal/thres * per-frame scale (:90-99)
-// (clamped at 0: a negative or NaN rate draws no events in every kernel)
-__device__ __forceinline__ float v2e_shot_lambda(float facf, float pre_prob, float scale) {
-  return fmaxf(__fmul_rn(__fmul_rn(facf, pre_prob), scale), 0.f);
-}
+// shot-noise Poisson rate of one pixel (float32, statistical mode): fac(v) * nominal/thres * per-frame scale (:90-99).
+// The two per-pixel / per-frame factors are clamped at 0 where they are formed (a negative or NaN factor draws no
+// events in every kernel), fac(v) is in [0.25, 1): the product needs no clamp of its own.
+__device__ __forceinline__ float v2e_pre_prob(double nominal, double thr) { return fmaxf(static_cast<float>(__ddiv_rn(nominal, thr)), 0.f); }   // :396-399
+__device__ __forceinline__ float v2e_scale_f32(double s) { return fmaxf(static_cast<float>(s), 0.f); }
+__device__ __forceinline__ float v2e_shot_lambda(float facf, float pre_prob, float scale) { return __fmul_rn(__fmul_rn(facf, pre_prob), scale); }
 
 // Poisson(lam) by inversion from one uniform.  lam is a fraction of an event per frame in every shipped preset:
 // the first three CDF steps are straight-line code (k <= 2 covers all but ~lam^3/6 of the draws), the tail is a loop.

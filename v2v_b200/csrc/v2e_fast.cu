@@ -28,17 +28,35 @@ struct __align__(16) IntervalRow {  // one row per frame interval, identical for
 };
 
 constexpr int kLutBytes = 256 * 16, kFacBytes = 256 * 4, kLogfBytes = 256 * 4, kTrigBytes = kTrigEntries * 8;
+constexpr int kRcpBytes = 4 * 2 * kThreads * 8;
 
 __device__ __forceinline__ double hi_double(int hi) { return __hiloint2double(hi, 0); }
+// x with the sign of s multiplied in (x >= 0): -x where s is negative — one logic op on the high word instead of a select pair
+__device__ __forceinline__ double with_sign_of(double x, double s) {
+  return __hiloint2double(__double2hiint(x) ^ (__double2hiint(s) & static_cast<int>(0x80000000u)), __double2loint(x));
+}
 
-template <bool F32STATE, bool CUTOFF, bool LEAK, bool SHOT, bool PHILOX>
+// floor(a/b) for a >= 0, b > 0 without branches (same candidate-and-correct scheme as floor_div_exact)
+__device__ __forceinline__ double floor_div_bf(double a, double b, double rb) {
+  const double q = floor(__dmul_rn(a, rb));
+  const double qp = __dadd_rn(q, 1.0), qm = __dadd_rn(q, -1.0);
+  const double r1 = __fma_rn(-q, b, a), r2 = __fma_rn(-qp, b, a);
+  double out = (r2 >= 0.0) ? qp : q;
+  out = (r1 < 0.0) ? qm : out;
+  return out;
+}
+
+// BF: every pixel takes the exact floor division (no trigger, no divergent block) — for footage where several
+// thresholds are crossed per frame in most warps (HDR-degraded clips); !BF: single-crossing fast path + divergent exact path.
+template <bool F32STATE, bool CUTOFF, bool LEAK, bool SHOT, bool PHILOX, bool BF>
 __global__ void __launch_bounds__(kThreads, 4) v2e_fast_kernel(const V2eArgs a) {
   extern __shared__ __align__(16) unsigned char dyn[];
   double2* lut2 = reinterpret_cast<double2*>(dyn);                                   // {double(logv), (v+20)/275}
   float* facf_s = reinterpret_cast<float*>(dyn + kLutBytes);                        // 1 - 0.75*inten as float
   float* logf_s = reinterpret_cast<float*>(dyn + kLutBytes + kFacBytes);            // float32 log LUT (float32-state path)
   float2* trig_s = reinterpret_cast<float2*>(dyn + kLutBytes + kFacBytes + kLogfBytes);
-  IntervalRow* itab = reinterpret_cast<IntervalRow*>(dyn + kLutBytes + kFacBytes + kLogfBytes + (LEAK && PHILOX ? kTrigBytes : 0));
+  double* rcp_s = reinterpret_cast<double*>(dyn + kLutBytes + kFacBytes + kLogfBytes + (LEAK && PHILOX ? kTrigBytes : 0));   // [4][2][kThreads] 1/thr
+  IntervalRow* itab = reinterpret_cast<IntervalRow*>(reinterpret_cast<unsigned char*>(rcp_s) + (BF ? kRcpBytes : 0));
   __shared__ unsigned long long cta_stats[2];
 
   const v2v_v2e_desc& d = a.d;
@@ -60,8 +78,8 @@ __global__ void __launch_bounds__(kThreads, 4) v2e_fast_kernel(const V2eArgs a) 
     r.sps = r.sns = r.pad[0] = r.pad[1] = 0.f;
     if (SHOT) {
       const int64_t si = static_cast<int64_t>(b) * (N - 1) + (i - 1);
-      r.sps = static_cast<float>(d.shot_pos_scale[si]);
-      r.sns = static_cast<float>(d.shot_neg_scale[si]);
+      r.sps = v2e_scale_f32(d.shot_pos_scale[si]);
+      r.sns = v2e_scale_f32(d.shot_neg_scale[si]);
     }
     itab[i - 1] = r;
   }
@@ -91,12 +109,16 @@ __global__ void __launch_bounds__(kThreads, 4) v2e_fast_kernel(const V2eArgs a) 
     thr2 = fmin(thr2, fmin(pth[k], nth[k]));
     if (LEAK) r32d[LEAK ? k : 0] = static_cast<double>(__fmul_rn(a.leak_hz_f32, d.noise_rate ? d.noise_rate[mp + k] : 1.0f));   // :205
     if (SHOT) {                                                                      // :396-399
-      ppf[SHOT ? k : 0] = static_cast<float>(__ddiv_rn(d.pos_thres_nominal, pth[k]));
-      npf[SHOT ? k : 0] = static_cast<float>(__ddiv_rn(d.neg_thres_nominal, nth[k]));
+      ppf[SHOT ? k : 0] = v2e_pre_prob(d.pos_thres_nominal, pth[k]);
+      npf[SHOT ? k : 0] = v2e_pre_prob(d.neg_thres_nominal, nth[k]);
     }
     if (F32STATE) {      // float32 diff compared with float64 thresholds: diff >= thr  <=>  diff >= RU_f32(thr)
       pthf[F32STATE ? k : 0] = __double2float_ru(pth[k]);
       nthf[F32STATE ? k : 0] = __double2float_ru(nth[k]);
+    }
+    if (BF) {            // own slots, read back by this lane only: no barrier
+      rcp_s[(2 * k) * kThreads + threadIdx.x] = __drcp_rn(pth[k]);
+      rcp_s[(2 * k + 1) * kThreads + threadIdx.x] = __drcp_rn(nth[k]);
     }
   }
   thr2 = __dadd_rn(thr2, thr2);       // below 2*min(threshold) of this lane's pixels at most one threshold is crossed
@@ -140,6 +162,22 @@ __global__ void __launch_bounds__(kThreads, 4) v2e_fast_kernel(const V2eArgs a) 
       if (F32STATE) {
         const float lognew = logf_s[v];                                               // :447 (lp == log_new)
         const float df = __fsub_rn(lognew, basef[F32STATE ? k : 0]);                    // :503 in float32
+        if (BF) {
+          const bool dn = df < 0.f;
+          const double thr = dn ? nth[k] : pth[k];
+          const double q = floor_div_bf(static_cast<double>(fabsf(df)), thr, rcp_s[(2 * k + (dn ? 1 : 0)) * kThreads + threadIdx.x]);
+          const double t = __dmul_rn(q, thr);                                          // pe*pth or ne*nth (the other product is 0)
+          const double dsg = static_cast<double>(df);
+          const double sq = with_sign_of(q, dsg), st = with_sign_of(t, dsg);
+          basef[F32STATE ? k : 0] = __double2float_rn(__dadd_rn(static_cast<double>(basef[F32STATE ? k : 0]), st));   // :547-548
+          if (want_stats) {
+            dpos = __dadd_rn(dpos, q);           // here: dpos = #pos + #neg, dneg = #pos - #neg (resolved after the loop)
+            dneg = __dadd_rn(dneg, sq);
+          }
+          acc[k] += static_cast<float>(sq);
+          outv[k] = acc[k];
+          continue;
+        }
         const bool upc = df >= pthf[F32STATE ? k : 0], dnc = -df >= nthf[F32STATE ? k : 0];
         pe = hi_double(upc ? 0x3ff00000 : 0);
         ne = hi_double(dnc ? 0x3ff00000 : 0);
@@ -170,6 +208,26 @@ __global__ void __launch_bounds__(kThreads, 4) v2e_fast_kernel(const V2eArgs a) 
           base[k] = __dsub_rn(base[k], __dmul_rn(__dmul_rn(row.dt, rate), pth[k]));
         }
         const double diff = __dsub_rn(lp[k], base[k]);                                 // :503
+        if (BF) {
+          const bool dn = diff < 0.0;
+          const double thr = dn ? nth[k] : pth[k];
+          const double q = floor_div_bf(fabs(diff), thr, rcp_s[(2 * k + (dn ? 1 : 0)) * kThreads + threadIdx.x]);    // :55-60
+          if (!SHOT) {
+            const double t = __dmul_rn(q, thr);                                        // pe*pth or ne*nth (the other product is 0)
+            base[k] = __dadd_rn(base[k], with_sign_of(t, diff));                       // :547-548
+            const double sq = with_sign_of(q, diff);
+            if (want_stats) {
+              dpos = __dadd_rn(dpos, q);         // here: dpos = #pos + #neg, dneg = #pos - #neg (resolved after the loop)
+              dneg = __dadd_rn(dneg, sq);
+            }
+            acc[k] += static_cast<float>(sq);
+            outv[k] = acc[k];
+            continue;
+          }
+          pe = dn ? 0.0 : q;
+          ne = dn ? q : 0.0;
+          of = static_cast<float>(with_sign_of(q, diff));
+        } else {
         const bool upc = diff >= pth[k], dnc = -diff >= nth[k];
         pe = hi_double(upc ? 0x3ff00000 : 0);
         ne = hi_double(dnc ? 0x3ff00000 : 0);
@@ -179,6 +237,7 @@ __global__ void __launch_bounds__(kThreads, 4) v2e_fast_kernel(const V2eArgs a) 
           if (upc) pe = count_floor(diff, pth[k]);
           else if (dnc) ne = count_floor(-diff, nth[k]);
           of = static_cast<float>(__dsub_rn(pe, ne));
+        }
         }
       }
       if (SHOT) {                                                                      // :90-103, 530-531
@@ -226,14 +285,37 @@ __global__ void __launch_bounds__(kThreads, 4) v2e_fast_kernel(const V2eArgs a) 
     }
   };
 
-  // ---- main loop: kPF frames per trip, the next trip's words already in flight ----
   const int M = N - 1;
+  if (SHOT) {
+    // ---- shot-noise variants: the step is ~600 instructions, so the loop stays rolled (one copy of the step: the unrolled
+    //      form overflows the instruction cache); three frames in flight through a rotating register window ----
+    uint32_t w0 = ld_stream_u32(fr + HW), w1 = M > 1 ? ld_stream_u32(fr + 2 * HW) : 0u, w2 = M > 2 ? ld_stream_u32(fr + 3 * HW) : 0u;
+    float le[4] = {0.f, 0.f, 0.f, 0.f}, lo[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 1
+    for (int j = 0; j < M; ++j) {                // interval j = frames (j, j+1)
+      const uint32_t w = w0;
+      w0 = w1;
+      w1 = w2;
+      if (j + 4 < N) w2 = ld_stream_u32(fr + static_cast<int64_t>(j + 4) * HW);
+      float lz[4] = {0.f, 0.f, 0.f, 0.f};
+      if (LEAK && PHILOX) {
+        if ((j & 1) == 0) v2e_leak_normals(g4, static_cast<uint32_t>(j) >> 1, clip_id, a.rk, trig_s, le, lo);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) lz[k] = (j & 1) ? lo[k] : le[k];
+      }
+      float up[4], un[4];
+      v2e_shot_uniforms(g4, static_cast<uint32_t>(j), clip_id, a.rk, up, un);
+      step(w, j, lz, up, un);
+    }
+  } else {
+  // ---- main loop: kPF frames per trip, the next trip's words already in flight ----
   const int trips = M / kPF;
   uint32_t cur[kPF], nxt[kPF];
   if (trips > 0) {
 #pragma unroll
     for (int u = 0; u < kPF; ++u) cur[u] = ld_stream_u32(fr + static_cast<int64_t>(1 + u) * HW);
   }
+  const float one4[4] = {1.f, 1.f, 1.f, 1.f};
   int i = 1;
   for (int t = 0; t < trips; ++t) {
     if (t + 1 < trips) {
@@ -244,11 +326,8 @@ __global__ void __launch_bounds__(kThreads, 4) v2e_fast_kernel(const V2eArgs a) 
     for (int h = 0; h < kPF / 2; ++h) {           // interval pairs (i-1+2h, i+2h)
       float le[4] = {0.f, 0.f, 0.f, 0.f}, lo[4] = {0.f, 0.f, 0.f, 0.f};
       if (LEAK && PHILOX) v2e_leak_normals(g4, static_cast<uint32_t>(i - 1 + 2 * h) >> 1, clip_id, a.rk, trig_s, le, lo);
-      float up[4] = {1.f, 1.f, 1.f, 1.f}, un[4] = {1.f, 1.f, 1.f, 1.f};
-      if (SHOT) v2e_shot_uniforms(g4, static_cast<uint32_t>(i - 1 + 2 * h), clip_id, a.rk, up, un);
-      step(cur[2 * h], i - 1 + 2 * h, le, up, un);
-      if (SHOT) v2e_shot_uniforms(g4, static_cast<uint32_t>(i + 2 * h), clip_id, a.rk, up, un);
-      step(cur[2 * h + 1], i + 2 * h, lo, up, un);
+      step(cur[2 * h], i - 1 + 2 * h, le, one4, one4);
+      step(cur[2 * h + 1], i + 2 * h, lo, one4, one4);
     }
     i += kPF;
 #pragma unroll
@@ -259,13 +338,17 @@ __global__ void __launch_bounds__(kThreads, 4) v2e_fast_kernel(const V2eArgs a) 
     if (LEAK && PHILOX) v2e_leak_normals(g4, static_cast<uint32_t>(i - 1) >> 1, clip_id, a.rk, trig_s, le, lo);
 #pragma unroll
     for (int k = 0; k < 4; ++k) lz[k] = ((i - 1) & 1) ? lo[k] : le[k];
-    float up[4] = {1.f, 1.f, 1.f, 1.f}, un[4] = {1.f, 1.f, 1.f, 1.f};
-    if (SHOT) v2e_shot_uniforms(g4, static_cast<uint32_t>(i - 1), clip_id, a.rk, up, un);
-    step(ld_stream_u32(fr + static_cast<int64_t>(i) * HW), i - 1, lz, up, un);
+    step(ld_stream_u32(fr + static_cast<int64_t>(i) * HW), i - 1, lz, one4, one4);
+  }
   }
 
   if (want_stats) {
     const unsigned int m = __activemask();
+    if (BF && !SHOT) {                 // (total, net) -> (#pos, #neg); exact: both are integers below 2^53
+      const double tot = dpos, net = dneg;
+      dpos = __dmul_rn(__dadd_rn(tot, net), 0.5);
+      dneg = __dmul_rn(__dsub_rn(tot, net), 0.5);
+    }
     unsigned long long sp = static_cast<unsigned long long>(dpos), sn = static_cast<unsigned long long>(dneg);
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
@@ -287,8 +370,8 @@ __global__ void __launch_bounds__(kThreads, 4) v2e_fast_kernel(const V2eArgs a) 
   }
 }
 
-size_t fast_smem_bytes(const V2eArgs& a, bool trig) {
-  return kLutBytes + kFacBytes + kLogfBytes + (trig ? kTrigBytes : 0) + static_cast<size_t>(a.d.N - 1) * sizeof(IntervalRow);
+size_t fast_smem_bytes(const V2eArgs& a, bool trig, bool bf) {
+  return kLutBytes + kFacBytes + kLogfBytes + (trig ? kTrigBytes : 0) + (bf ? kRcpBytes : 0) + static_cast<size_t>(a.d.N - 1) * sizeof(IntervalRow);
 }
 
 }  // namespace
@@ -311,11 +394,18 @@ int launch_v2e_fast(const V2eArgs& a, cudaStream_t s) {
   const bool ph = d.noise_mode == V2V_NOISE_PHILOX;
   const bool cut = d.cutoff_hz > 0.0, lk = d.leak_rate_hz > 0.0, sh = d.shot_noise_rate_hz > 0.0 && ph;
   const bool leak_variant = !d.state_f32 && (lk || !cut);      // the template's LEAK (a float64 state without cutoff runs the leak variant)
-  const size_t smem = fast_smem_bytes(a, leak_variant && ph);
-#define V2V_K(F32, CU, LK, SH, PH)                                                                                          \
+  // exact division for every pixel (default) or single-crossing fast path + divergent exact path (V2V_V2E_BF=0)
+  const char* e = getenv("V2V_V2E_BF");
+  const bool bf = e ? atoi(e) != 0 : true;
+  const size_t smem = fast_smem_bytes(a, leak_variant && ph, bf);
+#define V2V_KB(F32, CU, LK, SH, PH, BFV)                                                                                    \
   do {                                                                                                                      \
-    V2V_CUDA(cudaFuncSetAttribute(v2e_fast_kernel<F32, CU, LK, SH, PH>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem))); \
-    v2e_fast_kernel<F32, CU, LK, SH, PH><<<grid, kThreads, smem, s>>>(a);                                                   \
+    V2V_CUDA(cudaFuncSetAttribute(v2e_fast_kernel<F32, CU, LK, SH, PH, BFV>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem))); \
+    v2e_fast_kernel<F32, CU, LK, SH, PH, BFV><<<grid, kThreads, smem, s>>>(a);                                              \
+  } while (0)
+#define V2V_K(F32, CU, LK, SH, PH)                                          \
+  do {                                                                      \
+    if (bf) V2V_KB(F32, CU, LK, SH, PH, true); else V2V_KB(F32, CU, LK, SH, PH, false); \
   } while (0)
 #define V2V_PHX(F32, CU, LK)                                                     \
   do {                                                                           \
@@ -328,6 +418,7 @@ int launch_v2e_fast(const V2eArgs& a, cudaStream_t s) {
   else V2V_PHX(false, false, true);
 #undef V2V_PHX
 #undef V2V_K
+#undef V2V_KB
   count_launch();
   V2V_CUDA(cudaGetLastError());
   return V2V_OK;

@@ -113,7 +113,7 @@ def frames_to_voxel_v2e(frames: torch.Tensor, pos_thres, neg_thres, *, fps: floa
             _lib.check(lib.v2v_v2e_philox_fields(C.byref(d), _ptr(fl), _ptr(fp), _ptr(fn), C.c_void_p(s.cuda_stream)))
             fields = {"leak_randn": fl, "pos_shot": fp, "neg_shot": fn}
         _lib.check(lib.v2v_v2e_frames_to_voxel(C.byref(d), C.c_void_p(s.cuda_stream)))
-    return {"voxel": vox, "stats": stats_t, "fields": fields}
+    return {"voxel": vox, "stats": stats_t, "fields": fields, "shot_scales": scales}
 
 
 def video_to_voxel(video, FPS, threshold_model, thres_mean_mean, thres_mean_std, thres_diff_mean, thres_diff_std,
