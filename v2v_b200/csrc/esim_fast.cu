@@ -55,7 +55,7 @@ __device__ __forceinline__ void single_cross(double& x, float& ov, double pos, d
 }
 
 // Select form of the same update (one FP64 add of {-pos, +neg, 0}): fewer registers; used by the noise-free
-// variants, which run at 64 registers / 8 CTAs per SM and are closer to the HBM limit than to the ALU pipe's.
+// variants, which run at 64 registers / 8 CTAs per SM (the FMA form costs them registers: 1.20 vs 1.15 ms per 32 clips).
 __device__ __forceinline__ void single_cross_sel(double& x, float& ov, double pos, double mneg, double neg) {
   const bool up = x >= pos, dn = x <= mneg;
   double sel = up ? -pos : 0.0;
@@ -98,8 +98,7 @@ __global__ void __launch_bounds__(kFastThreads, CTAS) esim_fast_kernel(const Esi
   const double pos = d.pos_thres[b], neg = d.neg_thres[b];
   const double mneg = -neg;
   const double thr2 = __dadd_rn(fmin(pos, neg), fmin(pos, neg));   // below 2*min(pos,neg) at most one threshold is crossed
-  const int hibig = __double2hiint(thr2);
-  constexpr bool kFp64Trigger = NOISE == V2V_NOISE_PHILOX;         // which pipe pays for the trigger / the update (see single_cross*)
+  constexpr bool kFmaCross = NOISE == V2V_NOISE_PHILOX;            // which form of the single crossing (see single_cross*)
   const float nc2 = NOISE == V2V_NOISE_PHILOX ? noise_c2(static_cast<float>(d.base_noise_std[b])) : 0.f;
   // byte offset of this lane's LUT copy
   const uint32_t lut_base = static_cast<uint32_t>(__cvta_generic_to_shared(dyn_smem)) + (threadIdx.x & (kLutCopies - 1)) * 8u;
@@ -186,7 +185,7 @@ __global__ void __launch_bounds__(kFastThreads, CTAS) esim_fast_kernel(const Esi
       x0[2] = __dadd_rn(x0[2], static_cast<double>(h.z));
       x0[3] = __dadd_rn(x0[3], static_cast<double>(h.w));
     }
-    if (kFp64Trigger) {   // trigger of the exact multi-threshold path: four FP64 compares chained through one predicate
+    {   // trigger of the exact multi-threshold path: four FP64 compares chained through one predicate (no ALU-pipe work)
       unsigned int r;
       asm("{\n"
           " .reg .pred p;\n"
@@ -200,21 +199,18 @@ __global__ void __launch_bounds__(kFastThreads, CTAS) esim_fast_kernel(const Esi
           : "=r"(r)
           : "d"(x0[0]), "d"(x0[1]), "d"(x0[2]), "d"(x0[3]), "d"(thr2));
       rare = r != 0;
-    } else {              // same test on the high words (conservative: may also fire just below 2*min, which multi_cross handles)
-#pragma unroll
-      for (int k = 0; k < 4; ++k) rare = rare || ((__double2hiint(x0[k]) & 0x7fffffff) >= hibig);
     }
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
       double x = x0[k];
-      if (kFp64Trigger) single_cross(x, o[k], pos, mneg);
+      if (kFmaCross) single_cross(x, o[k], pos, mneg);
       else single_cross_sel(x, o[k], pos, mneg, neg);                        // :51-58 with q in {0,1}
       pot[k] = x;
     }
     if (rare) {                                                       // a few % of warp-steps on natural video
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
-        if (kFp64Trigger ? fabs(x0[k]) >= thr2 : (__double2hiint(x0[k]) & 0x7fffffff) >= hibig) {
+        if (fabs(x0[k]) >= thr2) {
           int cnt;
           pot[k] = multi_cross(x0[k], pos, neg, cta_rcp[0], cta_rcp[1], &cnt);   // conservative trigger: correct for any x
           o[k] = static_cast<float>(cnt);
