@@ -35,10 +35,33 @@ __device__ __forceinline__ double hi_double(int hi) { return __hiloint2double(hi
 __device__ __forceinline__ double with_sign_of(double x, double s) {
   return __hiloint2double(__double2hiint(x) ^ (__double2hiint(s) & static_cast<int>(0x80000000u)), __double2loint(x));
 }
+__device__ __forceinline__ double with_sign_of(double x, float s) {
+  return __hiloint2double(__double2hiint(x) ^ (__float_as_int(s) & static_cast<int>(0x80000000u)), __double2loint(x));
+}
+// float32 of an integer-valued float64 with |n| < 2^22, without the conversion unit: 2^52+2^51 + n leaves n as a two's
+// complement integer in the low word; 1.5*2^23 + n is exact in float32 and its bit pattern is 0x4b400000 + n.
+// `tiny` lanes (a threshold below 1e-5: counts could reach 2^22) take the plain conversion instead.
+template <bool MAGIC>
+__device__ __forceinline__ float small_int_to_float(double n, bool tiny) {
+  if (!MAGIC) return static_cast<float>(n);
+  if (tiny) {          // volatile: keeps this a branch, so the conversion is not issued speculatively on every step
+    float r;
+    asm volatile("cvt.rn.f32.f64 %0, %1;" : "=f"(r) : "d"(n));
+    return r;
+  }
+  const int i = __double2loint(__dadd_rn(n, 6755399441055744.0));
+  return __fsub_rn(__int_as_float(0x4b400000 + i), 12582912.0f);
+}
 
 // floor(a/b) for a >= 0, b > 0 without branches (same candidate-and-correct scheme as floor_div_exact)
+// The candidate is a*RN(1/b) rounded to the NEAREST integer with the 2^52 trick (two FP64 adds instead of a trip through
+// the conversion unit): it is floor or floor+1 of a value within 1 ulp of the true quotient, still inside the +-1 window
+// the two residual tests correct.
+// (MAGIC: for the variant that is bound by the conversion unit; the others keep floor().)
+template <bool MAGIC>
 __device__ __forceinline__ double floor_div_bf(double a, double b, double rb) {
-  const double q = floor(__dmul_rn(a, rb));
+  const double p = __dmul_rn(a, rb);
+  const double q = MAGIC ? __dsub_rn(__dadd_rn(p, 4503599627370496.0), 4503599627370496.0) : floor(p);
   const double qp = __dadd_rn(q, 1.0), qm = __dadd_rn(q, -1.0);
   const double r1 = __fma_rn(-q, b, a), r2 = __fma_rn(-qp, b, a);
   double out = (r2 >= 0.0) ? qp : q;
@@ -60,6 +83,9 @@ __global__ void __launch_bounds__(kThreads, 4) v2e_fast_kernel(const V2eArgs a) 
   __shared__ unsigned long long cta_stats[2];
 
   const v2v_v2e_desc& d = a.d;
+  // float32-state variant: conversion unit 71 % busy in ncu -> integer rounding and int->float by FP64/FP32 adds instead;
+  // the float64-state variants are shorter of FP64 issue slots and keep floor() / cvt (same-box A/B: 0.66 vs 0.70 ms)
+  constexpr bool kMagic = F32STATE;
   const int N = d.N, b = blockIdx.y;
   if (LEAK && PHILOX) fill_trig_table(trig_s);
   if (threadIdx.x < 2) cta_stats[threadIdx.x] = 0ull;
@@ -121,6 +147,7 @@ __global__ void __launch_bounds__(kThreads, 4) v2e_fast_kernel(const V2eArgs a) 
       rcp_s[(2 * k + 1) * kThreads + threadIdx.x] = __drcp_rn(nth[k]);
     }
   }
+  const bool tiny = !(thr2 >= 1e-5);  // absurdly small (or NaN) threshold on this lane: counts may not fit the small-integer shortcuts
   thr2 = __dadd_rn(thr2, thr2);       // below 2*min(threshold) of this lane's pixels at most one threshold is crossed
   const float thr2f = __double2float_rd(thr2);
 
@@ -165,16 +192,15 @@ __global__ void __launch_bounds__(kThreads, 4) v2e_fast_kernel(const V2eArgs a) 
         if (BF) {
           const bool dn = df < 0.f;
           const double thr = dn ? nth[k] : pth[k];
-          const double q = floor_div_bf(static_cast<double>(fabsf(df)), thr, rcp_s[(2 * k + (dn ? 1 : 0)) * kThreads + threadIdx.x]);
+          const double q = floor_div_bf<kMagic>(static_cast<double>(fabsf(df)), thr, rcp_s[(2 * k + (dn ? 1 : 0)) * kThreads + threadIdx.x]);
           const double t = __dmul_rn(q, thr);                                          // pe*pth or ne*nth (the other product is 0)
-          const double dsg = static_cast<double>(df);
-          const double sq = with_sign_of(q, dsg), st = with_sign_of(t, dsg);
+          const double sq = with_sign_of(q, df), st = with_sign_of(t, df);
           basef[F32STATE ? k : 0] = __double2float_rn(__dadd_rn(static_cast<double>(basef[F32STATE ? k : 0]), st));   // :547-548
           if (want_stats) {
             dpos = __dadd_rn(dpos, q);           // here: dpos = #pos + #neg, dneg = #pos - #neg (resolved after the loop)
             dneg = __dadd_rn(dneg, sq);
           }
-          acc[k] += static_cast<float>(sq);
+          acc[k] += small_int_to_float<kMagic>(sq, tiny);
           outv[k] = acc[k];
           continue;
         }
@@ -211,7 +237,7 @@ __global__ void __launch_bounds__(kThreads, 4) v2e_fast_kernel(const V2eArgs a) 
         if (BF) {
           const bool dn = diff < 0.0;
           const double thr = dn ? nth[k] : pth[k];
-          const double q = floor_div_bf(fabs(diff), thr, rcp_s[(2 * k + (dn ? 1 : 0)) * kThreads + threadIdx.x]);    // :55-60
+          const double q = floor_div_bf<kMagic>(fabs(diff), thr, rcp_s[(2 * k + (dn ? 1 : 0)) * kThreads + threadIdx.x]);    // :55-60
           if (!SHOT) {
             const double t = __dmul_rn(q, thr);                                        // pe*pth or ne*nth (the other product is 0)
             base[k] = __dadd_rn(base[k], with_sign_of(t, diff));                       // :547-548
@@ -220,13 +246,13 @@ __global__ void __launch_bounds__(kThreads, 4) v2e_fast_kernel(const V2eArgs a) 
               dpos = __dadd_rn(dpos, q);         // here: dpos = #pos + #neg, dneg = #pos - #neg (resolved after the loop)
               dneg = __dadd_rn(dneg, sq);
             }
-            acc[k] += static_cast<float>(sq);
+            acc[k] += small_int_to_float<kMagic>(sq, tiny);
             outv[k] = acc[k];
             continue;
           }
           pe = dn ? 0.0 : q;
           ne = dn ? q : 0.0;
-          of = static_cast<float>(with_sign_of(q, diff));
+          of = small_int_to_float<kMagic>(with_sign_of(q, diff), tiny);
         } else {
         const bool upc = diff >= pth[k], dnc = -diff >= nth[k];
         pe = hi_double(upc ? 0x3ff00000 : 0);
