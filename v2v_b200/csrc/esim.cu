@@ -51,6 +51,9 @@ __global__ void __launch_bounds__(kThreads) esim_kernel(const EsimArgs a) {
   const uint64_t clip_id = d.clip_index_base + static_cast<uint64_t>(b);
   const NoiseKey nkey = make_noise_key(clip_id);
   const float nc2 = noise_c2(static_cast<float>((NOISE != V2V_NOISE_NONE && d.base_noise_std) ? d.base_noise_std[b] : 0.0));
+  GroupStream gs{0u, 0u, 0u, 0u};          // base-noise stream of this lane's 4-pixel group (every lane of a group walks the same stream)
+  float nodd[4] = {0.f, 0.f, 0.f, 0.f};    // the odd interval's normals of the current pair
+  if (NOISE == V2V_NOISE_PHILOX) gs = group_stream_init(static_cast<uint64_t>(pix0) >> 2, nkey, a.rk);
 
   // ---- per-pixel / per-clip constants ----
   double pos[PERPIXEL ? P : 1], neg[PERPIXEL ? P : 1], rpos[PERPIXEL ? P : 1], rneg[PERPIXEL ? P : 1];
@@ -167,13 +170,14 @@ __global__ void __launch_bounds__(kThreads) esim_kernel(const EsimArgs a) {
             for (int k = 0; k < P; ++k) bn[k] = 0.0;
           }
         } else if (NOISE == V2V_NOISE_PHILOX) {
-          if (P == 4) {
-            float ev[4], od[4];
-            philox_noise8(static_cast<uint64_t>(pix0) >> 2, static_cast<uint32_t>(i - 1) >> 1, nkey, a.rk, nc2, trig_s, ev, od);
+          float nev[4] = {0.f, 0.f, 0.f, 0.f};
+          if (((i - 1) & 1) == 0) stream_noise8(gs, nc2, trig_s, nev, nodd);      // intervals are walked in order: one draw per pair
 #pragma unroll
-            for (int k = 0; k < P; ++k) bn[k] = static_cast<double>(((i - 1) & 1) ? od[k % 4] : ev[k % 4]);
-          } else {
-            bn[0] = static_cast<double>(philox_noise1(static_cast<uint64_t>(pix0), static_cast<uint32_t>(i - 1), nkey, a.rk, nc2, trig_s));
+          for (int k = 0; k < P; ++k) {
+            const int j = P == 4 ? k : static_cast<int>(pix0 & 3);
+            const float e = j == 0 ? nev[0] : j == 1 ? nev[1] : j == 2 ? nev[2] : nev[3];
+            const float o = j == 0 ? nodd[0] : j == 1 ? nodd[1] : j == 2 ? nodd[2] : nodd[3];
+            bn[k] = static_cast<double>(((i - 1) & 1) ? o : e);
           }
         }
 
@@ -315,9 +319,14 @@ __global__ void esim_philox_fields_kernel(const EsimArgs a, double* u0, double* 
   if (hot) hot[o] = h;
   if (bn) {
     const float nc2 = noise_c2(static_cast<float>(d.base_noise_std[b]));
+    GroupStream gs = group_stream_init(static_cast<uint64_t>(pix) >> 2, nkey, a.rk);
+    const int j = static_cast<int>(pix & 3);
+    float ev[4], od[4] = {0.f, 0.f, 0.f, 0.f};
     for (int i = 0; i < d.N - 1; ++i) {
-      bn[(static_cast<int64_t>(b) * (d.N - 1) + i) * a.HW + pix] =
-          static_cast<double>(philox_noise1(static_cast<uint64_t>(pix), static_cast<uint32_t>(i), nkey, a.rk, nc2, trig_s));
+      if ((i & 1) == 0) stream_noise8(gs, nc2, trig_s, ev, od);
+      const float e = j == 0 ? ev[0] : j == 1 ? ev[1] : j == 2 ? ev[2] : ev[3];
+      const float o = j == 0 ? od[0] : j == 1 ? od[1] : j == 2 ? od[2] : od[3];
+      bn[(static_cast<int64_t>(b) * (d.N - 1) + i) * a.HW + pix] = static_cast<double>((i & 1) ? o : e);
     }
   }
 }

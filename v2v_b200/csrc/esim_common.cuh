@@ -17,15 +17,18 @@ struct EsimArgs {
 
 constexpr int kEsimThreads = 256;
 
-// ---- Philox noise fields ------------------------------------------------------
+// ---- noise fields ----------------------------------------------------------------
 // All kernels (generic, fast, field dump) draw the same values for the same
 // (seed, clip, pixel, interval), independent of launch geometry:
-//   base noise : one Philox call per aligned group of 4 pixels and PAIR of intervals,
-//                counter (group lo32, interval/2, clip lo32, tag0|group hi|clip hi16)
-//                -> 8 normals (Box-Muller, 20-bit radius, 4096 tabulated directions); bn = double(std*r*cos|sin)
-//   init fields: counter (pixel lo32, pixel hi32, clip lo32, tag2|clip hi16)
+//   init fields: Philox4x32-10, counter (pixel lo32, pixel hi32, clip lo32, tag2|clip hi16)
 //                -> u0 (53 bit), hot-mask uniform (53 bit)
 //   hot normal : same counter with tag3 -> z; hot = double(float(hot_pixel_std) * z)
+//   base noise : one stream per aligned group of 4 pixels and clip: xoshiro128++ (Blackman & Vigna) seeded with the
+//                Philox4x32-10 output of counter (group lo32, 0, clip lo32, tag1|group hi|clip hi16); every PAIR of
+//                intervals consumes four 32-bit outputs, word k -> pixel k -> one Box-Muller pair (20-bit radius,
+//                2048 tabulated directions): .x for the even interval, .y for the odd one; bn = double(std*r*cos|sin).
+//                The counter-based generator pays for itself once per pixel group (and for the init fields); the
+//                per-interval draws cost 9 instructions per word instead of Philox's 19.
 struct NoiseKey {
   uint32_t clip_lo, clip_hi16;
 };
@@ -37,31 +40,41 @@ __device__ __forceinline__ NoiseKey make_noise_key(uint64_t clip_id) {
   return k;
 }
 
-// Base noise of the aligned 4-pixel group g4 for the interval pair (2*pair, 2*pair+1), already multiplied
-// by float(base_noise_std): even[k] belongs to pixel 4*g4+k at interval 2*pair, odd[k] at 2*pair+1.
 __device__ __forceinline__ float noise_c2(float scale) { return -1.3862943611198906f * scale * scale; }
 
-__device__ __forceinline__ void philox_noise8(uint64_t g4, uint32_t pair, const NoiseKey& nk, const uint32_t (&rk)[20], float c2,
-                                              const float2* trig, float (&even)[4], float (&odd)[4]) {
-  const uint4 r = Philox::run_rk(make_uint4(static_cast<uint32_t>(g4), pair, nk.clip_lo,
-                                            (static_cast<uint32_t>(g4 >> 32) & 0x3fffu) << 16 | nk.clip_hi16), rk);
-  const float2 p0 = box_muller16(r.x, c2, trig), p1 = box_muller16(r.y, c2, trig), p2 = box_muller16(r.z, c2, trig),
-               p3 = box_muller16(r.w, c2, trig);
+struct GroupStream {
+  uint32_t s0, s1, s2, s3;
+};
+
+__device__ __forceinline__ GroupStream group_stream_init(uint64_t g4, const NoiseKey& nk, const uint32_t (&rk)[20]) {
+  const uint4 r = Philox::run_rk(make_uint4(static_cast<uint32_t>(g4), 0u, nk.clip_lo,
+                                            0x40000000u | (static_cast<uint32_t>(g4 >> 32) & 0x3fffu) << 16 | nk.clip_hi16), rk);
+  GroupStream s{r.x, r.y, r.z, r.w};
+  if ((s.s0 | s.s1 | s.s2 | s.s3) == 0u) s.s0 = 0x9E3779B9u;      // the all-zero state is the generator's only fixed point
+  return s;
+}
+
+__device__ __forceinline__ uint32_t group_stream_next(GroupStream& s) {      // xoshiro128++
+  const uint32_t r = __funnelshift_l(s.s0 + s.s3, s.s0 + s.s3, 7) + s.s0;
+  const uint32_t t = s.s1 << 9;
+  const uint32_t n1 = s.s1 ^ s.s2 ^ s.s0, n0 = s.s0 ^ s.s3 ^ s.s1, n2 = s.s2 ^ s.s0 ^ t, x3 = s.s3 ^ s.s1;
+  s.s0 = n0;
+  s.s1 = n1;
+  s.s2 = n2;
+  s.s3 = __funnelshift_l(x3, x3, 11);
+  return r;
+}
+
+// Base noise of one aligned 4-pixel group for the NEXT pair of intervals, already multiplied by float(base_noise_std):
+// even[k] belongs to pixel 4*g4+k at the even interval of the pair, odd[k] at the odd one.  Advances the stream.
+__device__ __forceinline__ void stream_noise8(GroupStream& s, float c2, const float2* trig, float (&even)[4], float (&odd)[4]) {
+  const uint32_t w0 = group_stream_next(s), w1 = group_stream_next(s), w2 = group_stream_next(s), w3 = group_stream_next(s);
+  const float2 p0 = box_muller16(w0, c2, trig), p1 = box_muller16(w1, c2, trig), p2 = box_muller16(w2, c2, trig),
+               p3 = box_muller16(w3, c2, trig);
   even[0] = p0.x; odd[0] = p0.y;
   even[1] = p1.x; odd[1] = p1.y;
   even[2] = p2.x; odd[2] = p2.y;
   even[3] = p3.x; odd[3] = p3.y;
-}
-
-// Same values for one pixel and one interval (generic kernel, field dump).
-__device__ __forceinline__ float philox_noise1(uint64_t px, uint32_t interval, const NoiseKey& nk, const uint32_t (&rk)[20], float c2,
-                                               const float2* trig) {
-  float ev[4], od[4];
-  philox_noise8(px >> 2, interval >> 1, nk, rk, c2, trig, ev, od);
-  const int k = static_cast<int>(px & 3);
-  const float e = k == 0 ? ev[0] : k == 1 ? ev[1] : k == 2 ? ev[2] : ev[3];
-  const float o = k == 0 ? od[0] : k == 1 ? od[1] : k == 2 ? od[2] : od[3];
-  return (interval & 1u) ? o : e;
 }
 
 __device__ __forceinline__ void philox_init_pixel(uint64_t px, const NoiseKey& nk, const uint32_t (&rk)[20], double hot_fraction,

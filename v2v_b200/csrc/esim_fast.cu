@@ -91,7 +91,8 @@ __global__ void __launch_bounds__(kFastThreads, CTAS) esim_fast_kernel(const Esi
   const int N = d.N;
   const int64_t clip_pix = static_cast<int64_t>(b) * HW + pix0;
   const NoiseKey nkey = make_noise_key(d.clip_index_base + static_cast<uint64_t>(b));
-  const uint64_t g4 = static_cast<uint64_t>(pix0) >> 2;
+  GroupStream gs{0u, 0u, 0u, 0u};
+  if (NOISE == V2V_NOISE_PHILOX) gs = group_stream_init(static_cast<uint64_t>(pix0) >> 2, nkey, a.rk);
 
   const double pos = d.pos_thres[b], neg = d.neg_thres[b];
   const double mneg = -neg;
@@ -244,12 +245,12 @@ __global__ void __launch_bounds__(kFastThreads, CTAS) esim_fast_kernel(const Esi
       for (int u = 0; u < kPF; ++u) nxt[u] = ld_stream_u32(fr + static_cast<int64_t>(i + kPF + u) * HW);
     }
     if (NOISE == V2V_NOISE_PHILOX) {
-      // intervals i-1 .. i+2 = 4t .. 4t+3: two Philox calls, 8 normals each
+      // intervals i-1 .. i+2 = 4t .. 4t+3: two draws of the group's stream, 8 normals each
       float e0[4], o0[4], e1[4], o1[4];
-      philox_noise8(g4, static_cast<uint32_t>(2 * t), nkey, a.rk, nc2, trig_s, e0, o0);
+      stream_noise8(gs, nc2, trig_s, e0, o0);
       step(cur[0], e0);
       step(cur[1], o0);
-      philox_noise8(g4, static_cast<uint32_t>(2 * t + 1), nkey, a.rk, nc2, trig_s, e1, o1);
+      stream_noise8(gs, nc2, trig_s, e1, o1);
       step(cur[2], e1);
       step(cur[3], o1);
     } else {
@@ -261,15 +262,17 @@ __global__ void __launch_bounds__(kFastThreads, CTAS) esim_fast_kernel(const Esi
     for (int u = 0; u < kPF; ++u) cur[u] = nxt[u];
     if (STATS && (t & (kFlushTrips - 1)) == kFlushTrips - 1) flush_stats();
   }
-  for (; i < N; ++i) {                                                // ragged tail (< kPF intervals)
-    float bn1[4] = {0.f, 0.f, 0.f, 0.f};
-    if (NOISE == V2V_NOISE_PHILOX) {
-      float ev[4], od[4];
-      philox_noise8(g4, static_cast<uint32_t>(i - 1) >> 1, nkey, a.rk, nc2, trig_s, ev, od);
+  {
+    float tev[4] = {0.f, 0.f, 0.f, 0.f}, tod[4] = {0.f, 0.f, 0.f, 0.f};
+    for (; i < N; ++i) {                                              // ragged tail (< kPF intervals; starts at an even interval)
+      float bn1[4] = {0.f, 0.f, 0.f, 0.f};
+      if (NOISE == V2V_NOISE_PHILOX) {
+        if (((i - 1) & 1) == 0) stream_noise8(gs, nc2, trig_s, tev, tod);
 #pragma unroll
-      for (int k = 0; k < 4; ++k) bn1[k] = ((i - 1) & 1) ? od[k] : ev[k];
+        for (int k = 0; k < 4; ++k) bn1[k] = ((i - 1) & 1) ? tod[k] : tev[k];
+      }
+      step(ld_stream_u32(fr + static_cast<int64_t>(i) * HW), bn1);
     }
-    step(ld_stream_u32(fr + static_cast<int64_t>(i) * HW), bn1);
   }
 
   if (d.potential_out) {
@@ -305,8 +308,8 @@ int launch_esim_fast(const EsimArgs& a, cudaStream_t s) {
   const bool ph = a.d.noise_mode == V2V_NOISE_PHILOX, fr = a.d.frame_out_mode != 0, st = a.d.stats != nullptr;
   // resident CTAs per SM the register allocator must allow (4 -> 128 regs, 6 -> 80, 8 -> 64), chosen per
   // variant from same-box sweeps on B200 (profiles/r01_esim_minb_sweep.txt); V2V_ESIM_CTAS overrides for tuning.
-  // The Philox variants need 94-100 registers, so 5 CTAs are resident under the 4-CTA bound.
-  int ctas = ph ? 4 : 8;
+  // (Philox without statistics needs 96 registers: 5 CTAs are resident under the 4-CTA bound.)
+  int ctas = ph ? (st ? 6 : 4) : 8;
   if (const char* e = getenv("V2V_ESIM_CTAS")) ctas = atoi(e);
   const size_t smem = 256 * kLutCopies * sizeof(double) + (ph ? kTrigEntries * sizeof(float2) : 0);
 #define V2V_G(NM, FR, ST, CT)                                                                                     \

@@ -80,7 +80,6 @@ __global__ void __launch_bounds__(kThreads, 4) v2e_fast_kernel(const V2eArgs a) 
   float2* trig_s = reinterpret_cast<float2*>(dyn + kLutBytes + kFacBytes + kLogfBytes);
   double* rcp_s = reinterpret_cast<double*>(dyn + kLutBytes + kFacBytes + kLogfBytes + (LEAK && PHILOX ? kTrigBytes : 0));   // [4][2][kThreads] 1/thr
   IntervalRow* itab = reinterpret_cast<IntervalRow*>(reinterpret_cast<unsigned char*>(rcp_s) + (BF ? kRcpBytes : 0));
-  __shared__ unsigned long long cta_stats[2];
 
   const v2v_v2e_desc& d = a.d;
   // float32-state variant: conversion unit 71 % busy in ncu -> integer rounding and int->float by FP64/FP32 adds instead;
@@ -88,7 +87,6 @@ __global__ void __launch_bounds__(kThreads, 4) v2e_fast_kernel(const V2eArgs a) 
   constexpr bool kMagic = F32STATE;
   const int N = d.N, b = blockIdx.y;
   if (LEAK && PHILOX) fill_trig_table(trig_s);
-  if (threadIdx.x < 2) cta_stats[threadIdx.x] = 0ull;
   for (int i = threadIdx.x; i < 256; i += kThreads) {
     const double it = __ddiv_rn(__dadd_rn(static_cast<double>(i), 20.0), 275.0);       // :190
     lut2[i] = make_double2(static_cast<double>(d.lut[i]), it);
@@ -383,17 +381,12 @@ __global__ void __launch_bounds__(kThreads, 4) v2e_fast_kernel(const V2eArgs a) 
       sp += ok ? op : 0ull;
       sn += ok ? on : 0ull;
     }
-    if ((threadIdx.x & 31) == (__ffs(m) - 1)) {
-      atomicAdd(&cta_stats[0], sp);
-      atomicAdd(&cta_stats[1], sn);
+    if ((threadIdx.x & 31) == (__ffs(m) - 1)) {      // one pair of global reductions per warp: no CTA barrier, no shared stage
+      if (sp) atomicAdd(reinterpret_cast<unsigned long long*>(d.stats + 2 * b), sp);
+      if (sn) atomicAdd(reinterpret_cast<unsigned long long*>(d.stats + 2 * b) + 1, sn);
     }
   }
   }  // valid
-  if (want_stats) {
-    __syncthreads();
-    if (threadIdx.x < 2 && cta_stats[threadIdx.x])
-      atomicAdd(reinterpret_cast<unsigned long long*>(d.stats + 2 * b) + threadIdx.x, cta_stats[threadIdx.x]);
-  }
 }
 
 size_t fast_smem_bytes(const V2eArgs& a, bool trig, bool bf) {
