@@ -117,6 +117,24 @@ struct Philox {
   }
 };
 
+// ---- xoshiro128++ (Blackman & Vigna): the sequential generator behind the per-pixel-group noise streams ----------
+// Seeded from Philox4x32-10 (one counter per stream), so streams of different groups / clips are independent and the
+// values do not depend on launch geometry; 9 instructions per 32-bit word.
+struct GroupStream {
+  uint32_t s0, s1, s2, s3;
+};
+
+__device__ __forceinline__ uint32_t group_stream_next(GroupStream& s) {      // xoshiro128++
+  const uint32_t r = __funnelshift_l(s.s0 + s.s3, s.s0 + s.s3, 7) + s.s0;
+  const uint32_t t = s.s1 << 9;
+  const uint32_t n1 = s.s1 ^ s.s2 ^ s.s0, n0 = s.s0 ^ s.s3 ^ s.s1, n2 = s.s2 ^ s.s0 ^ t, x3 = s.s3 ^ s.s1;
+  s.s0 = n0;
+  s.s1 = n1;
+  s.s2 = n2;
+  s.s3 = __funnelshift_l(x3, x3, 11);
+  return r;
+}
+
 // Two scaled normals from ONE 32-bit word (Box-Muller): the low 20 bits give the radius (lg2 + sqrt on the SFU,
 // tail cut at sqrt(2 ln 2^20) = 5.27 sigma), the high 12 bits pick one of 4096 directions from a (cos, sin) table in
 // shared memory (bin centres, filled once per CTA), so one Philox4x32 call yields 8 normals with 2 SFU ops each.

@@ -42,27 +42,12 @@ __device__ __forceinline__ NoiseKey make_noise_key(uint64_t clip_id) {
 
 __device__ __forceinline__ float noise_c2(float scale) { return -1.3862943611198906f * scale * scale; }
 
-struct GroupStream {
-  uint32_t s0, s1, s2, s3;
-};
-
 __device__ __forceinline__ GroupStream group_stream_init(uint64_t g4, const NoiseKey& nk, const uint32_t (&rk)[20]) {
   const uint4 r = Philox::run_rk(make_uint4(static_cast<uint32_t>(g4), 0u, nk.clip_lo,
                                             0x40000000u | (static_cast<uint32_t>(g4 >> 32) & 0x3fffu) << 16 | nk.clip_hi16), rk);
   GroupStream s{r.x, r.y, r.z, r.w};
   if ((s.s0 | s.s1 | s.s2 | s.s3) == 0u) s.s0 = 0x9E3779B9u;      // the all-zero state is the generator's only fixed point
   return s;
-}
-
-__device__ __forceinline__ uint32_t group_stream_next(GroupStream& s) {      // xoshiro128++
-  const uint32_t r = __funnelshift_l(s.s0 + s.s3, s.s0 + s.s3, 7) + s.s0;
-  const uint32_t t = s.s1 << 9;
-  const uint32_t n1 = s.s1 ^ s.s2 ^ s.s0, n0 = s.s0 ^ s.s3 ^ s.s1, n2 = s.s2 ^ s.s0 ^ t, x3 = s.s3 ^ s.s1;
-  s.s0 = n0;
-  s.s1 = n1;
-  s.s2 = n2;
-  s.s3 = __funnelshift_l(x3, x3, 11);
-  return r;
 }
 
 // Base noise of one aligned 4-pixel group for the NEXT pair of intervals, already multiplied by float(base_noise_std):

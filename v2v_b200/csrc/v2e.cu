@@ -50,6 +50,10 @@ __global__ void __launch_bounds__(kV2eThreads) v2e_kernel(const V2eArgs a) {
   const int N = d.N;
   const int64_t mp = static_cast<int64_t>(b) * HW + pix0;
   const uint64_t clip_id = d.clip_index_base + static_cast<uint64_t>(b);
+  const bool leak_on = d.leak_rate_hz > 0.0;
+  GroupStream gs{0u, 0u, 0u, 0u};
+  float lodd[4] = {0.f, 0.f, 0.f, 0.f};
+  if (d.noise_mode == V2V_NOISE_PHILOX) gs = v2e_stream_init(static_cast<uint64_t>(pix0) >> 2, clip_id, a.rk);
   const bool philox = d.noise_mode == V2V_NOISE_PHILOX, explicit_noise = d.noise_mode == V2V_NOISE_EXPLICIT;
 
   double pth[P], nth[P], lp[P], base[P];
@@ -126,16 +130,15 @@ __global__ void __launch_bounds__(kV2eThreads) v2e_kernel(const V2eArgs a) {
           for (int k = 0; k < P; ++k) { sp[k] = d.pos_shot[fo + k]; sn[k] = d.neg_shot[fo + k]; }
         }
       } else if (philox && (LEAK || SHOT)) {
-        float lz[4] = {0.f, 0.f, 0.f, 0.f}, lo[4] = {0.f, 0.f, 0.f, 0.f}, up[4] = {1.f, 1.f, 1.f, 1.f}, un[4] = {1.f, 1.f, 1.f, 1.f};
-        const uint64_t g4 = static_cast<uint64_t>(pix0) >> 2;
-        if (SHOT) v2e_shot_uniforms(g4, static_cast<uint32_t>(i - 1), clip_id, a.rk, up, un);
-        if (LEAK) {
-          v2e_leak_normals(g4, static_cast<uint32_t>(i - 1) >> 1, clip_id, a.rk, trig_s, lz, lo);
-          if ((i - 1) & 1) {
+        float lz[4] = {0.f, 0.f, 0.f, 0.f}, up[4] = {1.f, 1.f, 1.f, 1.f}, un[4] = {1.f, 1.f, 1.f, 1.f};
+        if (LEAK && leak_on) {                       // stream order: leak pair (even intervals), then shot
+          if (((i - 1) & 1) == 0) v2e_leak_normals(gs, trig_s, lz, lodd);
+          else {
 #pragma unroll
-            for (int k = 0; k < 4; ++k) lz[k] = lo[k];
+            for (int k = 0; k < 4; ++k) lz[k] = lodd[k];
           }
         }
+        if (SHOT) v2e_shot_uniforms(gs, up, un);
 #pragma unroll
         for (int k = 0; k < P; ++k) {
           const int j = P == 4 ? k : static_cast<int>(pix0 & 3);
@@ -340,16 +343,17 @@ __global__ void v2e_philox_fields_kernel(const V2eArgs a, double* leak_randn, in
   const float ppf = v2e_pre_prob(d.pos_thres_nominal, d.pos_thres[mp]);
   const float npf = v2e_pre_prob(d.neg_thres_nominal, d.neg_thres[mp]);
   const int j = static_cast<int>(pix & 3);
+  GroupStream gs = v2e_stream_init(static_cast<uint64_t>(pix) >> 2, clip_id, a.rk);
+  float lodd[4] = {0.f, 0.f, 0.f, 0.f};
   for (int i = 1; i < d.N; ++i) {
-    float lz[4] = {0.f, 0.f, 0.f, 0.f}, lo[4] = {0.f, 0.f, 0.f, 0.f}, up[4] = {1.f, 1.f, 1.f, 1.f}, un[4] = {1.f, 1.f, 1.f, 1.f};
-    const uint64_t g4 = static_cast<uint64_t>(pix) >> 2;
-    if (shot) v2e_shot_uniforms(g4, static_cast<uint32_t>(i - 1), clip_id, a.rk, up, un);
+    float lz[4] = {0.f, 0.f, 0.f, 0.f}, up[4] = {1.f, 1.f, 1.f, 1.f}, un[4] = {1.f, 1.f, 1.f, 1.f};
     if (leak) {
-      v2e_leak_normals(g4, static_cast<uint32_t>(i - 1) >> 1, clip_id, a.rk, trig_s, lz, lo);
-      if ((i - 1) & 1) {
-        for (int k = 0; k < 4; ++k) lz[k] = lo[k];
+      if (((i - 1) & 1) == 0) v2e_leak_normals(gs, trig_s, lz, lodd);
+      else {
+        for (int k = 0; k < 4; ++k) lz[k] = lodd[k];
       }
     }
+    if (shot) v2e_shot_uniforms(gs, up, un);
     const int64_t o = (static_cast<int64_t>(b) * (d.N - 1) + (i - 1)) * a.HW + pix;
     if (leak_randn) leak_randn[o] = static_cast<double>(lz[j]);
     if (shot && pos_shot && neg_shot) {

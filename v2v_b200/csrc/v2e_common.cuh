@@ -20,15 +20,21 @@ __device__ __forceinline__ double count_floor(double a, double thr) {
   return floor_div_exact(a, thr, __drcp_rn(thr));
 }
 
-// ---- Philox draws of the v2e model -------------------------------------------------------------------------
+// ---- random draws of the v2e model ----------------------------------------------------------------------------
 // Every kernel (generic, fast, field dump) draws the same values for the same (seed, clip, pixel, interval),
-// independent of launch geometry.  Per aligned group of 4 pixels:
-//   shot noise : one call per interval, counter (group lo32, interval, clip lo32, tag1|group hi|clip hi16);
-//                word k -> pixel k: low 16 bits = uniform of the ON draw, high 16 bits = OFF draw (bin centres)
-//   leak jitter: one call per PAIR of intervals, counter (group lo32, interval/2, clip lo32, tag3|...);
-//                word k -> pixel k: one Box-Muller pair, .x for the even interval, .y for the odd one
-__device__ __forceinline__ uint32_t v2e_ctr_hi(uint64_t g4, uint64_t clip_id) {
-  return (static_cast<uint32_t>(g4 >> 32) & 0x3fffu) << 16 | static_cast<uint32_t>((clip_id >> 32) & 0xffffu);
+// independent of launch geometry: one xoshiro128++ stream per aligned group of 4 pixels and clip, seeded with the
+// Philox4x32-10 output of counter (group lo32, 0, clip lo32, tag2|group hi|clip hi16).  Interval j (0-based) consumes,
+// in this order:
+//   leak jitter (only if leak_rate_hz > 0, only when j is even): four words, word k -> pixel k: one Box-Muller pair,
+//                .x for interval j, .y for interval j+1;
+//   shot noise  (only if shot_noise_rate_hz > 0): four words, word k -> pixel k: low 16 bits = uniform of the ON draw,
+//                high 16 bits = OFF draw (bin centres).
+__device__ __forceinline__ GroupStream v2e_stream_init(uint64_t g4, uint64_t clip_id, const uint32_t (&rk)[20]) {
+  const uint32_t hi = (static_cast<uint32_t>(g4 >> 32) & 0x3fffu) << 16 | static_cast<uint32_t>((clip_id >> 32) & 0xffffu);
+  const uint4 r = Philox::run_rk(make_uint4(static_cast<uint32_t>(g4), 0u, static_cast<uint32_t>(clip_id), 0x80000000u | hi), rk);
+  GroupStream s{r.x, r.y, r.z, r.w};
+  if ((s.s0 | s.s1 | s.s2 | s.s3) == 0u) s.s0 = 0x9E3779B9u;
+  return s;
 }
 
 // (h + 0.5) / 65536 for a 16-bit h, through the mantissa (no int->float conversion)
@@ -36,29 +42,23 @@ __device__ __forceinline__ float v2e_u16(uint32_t h) {
   return __uint_as_float(0x3f800000u | (h << 7)) - 0.99999237060546875f;
 }
 
-__device__ __forceinline__ void v2e_shot_uniforms(uint64_t g4, uint32_t interval, uint64_t clip_id, const uint32_t (&rk)[20],
-                                                  float (&up)[4], float (&un)[4]) {
-  const uint4 r = Philox::run_rk(make_uint4(static_cast<uint32_t>(g4), interval, static_cast<uint32_t>(clip_id),
-                                            0x40000000u | v2e_ctr_hi(g4, clip_id)), rk);
-  const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+__device__ __forceinline__ void v2e_shot_uniforms(GroupStream& s, float (&up)[4], float (&un)[4]) {
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
-    up[k] = v2e_u16(w[k] & 0xffffu);
-    un[k] = v2e_u16(w[k] >> 16);
+    const uint32_t w = group_stream_next(s);
+    up[k] = v2e_u16(w & 0xffffu);
+    un[k] = v2e_u16(w >> 16);
   }
 }
 
-__device__ __forceinline__ void v2e_leak_normals(uint64_t g4, uint32_t pair, uint64_t clip_id, const uint32_t (&rk)[20],
-                                                 const float2* trig, float (&even)[4], float (&odd)[4]) {
-  const uint4 r = Philox::run_rk(make_uint4(static_cast<uint32_t>(g4), pair, static_cast<uint32_t>(clip_id),
-                                            0xC0000000u | v2e_ctr_hi(g4, clip_id)), rk);
+__device__ __forceinline__ void v2e_leak_normals(GroupStream& s, const float2* trig, float (&even)[4], float (&odd)[4]) {
   const float c2 = -1.3862943611198906f;      // -2 ln 2: unit variance
-  const float2 p0 = box_muller16(r.x, c2, trig), p1 = box_muller16(r.y, c2, trig), p2 = box_muller16(r.z, c2, trig),
-               p3 = box_muller16(r.w, c2, trig);
-  even[0] = p0.x; odd[0] = p0.y;
-  even[1] = p1.x; odd[1] = p1.y;
-  even[2] = p2.x; odd[2] = p2.y;
-  even[3] = p3.x; odd[3] = p3.y;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const float2 p = box_muller16(group_stream_next(s), c2, trig);
+    even[k] = p.x;
+    odd[k] = p.y;
+  }
 }
 
 // shot-noise Poisson rate of one pixel (float32, statistical mode): fac(v) * nominal/thres * per-frame scale (:90-99).

@@ -115,7 +115,9 @@ __global__ void __launch_bounds__(kThreads, 4) v2e_fast_kernel(const V2eArgs a) 
   if (pix0 < HW) {
   const int64_t mp = static_cast<int64_t>(b) * HW + pix0;
   const uint64_t clip_id = d.clip_index_base + static_cast<uint64_t>(b);
-  const uint64_t g4 = static_cast<uint64_t>(pix0) >> 2;
+  GroupStream gs{0u, 0u, 0u, 0u};
+  if (PHILOX) gs = v2e_stream_init(static_cast<uint64_t>(pix0) >> 2, clip_id, a.rk);
+  const bool leak_on = d.leak_rate_hz > 0.0;       // the leak variant also serves a float64 state with the leak switched off
 
   double pth[4], nth[4], lp[4], base[4];
   float basef[F32STATE ? 4 : 1], pthf[F32STATE ? 4 : 1], nthf[F32STATE ? 4 : 1];
@@ -322,13 +324,13 @@ __global__ void __launch_bounds__(kThreads, 4) v2e_fast_kernel(const V2eArgs a) 
       w1 = w2;
       if (j + 4 < N) w2 = ld_stream_u32(fr + static_cast<int64_t>(j + 4) * HW);
       float lz[4] = {0.f, 0.f, 0.f, 0.f};
-      if (LEAK && PHILOX) {
-        if ((j & 1) == 0) v2e_leak_normals(g4, static_cast<uint32_t>(j) >> 1, clip_id, a.rk, trig_s, le, lo);
+      if (LEAK && PHILOX && leak_on) {
+        if ((j & 1) == 0) v2e_leak_normals(gs, trig_s, le, lo);
 #pragma unroll
         for (int k = 0; k < 4; ++k) lz[k] = (j & 1) ? lo[k] : le[k];
       }
       float up[4], un[4];
-      v2e_shot_uniforms(g4, static_cast<uint32_t>(j), clip_id, a.rk, up, un);
+      v2e_shot_uniforms(gs, up, un);
       step(w, j, lz, up, un);
     }
   } else {
@@ -349,7 +351,7 @@ __global__ void __launch_bounds__(kThreads, 4) v2e_fast_kernel(const V2eArgs a) 
 #pragma unroll
     for (int h = 0; h < kPF / 2; ++h) {           // interval pairs (i-1+2h, i+2h)
       float le[4] = {0.f, 0.f, 0.f, 0.f}, lo[4] = {0.f, 0.f, 0.f, 0.f};
-      if (LEAK && PHILOX) v2e_leak_normals(g4, static_cast<uint32_t>(i - 1 + 2 * h) >> 1, clip_id, a.rk, trig_s, le, lo);
+      if (LEAK && PHILOX && leak_on) v2e_leak_normals(gs, trig_s, le, lo);
       step(cur[2 * h], i - 1 + 2 * h, le, one4, one4);
       step(cur[2 * h + 1], i + 2 * h, lo, one4, one4);
     }
@@ -357,12 +359,14 @@ __global__ void __launch_bounds__(kThreads, 4) v2e_fast_kernel(const V2eArgs a) 
 #pragma unroll
     for (int u = 0; u < kPF; ++u) cur[u] = nxt[u];
   }
-  for (; i < N; ++i) {                                                   // ragged tail (< kPF intervals)
+  {
     float le[4] = {0.f, 0.f, 0.f, 0.f}, lo[4] = {0.f, 0.f, 0.f, 0.f}, lz[4];
-    if (LEAK && PHILOX) v2e_leak_normals(g4, static_cast<uint32_t>(i - 1) >> 1, clip_id, a.rk, trig_s, le, lo);
+    for (; i < N; ++i) {                                                 // ragged tail (< kPF intervals; starts at an even interval)
+      if (LEAK && PHILOX && leak_on && ((i - 1) & 1) == 0) v2e_leak_normals(gs, trig_s, le, lo);
 #pragma unroll
-    for (int k = 0; k < 4; ++k) lz[k] = ((i - 1) & 1) ? lo[k] : le[k];
-    step(ld_stream_u32(fr + static_cast<int64_t>(i) * HW), i - 1, lz, one4, one4);
+      for (int k = 0; k < 4; ++k) lz[k] = ((i - 1) & 1) ? lo[k] : le[k];
+      step(ld_stream_u32(fr + static_cast<int64_t>(i) * HW), i - 1, lz, one4, one4);
+    }
   }
   }
 
