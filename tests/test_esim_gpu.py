@@ -386,3 +386,39 @@ def test_full_size_clip_bit_exact_vs_c_oracle(cuda_device):
     assert np.array_equal(o.potential[0].cpu().numpy(), pot)
     st = o.stats[0].cpu().numpy()
     assert st[0] == int(np.maximum(ref, 0).sum()) and st[1] == int(np.maximum(-ref, 0).sum())
+
+
+def test_noise_field_distribution_and_independence(cuda_device):
+    """Statistical audit of the in-kernel generator (Philox-seeded xoshiro128++ streams + table Box-Muller) on the dumped
+    base-noise field: moments, Kolmogorov distance to the normal law, tails, and the correlations the construction could
+    plausibly introduce (the two normals of a Box-Muller pair = consecutive intervals, the four pixels of a group =
+    consecutive stream words, neighbouring groups = different streams, consecutive pairs of one stream, different clips)."""
+    from scipy import stats as sst
+    from v2v_b200.esim import philox_fields
+    n, h, w = 65, 96, 128
+    _, _, bn = philox_fields(n, h, w, base_noise_std=[1.0, 1.0], hot_pixel_fraction=[0.0, 0.0], hot_pixel_std=[0.0, 0.0], seed=77)
+    z = bn.cpu().numpy()                                   # [2, 64, h, w], unit variance
+    x = z.ravel()
+    m = x.size
+    assert abs(x.mean()) < 5 / np.sqrt(m)
+    assert abs(x.var() - 1) < 5 * np.sqrt(2 / m)
+    assert abs(sst.skew(x)) < 5 * np.sqrt(6 / m)
+    assert abs(sst.kurtosis(x)) < 5 * np.sqrt(24 / m) + 2e-3      # 20-bit radius: the tail is cut at 5.27 sigma
+    sub = x[:: 7][:400_000]
+    assert sst.kstest(sub, "norm").statistic < 1.95 / np.sqrt(sub.size)   # alpha ~ 1e-3
+    for t in (1.0, 2.0, 3.0, 4.0):                          # two-sided tail mass
+        p = 2 * sst.norm.sf(t)
+        assert abs((np.abs(x) > t).mean() - p) < 5 * np.sqrt(p / m) + 1e-7
+    assert np.abs(x).max() < 5.3
+
+    def corr(a, b):
+        return float(np.corrcoef(a.ravel(), b.ravel())[0, 1])
+
+    lim = 5 / np.sqrt(m / 2)
+    assert abs(corr(z[:, 0::2], z[:, 1::2])) < lim                                  # the two normals of one Box-Muller pair
+    assert abs(corr(z[:, 0::2] ** 2, z[:, 1::2] ** 2)) < lim                         # ... and their magnitudes
+    assert abs(corr(z[:, 0:-2:2], z[:, 2::2])) < lim                                 # consecutive pairs of one stream
+    assert abs(corr(z[..., 0::4], z[..., 1::4])) < lim and abs(corr(z[..., 1::4], z[..., 2::4])) < lim   # pixels of a group
+    assert abs(corr(z[..., 3:-4:4], z[..., 4::4])) < lim                             # neighbouring groups (different streams)
+    assert abs(corr(z[..., :-1, :], z[..., 1:, :])) < lim                            # neighbouring rows
+    assert abs(corr(z[0], z[1])) < lim                                                # different clips, same seed
