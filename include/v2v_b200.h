@@ -95,6 +95,13 @@ typedef struct v2v_esim_desc {
   int64_t voxel_plane_stride;    /* elements between planes (0 -> H*W); pads are NOT written */
   float* frame_out;              /* [B,T or T+1,1,H,W] float32 = frame/255, or NULL     */
   long long* stats;              /* [B,2] int64 += {positive events, negative events}, or NULL */
+  /* optional frame-side packing fused into the pass: the dataset's pause gather
+   * `all_imgs = np.stack([raw_imgs[i] for i in img_idxes])` (data/v2v_datasets.py:285-311) and the HDR/LDR degrade
+   * `np.clip((img-127.5)*scale+127.5, 0, 255).astype(np.uint8)` (:473-483), a function of the pixel value alone */
+  const int32_t* frame_index;    /* [B,N] raw frame used as frame n of the clip (clamped to the clip), or NULL = identity */
+  int32_t raw_frames_per_clip;   /* frames per clip in `frames` when frame_index is given ([B,M,H,W]); 0 = N              */
+  int32_t reserved0;
+  const uint8_t* value_map;      /* [B,256] uint8 -> uint8 applied to every pixel before the LUT and frame_out, or NULL   */
 } v2v_esim_desc;
 
 int v2v_esim_frames_to_voxel(const v2v_esim_desc* desc, void* stream);
@@ -244,6 +251,11 @@ int v2v_pack_events_n5(const void* xs, int xs_dtype, const void* ys, int ys_dtyp
 int v2v_voxel_add_noise(float* voxel, int64_t n, const double* noise, const double* mask_u, double noise_std,
                         double noise_fraction, int integer_noise, int philox, uint64_t seed, uint64_t stream_id, void* stream);
 /* voxel [planes, hw] float32 += map [hw] float64 for every plane. */
+/* bgr_to_gray of the dataset (data/v2v_datasets.py:19-22): gray = uint8(dot(img[..., :3], [0.5870, 0.1140, 0.2989])),
+ * evaluated as fma(c2, w2, fma(c1, w1, c0*w0)) in float64 (what NumPy's dot computes for a length-3 row on FMA hosts;
+ * pinned by tests/golden), truncated toward zero.  `channels` >= 3 values per pixel, the first three are used. */
+int v2v_bgr_to_gray(const uint8_t* img, int32_t channels, uint8_t* gray, int64_t num_pixels, void* stream);
+
 int v2v_voxel_add_map(float* voxel, int64_t planes, int64_t hw, const double* map, void* stream);
 
 #ifdef __cplusplus

@@ -478,3 +478,32 @@ def event_count_map(xs, ys, height, width):
     cnt = np.zeros((height, width), dtype=np.int64)
     np.add.at(cnt, (np.asarray(ys).astype(np.int64), np.asarray(xs).astype(np.int64)), 1)
     return cnt
+
+
+# ---- frame-side packing of the dataset ------------------------------------------------------
+
+def pause_indices(count, proba_pause_when_running, proba_pause_when_paused, rs=np.random):
+    """Pause sequence of WebvidDatasetV2.__getitem__ (data/v2v_datasets.py:285-301): ``count`` indices into the raw
+    clip, one ``rs.rand()`` per frame in the reference's order.  Returns (img_idxes, true_img_cnt)."""
+    img_idxes, idx, is_pause = [], 0, False
+    for _ in range(count):
+        img_idxes.append(idx)
+        if is_pause and rs.rand() > proba_pause_when_paused:
+            is_pause = False
+        elif not is_pause and rs.rand() < proba_pause_when_running:
+            is_pause = True
+        if not is_pause:
+            idx += 1
+    return np.asarray(img_idxes, dtype=np.int64), idx + 1
+
+
+def degrade_video(imgs, kind, rs=np.random):
+    """HDR / LDR degrade (data/v2v_datasets.py:473-483): one ``rs.uniform`` for the scale, then per frame
+    ``np.clip((img-127.5)*scale+127.5, 0, 255).astype(np.uint8)``.  Returns (list of frames, scale)."""
+    scale = rs.uniform(1, 3) if kind == "hdr" else rs.uniform(0.3, 1)
+    return [np.clip((im - 127.5) * scale + 127.5, 0, 255).astype(np.uint8) for im in imgs], scale
+
+
+def bgr_to_gray(img_stack):
+    """data/v2v_datasets.py:19-22 (the float64 summation order is NumPy's / the BLAS kernel's: pinned by tests/golden)."""
+    return np.dot(img_stack[..., :3], [0.5870, 0.1140, 0.2989]).astype(np.uint8)

@@ -315,12 +315,66 @@ def gen_scatter(testh5, eu, out):
                               ref=ref)
 
 
+def gen_frames(dsets, out):
+    """Frame-side packing: pause gather, HDR/LDR degrade, bgr_to_gray — outputs of the reference's own code."""
+    import textwrap
+    # -- pause sequence: the reference has it inline in __getitem__; execute exactly those source lines
+    lines = open(os.path.join(REF, "data", "v2v_datasets.py")).read().split("\n")
+    i0 = next(i for i, l in enumerate(lines) if l.strip() == "img_idxes = []")
+    i1 = next(i for i, l in enumerate(lines) if l.strip() == "true_img_cnt = idx + 1")
+    block = textwrap.dedent("\n".join(lines[i0:i1 + 1]).replace("\t", "    "))
+    for ci, (seed, p_run, p_paused, img_cnt, fpi, add_evs) in enumerate([
+            (0, 0.0102, 0.9791, 24, 5, False), (1, 0.05, 0.9, 24, 5, False), (2, 0.3, 0.5, 10, 10, True),
+            (3, 0.0, 0.9, 8, 5, False), (4, 1.0, 1.0, 6, 5, False), (5, 0.5, 0.0, 12, 5, True)]):
+        fake = types.SimpleNamespace(proba_pause_when_running=p_run, proba_pause_when_paused=p_paused, frames_per_img=fpi,
+                                     output_additional_evs=add_evs)
+        ns = {"np": np, "self": fake, "start_frame": 7, "img_cnt": img_cnt}
+        np.random.seed(seed)
+        exec(block, ns)
+        count = img_cnt * fpi + 1 + (fpi if add_evs else 0)
+        np.random.seed(seed)
+        o_idx, o_cnt = orc.pause_indices(count, p_run, p_paused)
+        assert list(o_idx) == list(ns["img_idxes"]) and o_cnt == ns["true_img_cnt"]
+        out[f"pause_{ci}"] = dict(seed=seed, p_run=p_run, p_paused=p_paused, count=count,
+                                  img_idxes=np.asarray(ns["img_idxes"], dtype=np.int32), true_img_cnt=ns["true_img_cnt"])
+    # -- degrade_video (hdr / ldr)
+    for ci, (kind, seed) in enumerate([("hdr", 0), ("hdr", 1), ("ldr", 2), ("ldr", 3)]):
+        g = np.random.Generator(np.random.PCG64(seed))
+        imgs = [g.integers(0, 256, (12, 16, 1), dtype=np.uint8) for _ in range(5)]
+        imgs[0][:, :, 0].flat[:256] = np.arange(256, dtype=np.uint8)          # every value occurs
+        fake = types.SimpleNamespace(video_degrade=kind)
+        np.random.seed(seed)
+        ref = dsets.WebvidDatasetV2.degrade_video(fake, [im.copy() for im in imgs])
+        np.random.seed(seed)
+        mine, scale = orc.degrade_video([im.copy() for im in imgs], kind)
+        assert all(same(a, b) for a, b in zip(ref, mine))
+        out[f"degrade_{ci}"] = dict(kind=np.array(kind), seed=seed, scale=scale, imgs=np.stack(imgs), ref=np.stack(ref))
+    # -- bgr_to_gray: every colour triple whose exact weighted sum is an integer (the summation order decides the result) + random ones
+    a, b, c = np.meshgrid(np.arange(256), np.arange(256), np.arange(256), indexing="ij")
+    sens = (5870 * a + 1140 * b + 2989 * c) % 10000 == 0
+    tri = np.stack([a[sens], b[sens], c[sens]], -1).astype(np.uint8)
+    g = np.random.Generator(np.random.PCG64(9))
+    tri = np.concatenate([tri, g.integers(0, 256, (20000, 3), dtype=np.uint8)])
+    img = np.concatenate([tri, g.integers(0, 256, (tri.shape[0], 1), dtype=np.uint8)], -1)[None]     # [1, n, 4]: BGRA-like, 4th channel ignored
+    ref = dsets.bgr_to_gray(img)
+    assert same(ref, orc.bgr_to_gray(img))
+    out["bgr_to_gray"] = dict(img=img, ref=ref, n_sensitive=int(sens.sum()))
+
+
 def main():
     esim, v2e, dsets, testh5, eu = import_reference()
-    groups = {"esim": {}, "v2e": {}, "scatter": {}}
-    gen_esim(esim, dsets, groups["esim"])
-    gen_v2e(v2e, groups["v2e"])
-    gen_scatter(testh5, eu, groups["scatter"])
+    only = sys.argv[sys.argv.index("--only") + 1].split(",") if "--only" in sys.argv else None
+    groups = {"esim": {}, "v2e": {}, "scatter": {}, "frames": {}}
+    if only:
+        groups = {k: v for k, v in groups.items() if k in only}
+    if "esim" in groups:
+        gen_esim(esim, dsets, groups["esim"])
+    if "v2e" in groups:
+        gen_v2e(v2e, groups["v2e"])
+    if "scatter" in groups:
+        gen_scatter(testh5, eu, groups["scatter"])
+    if "frames" in groups:
+        gen_frames(dsets, groups["frames"])
     import torch
     meta = dict(numpy=np.__version__, torch=torch.__version__)
     for gname, cases in groups.items():

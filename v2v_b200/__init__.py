@@ -11,11 +11,12 @@ from .esim import (EventEmulator, EsimOutput, esim_log_lut, frames_to_voxel, dra
 from .events import (MakeVoxelMixin, event_count_map, events_to_image, events_to_image_torch,
                      events_to_neg_pos_voxel_torch, events_to_voxel, events_to_voxel_torch, fps_window_offsets, make_voxel,
                      pack_events_n5, voxelize_windows)
-from .datasets import ImgsToVoxelsMixin, V2VVoxelizer, sample_v2e_params
+from .datasets import (ImgsToVoxelsMixin, V2VVoxelizer, bgr_to_gray, degrade_value_map, sample_pause_indices,
+                       sample_v2e_params)
 from .pipeline import HostPipeline
 
 __all__ = [
-    "V2VError", "launch_count", "EventEmulator", "EsimOutput", "esim_log_lut", "frames_to_voxel",
+    "V2VError", "launch_count", "bgr_to_gray", "degrade_value_map", "sample_pause_indices", "EventEmulator", "EsimOutput", "esim_log_lut", "frames_to_voxel",
     "draw_reference_randomness", "philox_fields", "MakeVoxelMixin", "event_count_map", "events_to_image",
     "events_to_image_torch", "events_to_neg_pos_voxel_torch", "events_to_voxel", "events_to_voxel_torch",
     "make_voxel", "voxelize_windows", "fps_window_offsets", "pack_events_n5", "ImgsToVoxelsMixin", "V2VVoxelizer", "sample_v2e_params", "HostPipeline",

@@ -42,6 +42,7 @@ class EsimDesc(C.Structure):
         ("potential_in", _p), ("potential_out", _p),
         ("voxel", _p), ("voxel_row_stride", C.c_int64), ("voxel_plane_stride", C.c_int64),
         ("frame_out", _p), ("stats", _p),
+        ("frame_index", _p), ("raw_frames_per_clip", C.c_int32), ("reserved0", C.c_int32), ("value_map", _p),
     ]
 
 
@@ -100,6 +101,7 @@ SYMBOLS = {
     "v2v_events_to_image": (C.c_int, [C.POINTER(ImageDesc), _p]),
     "v2v_voxel_add_noise": (C.c_int, [_p, C.c_int64, _p, _p, C.c_double, C.c_double, C.c_int, C.c_int, C.c_uint64, C.c_uint64, _p]),
     "v2v_voxel_add_map": (C.c_int, [_p, C.c_int64, C.c_int64, _p, _p]),
+    "v2v_bgr_to_gray": (C.c_int, [_p, C.c_int32, _p, C.c_int64, _p]),
     "v2v_searchsorted_f64": (C.c_int, [_p, C.c_int64, _p, C.c_int64, _p, _p]),
     "v2v_pack_events_n5": (C.c_int, [_p, C.c_int, _p, C.c_int, _p, C.c_int, _p, C.c_int, C.c_int64, _p, _p]),
 }

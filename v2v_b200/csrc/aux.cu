@@ -203,6 +203,34 @@ extern "C" int v2v_voxel_add_noise(float* voxel, int64_t n, const double* noise,
   return V2V_OK;
 }
 
+// bgr_to_gray (data/v2v_datasets.py:19-22): uint8(dot(img[..., :3], [0.5870, 0.1140, 0.2989])).  NumPy evaluates the
+// length-3 dot product as fma(c2, w2, fma(c1, w1, c0*w0)) on FMA hosts (pinned by tests/golden: 261 of the 2^24 colour
+// triples land exactly on an integer in rational arithmetic, and the summation order decides which side they fall on).
+namespace v2v {
+namespace {
+__global__ void bgr_to_gray_kernel(const uint8_t* __restrict__ img, int channels, uint8_t* __restrict__ gray, int64_t n) {
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const uint8_t* p = img + i * channels;
+    const double s = __fma_rn(static_cast<double>(p[2]), 0.2989,
+                              __fma_rn(static_cast<double>(p[1]), 0.1140, __dmul_rn(static_cast<double>(p[0]), 0.5870)));
+    gray[i] = static_cast<uint8_t>(static_cast<int>(s));          // astype(np.uint8) of a value in [0, 255): truncation
+  }
+}
+}  // namespace
+}  // namespace v2v
+
+extern "C" int v2v_bgr_to_gray(const uint8_t* img, int32_t channels, uint8_t* gray, int64_t num_pixels, void* stream) {
+  using namespace v2v;
+  V2V_REQUIRE(num_pixels >= 0 && channels >= 3, V2V_ERR_INVALID_ARG, "need num_pixels >= 0 and channels >= 3");
+  if (num_pixels == 0) return V2V_OK;
+  V2V_REQUIRE(img && gray, V2V_ERR_INVALID_ARG, "NULL pointer");
+  const int64_t blocks = (num_pixels + 255) / 256;
+  bgr_to_gray_kernel<<<static_cast<unsigned int>(blocks < 148 * 32 ? blocks : 148 * 32), 256, 0, static_cast<cudaStream_t>(stream)>>>(img, channels, gray, num_pixels);
+  count_launch();
+  V2V_CUDA(cudaGetLastError());
+  return V2V_OK;
+}
+
 extern "C" int v2v_voxel_add_map(float* voxel, int64_t planes, int64_t hw, const double* map, void* stream) {
   using namespace v2v;
   V2V_REQUIRE(planes >= 0 && hw >= 0, V2V_ERR_INVALID_ARG, "negative size");

@@ -37,7 +37,12 @@ __global__ void __launch_bounds__(kThreads) esim_kernel(const EsimArgs a) {
   __shared__ float2 trig_s[NOISE == V2V_NOISE_PHILOX ? kTrigEntries : 1];
   if (NOISE == V2V_NOISE_PHILOX) fill_trig_table(trig_s);
   const v2v_esim_desc& d = a.d;
-  for (int i = threadIdx.x; i < 256 * LUTC; i += kThreads) lut_s[i] = d.lut[i / LUTC];
+  __shared__ float f255_s[256];                                    // (mapped value)/255 of the ground-truth frame output
+  {
+    const uint8_t* vmap = d.value_map ? d.value_map + static_cast<int64_t>(blockIdx.y) * 256 : nullptr;   // degrade folded into the LUTs
+    for (int i = threadIdx.x; i < 256 * LUTC; i += kThreads) lut_s[i] = d.lut[vmap ? vmap[i / LUTC] : i / LUTC];
+    for (int i = threadIdx.x; i < 256; i += kThreads) f255_s[i] = __fdiv_rn(static_cast<float>(vmap ? vmap[i] : i), 255.0f);
+  }
   __syncthreads();
 
   const int b = blockIdx.y;
@@ -76,9 +81,16 @@ __global__ void __launch_bounds__(kThreads) esim_kernel(const EsimArgs a) {
 
   // ---- initial state ----
   double pot[P], lprev[P], hot[P];
-  const uint8_t* fr = d.frames + (static_cast<int64_t>(b) * N) * HW + pix0;
+  // frame n of the clip = raw frame frame_index[b][n] (pause gather, data/v2v_datasets.py:285-311), or n itself
+  const int Mraw = a.Mraw;
+  const int32_t* fidx = d.frame_index ? d.frame_index + static_cast<int64_t>(b) * N : nullptr;
+  const uint8_t* fr = d.frames + (static_cast<int64_t>(b) * Mraw) * HW + pix0;
+  auto frame_ptr = [&](int n) -> const uint8_t* {
+    const int r = fidx ? min(max(fidx[n], 0), Mraw - 1) : n;
+    return fr + static_cast<int64_t>(r) * HW;
+  };
   {
-    uint32_t w0 = PixWord<P>::load(fr);
+    uint32_t w0 = PixWord<P>::load(frame_ptr(0));
 #pragma unroll
     for (int k = 0; k < P; ++k) lprev[k] = lut_s[((w0 >> (8 * k)) & 0xffu) * LUTC + lutc];
   }
@@ -119,9 +131,9 @@ __global__ void __launch_bounds__(kThreads) esim_kernel(const EsimArgs a) {
                             : nullptr;
 
   if (fout && d.frame_out_mode == 2) {   // frame 0 is an output frame (output_additional_frame)
-    const uint32_t w0 = PixWord<P>::load(fr);
+    const uint32_t w0 = PixWord<P>::load(frame_ptr(0));
 #pragma unroll
-    for (int k = 0; k < P; ++k) fout[k] = __fdiv_rn(static_cast<float>((w0 >> (8 * k)) & 0xffu), 255.0f);
+    for (int k = 0; k < P; ++k) fout[k] = f255_s[(w0 >> (8 * k)) & 0xffu];
   }
 
   // accumulators over frames_per_bin
@@ -140,7 +152,7 @@ __global__ void __launch_bounds__(kThreads) esim_kernel(const EsimArgs a) {
   // ---- register ring of PF frames in flight ----
   uint32_t ring[PF];
 #pragma unroll
-  for (int u = 0; u < PF; ++u) ring[u] = (1 + u < N) ? PixWord<P>::load(fr + static_cast<int64_t>(1 + u) * HW) : 0u;
+  for (int u = 0; u < PF; ++u) ring[u] = (1 + u < N) ? PixWord<P>::load(frame_ptr(1 + u)) : 0u;
 
   for (int i0 = 1; i0 < N; i0 += PF) {
 #pragma unroll
@@ -148,7 +160,7 @@ __global__ void __launch_bounds__(kThreads) esim_kernel(const EsimArgs a) {
       const int i = i0 + u;
       if (i < N) {
         const uint32_t w = ring[u];
-        if (i + PF < N) ring[u] = PixWord<P>::load(fr + static_cast<int64_t>(i + PF) * HW);
+        if (i + PF < N) ring[u] = PixWord<P>::load(frame_ptr(i + PF));
 
         // noise for this interval
         double bn[P];
@@ -239,12 +251,9 @@ __global__ void __launch_bounds__(kThreads) esim_kernel(const EsimArgs a) {
           float* fo = fout + static_cast<int64_t>(tframe) * HW;
           ++tframe;
           if (P == 4) {
-            st_stream_f32x4(fo, __fdiv_rn(static_cast<float>(w & 0xffu), 255.0f),
-                            __fdiv_rn(static_cast<float>((w >> 8) & 0xffu), 255.0f),
-                            __fdiv_rn(static_cast<float>((w >> 16) & 0xffu), 255.0f),
-                            __fdiv_rn(static_cast<float>((w >> 24) & 0xffu), 255.0f));
+            st_stream_f32x4(fo, f255_s[w & 0xffu], f255_s[(w >> 8) & 0xffu], f255_s[(w >> 16) & 0xffu], f255_s[(w >> 24) & 0xffu]);
           } else {
-            st_stream_f32(fo, __fdiv_rn(static_cast<float>(w & 0xffu), 255.0f));
+            st_stream_f32(fo, f255_s[w & 0xffu]);
           }
         }
       }
@@ -356,6 +365,9 @@ extern "C" int v2v_esim_frames_to_voxel(const v2v_esim_desc* desc, void* stream)
   V2V_REQUIRE(d.noise_mode != V2V_NOISE_EXPLICIT || d.base_noise_std || !d.base_gauss, V2V_ERR_INVALID_ARG,
               "EXPLICIT noise with base_gauss needs base_noise_std");
   V2V_REQUIRE(d.frame_out_mode == 0 || d.frame_out, V2V_ERR_INVALID_ARG, "frame_out_mode set but frame_out is NULL");
+  V2V_REQUIRE(d.raw_frames_per_clip >= 0 && (d.frame_index || d.raw_frames_per_clip == 0 || d.raw_frames_per_clip == d.N),
+              V2V_ERR_INVALID_ARG, "raw_frames_per_clip=%d needs frame_index (frames is [B,N,H,W] without it)", d.raw_frames_per_clip);
+  V2V_REQUIRE(!d.frame_index || aligned(d.frame_index, 4), V2V_ERR_ALIGNMENT, "frame_index must be 4-byte aligned");
   V2V_REQUIRE(aligned(d.lut, 8) && aligned(d.pos_thres, 8) && aligned(d.neg_thres, 8) && aligned(d.voxel, 4),
               V2V_ERR_ALIGNMENT, "misaligned float64/float32 pointer");
 
@@ -371,6 +383,7 @@ extern "C" int v2v_esim_frames_to_voxel(const v2v_esim_desc* desc, void* stream)
   a.padded = a.row_stride != d.W;
   Philox::round_keys(d.seed, a.rk);
   a.Tf = d.frame_out_mode == 2 ? a.T + 1 : a.T;
+  a.Mraw = (d.frame_index && d.raw_frames_per_clip > 0) ? d.raw_frames_per_clip : d.N;
   if (!d.frame_out) a.d.frame_out_mode = 0;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
 

@@ -12,6 +12,7 @@ struct EsimArgs {
   int64_t row_stride, plane_stride;
   int32_t padded;     // voxel rows are strided (row_stride != W)
   int32_t Tf;         // frames written per clip in frame_out
+  int32_t Mraw;       // frames per clip in d.frames (N, or raw_frames_per_clip with frame_index)
   uint32_t rk[20];    // Philox round keys of d.seed (host-precomputed)
 };
 

@@ -70,14 +70,23 @@ __global__ void __launch_bounds__(kFastThreads, CTAS) esim_fast_kernel(const Esi
   extern __shared__ __align__(16) unsigned char dyn_smem[];     // [LUT copies 32 KB][trig table 32 KB, Philox only]
   double* lut_s = reinterpret_cast<double*>(dyn_smem);
   float2* trig_s = reinterpret_cast<float2*>(dyn_smem + 256 * kLutCopies * sizeof(double));
+  __shared__ float f255_s[FRAMES ? 256 : 1];                       // (mapped value)/255 of the ground-truth frame output
   __shared__ double cta_rcp[2];                                    // 1/pos, 1/neg of this CTA's clip: only the rare path reads them
   __shared__ float4 hot_s[NOISE == V2V_NOISE_PHILOX ? kFastThreads : 1];   // per-lane hot-pixel noise: read by the ~6 % of warps that own one
+  int* fnum_s = reinterpret_cast<int*>(dyn_smem + 256 * kLutCopies * sizeof(double) + (NOISE == V2V_NOISE_PHILOX ? kTrigEntries * sizeof(float2) : 0));
   if (NOISE == V2V_NOISE_PHILOX) fill_trig_table(trig_s);
   const v2v_esim_desc& d = a.d;
+  {
+    const int32_t* fidx = d.frame_index ? d.frame_index + static_cast<int64_t>(blockIdx.y) * d.N : nullptr;
+    for (int n = threadIdx.x; n < d.N; n += kFastThreads) fnum_s[n] = fidx ? min(max(fidx[n], 0), a.Mraw - 1) : n;
+  }
   if (threadIdx.x < 2) cta_rcp[threadIdx.x] = __drcp_rn(threadIdx.x ? d.neg_thres[blockIdx.y] : d.pos_thres[blockIdx.y]);
   {
+    const uint8_t* vmap = d.value_map ? d.value_map + static_cast<int64_t>(blockIdx.y) * 256 : nullptr;   // degrade folded into the LUTs
     for (int e = threadIdx.x; e < 256; e += kFastThreads) {
-      const double v = d.lut[e];
+      const int ev = vmap ? vmap[e] : e;
+      const double v = d.lut[ev];
+      if (FRAMES) f255_s[e] = __fdiv_rn(static_cast<float>(ev), 255.0f);
 #pragma unroll
       for (int c = 0; c < kLutCopies; ++c) lut_s[e * kLutCopies + c] = v;
     }
@@ -112,10 +121,13 @@ __global__ void __launch_bounds__(kFastThreads, CTAS) esim_fast_kernel(const Esi
     return v;
   };
 
-  const uint8_t* fr = d.frames + (static_cast<int64_t>(b) * N) * HW + pix0;
+  // frame n of the clip = raw frame frame_index[b][n] (pause gather, data/v2v_datasets.py:285-311), or n itself: the
+  // per-clip table of raw frame numbers sits in shared memory (one broadcast LDS per load, no extra live registers)
+  const uint8_t* fr = d.frames + (static_cast<int64_t>(b) * a.Mraw) * HW + pix0;
+  auto frame_ptr = [&](int n) -> const uint8_t* { return fr + static_cast<int64_t>(fnum_s[n]) * HW; };
   double pot[4], lprev[4];
   float hotf[4];            // Philox hot-pixel noise is double(float) by construction: keep the float (parked in smem)
-  const uint32_t w0 = ld_stream_u32(fr);
+  const uint32_t w0 = ld_stream_u32(frame_ptr(0));
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
     lprev[k] = lut_at(byte_of(w0, k));
@@ -141,8 +153,7 @@ __global__ void __launch_bounds__(kFastThreads, CTAS) esim_fast_kernel(const Esi
   float* fout = FRAMES ? d.frame_out + static_cast<int64_t>(b) * a.Tf * HW + pix0 : nullptr;
   int gsub = 0;
   if (FRAMES && d.frame_out_mode == 2) {
-    st_stream_f32x4(fout, __fdiv_rn(static_cast<float>(w0 & 0xffu), 255.0f), __fdiv_rn(static_cast<float>((w0 >> 8) & 0xffu), 255.0f),
-                    __fdiv_rn(static_cast<float>((w0 >> 16) & 0xffu), 255.0f), __fdiv_rn(static_cast<float>(w0 >> 24), 255.0f));
+    st_stream_f32x4(fout, f255_s[w0 & 0xffu], f255_s[(w0 >> 8) & 0xffu], f255_s[(w0 >> 16) & 0xffu], f255_s[w0 >> 24]);
     fout += HW;
   }
   float net = 0.f, tot = 0.f;             // since the last flush: net = #pos - #neg, tot = #pos + #neg
@@ -222,8 +233,7 @@ __global__ void __launch_bounds__(kFastThreads, CTAS) esim_fast_kernel(const Esi
     if (FRAMES) {                                                     // data/v2v_datasets.py:329-338,352
       if (++gsub == a.G) {
         gsub = 0;
-        st_stream_f32x4(fout, __fdiv_rn(static_cast<float>(w & 0xffu), 255.0f), __fdiv_rn(static_cast<float>((w >> 8) & 0xffu), 255.0f),
-                        __fdiv_rn(static_cast<float>((w >> 16) & 0xffu), 255.0f), __fdiv_rn(static_cast<float>(w >> 24), 255.0f));
+        st_stream_f32x4(fout, f255_s[w & 0xffu], f255_s[(w >> 8) & 0xffu], f255_s[(w >> 16) & 0xffu], f255_s[w >> 24]);
         fout += HW;
       }
     }
@@ -235,14 +245,14 @@ __global__ void __launch_bounds__(kFastThreads, CTAS) esim_fast_kernel(const Esi
   uint32_t cur[kPF], nxt[kPF];
   if (trips > 0) {
 #pragma unroll
-    for (int u = 0; u < kPF; ++u) cur[u] = ld_stream_u32(fr + static_cast<int64_t>(1 + u) * HW);
+    for (int u = 0; u < kPF; ++u) cur[u] = ld_stream_u32(frame_ptr(1 + u));
   }
   int i = 1;
   const float zero4[4] = {0.f, 0.f, 0.f, 0.f};
   for (int t = 0; t < trips; ++t) {
     if (t + 1 < trips) {
 #pragma unroll
-      for (int u = 0; u < kPF; ++u) nxt[u] = ld_stream_u32(fr + static_cast<int64_t>(i + kPF + u) * HW);
+      for (int u = 0; u < kPF; ++u) nxt[u] = ld_stream_u32(frame_ptr(i + kPF + u));
     }
     if (NOISE == V2V_NOISE_PHILOX) {
       // intervals i-1 .. i+2 = 4t .. 4t+3: two draws of the group's stream, 8 normals each
@@ -271,7 +281,7 @@ __global__ void __launch_bounds__(kFastThreads, CTAS) esim_fast_kernel(const Esi
 #pragma unroll
         for (int k = 0; k < 4; ++k) bn1[k] = ((i - 1) & 1) ? tod[k] : tev[k];
       }
-      step(ld_stream_u32(fr + static_cast<int64_t>(i) * HW), bn1);
+      step(ld_stream_u32(frame_ptr(i)), bn1);
     }
   }
 
@@ -299,6 +309,7 @@ bool esim_fast_eligible(const EsimArgs& a) {
   if (d.frames_per_bin != 1 || d.threshold_mode != V2V_THRES_PER_CLIP) return false;
   if (d.noise_mode == V2V_NOISE_EXPLICIT) return false;
   if (d.noise_mode == V2V_NOISE_PHILOX && d.put_noise_external) return false;
+  if (d.N > 16384) return false;          // the per-clip frame-number table lives in shared memory
   return true;
 }
 
@@ -311,7 +322,7 @@ int launch_esim_fast(const EsimArgs& a, cudaStream_t s) {
   // (Philox without statistics needs 96 registers: 5 CTAs are resident under the 4-CTA bound.)
   int ctas = ph ? (st ? 6 : 4) : 8;
   if (const char* e = getenv("V2V_ESIM_CTAS")) ctas = atoi(e);
-  const size_t smem = 256 * kLutCopies * sizeof(double) + (ph ? kTrigEntries * sizeof(float2) : 0);
+  const size_t smem = 256 * kLutCopies * sizeof(double) + (ph ? kTrigEntries * sizeof(float2) : 0) + static_cast<size_t>(a.d.N) * sizeof(int);
 #define V2V_G(NM, FR, ST, CT)                                                                                     \
   do {                                                                                                            \
     V2V_CUDA(cudaFuncSetAttribute(esim_fast_kernel<NM, FR, ST, CT>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem))); \

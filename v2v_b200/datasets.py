@@ -41,6 +41,46 @@ def sample_v2e_params(configs, pos_thres=None, neg_thres=None, rs=np.random) -> 
             "hot_pixel_fraction": hot_pixel_fraction, "hot_pixel_std": hot_pixel_std}
 
 
+def sample_pause_indices(count: int, proba_pause_when_running: float, proba_pause_when_paused: float, rs=np.random):
+    """The dataset's pause sequence (data/v2v_datasets.py:285-301): ``count`` frame indices into the raw clip,
+    non-decreasing with repeats while "paused"; one ``rs.rand()`` per frame in the reference's order.
+    Returns (img_idxes int32 [count], true_img_cnt) — ``true_img_cnt`` raw frames have to be decoded."""
+    img_idxes, idx, is_pause = [], 0, False
+    for _ in range(count):
+        img_idxes.append(idx)
+        if is_pause and rs.rand() > proba_pause_when_paused:
+            is_pause = False
+        elif not is_pause and rs.rand() < proba_pause_when_running:
+            is_pause = True
+        if not is_pause:
+            idx += 1
+    return np.asarray(img_idxes, dtype=np.int32), idx + 1
+
+
+def degrade_value_map(kind: str, scale: float) -> np.ndarray:
+    """uint8[256] map of the HDR / LDR degrade (data/v2v_datasets.py:473-483): the reference's own NumPy expression
+    evaluated on every pixel value, so applying the map equals degrading the frames bit for bit.
+    kind: "hdr" (scale ~ U(1,3)) or "ldr" (scale ~ U(0.3,1)); the caller draws ``scale`` like the reference does."""
+    if kind not in ("hdr", "ldr"):
+        raise NotImplementedError("Video degrade type not supported.")
+    v = np.arange(256, dtype=np.uint8)
+    return np.clip((v - 127.5) * scale + 127.5, 0, 255).astype(np.uint8)
+
+
+def bgr_to_gray(img_stack: torch.Tensor) -> torch.Tensor:
+    """CUDA uint8 ``[..., C>=3]`` -> uint8 ``[...]``: the dataset's ``bgr_to_gray`` (data/v2v_datasets.py:19-22)."""
+    import ctypes as C
+    from . import _lib
+    if not img_stack.is_cuda or img_stack.dtype != torch.uint8 or img_stack.shape[-1] < 3:
+        raise _lib.V2VError(-1, "bgr_to_gray needs a CUDA uint8 tensor [..., C>=3] (no CPU fallback)")
+    img = img_stack.contiguous()
+    gray = torch.empty(img.shape[:-1], dtype=torch.uint8, device=img.device)
+    with torch.cuda.device(img.device):
+        _lib.check(_lib.load().v2v_bgr_to_gray(C.c_void_p(img.data_ptr()), int(img.shape[-1]), C.c_void_p(gray.data_ptr()),
+                                               int(gray.numel()), C.c_void_p(torch.cuda.current_stream(img.device).cuda_stream)))
+    return gray
+
+
 class ImgsToVoxelsMixin:
     """GPU override of ``WebvidDatasetV2.imgs_to_voxels``.
 
@@ -100,8 +140,11 @@ class V2VVoxelizer(ImgsToVoxelsMixin):
         return ps
 
     def batch_to_tensors(self, frames: torch.Tensor, params: Optional[Sequence[dict]] = None, *, seed: int = 0,
-                         clip_index_base: int = 0, pad_multiple: int = 0, with_stats: bool = False, out=None):
-        """CUDA uint8 ``[B,N,H,W]`` gray clips -> the train batch dict on the GPU.
+                         clip_index_base: int = 0, pad_multiple: int = 0, with_stats: bool = False, out=None,
+                         frame_index=None, value_map=None):
+        """CUDA uint8 ``[B,N,H,W]`` gray clips -> the train batch dict on the GPU.  With ``frame_index`` ``[B,N]`` the input
+        is the raw decoded stack ``[B,M,H,W]`` and the pause gather happens inside the kernel; ``value_map`` ``[B,256]``
+        applies the HDR/LDR degrade (``sample_pause_indices``, ``degrade_value_map``).
 
         Returns {"events": float32 [B,T,bins,H,W], "frame": float32 [B,T(+1),1,H,W] in [0,1],
         "v2e_params": list of dicts[, "stats": int64 [B,2]]} — the layout
@@ -118,7 +161,7 @@ class V2VVoxelizer(ImgsToVoxelsMixin):
             noise="philox", base_noise_std=col("base_noise_std"), hot_pixel_fraction=col("hot_pixel_fraction"),
             hot_pixel_std=col("hot_pixel_std"), put_noise_external=self.put_noise_external, seed=seed,
             clip_index_base=clip_index_base, pad_multiple=pad_multiple, with_stats=with_stats, out=out,
-            frame_out="frames+first" if self.output_additional_frame else "frames")
+            frame_out="frames+first" if self.output_additional_frame else "frames", frame_index=frame_index, value_map=value_map)
         batch = {"events": o.voxel, "frame": o.frames, "v2e_params": list(params)}
         if with_stats:
             batch["stats"] = o.stats

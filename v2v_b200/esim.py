@@ -86,7 +86,7 @@ def frames_to_voxel(frames: torch.Tensor, pos_thres, neg_thres, *, num_bins: int
                     seed: int = 0, clip_index_base: int = 0, potential_in=None, return_potential: bool = False,
                     frame_out: Optional[str] = None, with_stats: bool = False, pad_multiple: int = 0,
                     out: Optional[torch.Tensor] = None, lut: Optional[np.ndarray] = None,
-                    stream: Optional[torch.cuda.Stream] = None) -> EsimOutput:
+                    stream: Optional[torch.cuda.Stream] = None, frame_index=None, value_map=None) -> EsimOutput:
     """Simulate ``B`` clips in one launch.
 
     frames: CUDA uint8 ``[B,N,H,W]`` (or ``[N,H,W]``).  pos_thres / neg_thres:
@@ -100,6 +100,11 @@ def frames_to_voxel(frames: torch.Tensor, pos_thres, neg_thres, *, num_bins: int
     output_additional_frame).  pad_multiple: allocate the voxel with H and W
     rounded up (the consumer's /16 padding, model/train_utils.py:322-326); pads
     are zero and the returned ``voxel`` is the unpadded view.
+
+    Frame-side packing fused into the pass (data/v2v_datasets.py:285-311,473-483): ``frame_index`` int32 ``[B,N]`` makes
+    frame ``n`` of clip ``b`` the raw frame ``frames[b, frame_index[b,n]]`` (the dataset's pause gather; ``frames`` is
+    then the raw stack ``[B,M,H,W]``); ``value_map`` uint8 ``[B,256]`` is applied to every pixel before the simulation and
+    the ``frame_out`` (``degrade_value_map`` builds the HDR/LDR degrade).
     """
     if frames.dim() == 3:
         frames = frames.unsqueeze(0)
@@ -108,6 +113,23 @@ def frames_to_voxel(frames: torch.Tensor, pos_thres, neg_thres, *, num_bins: int
     frames = frames.contiguous()
     dev = frames.device
     B, N, H, W = frames.shape
+    M = N
+    fidx_t = vmap_t = None
+    if frame_index is not None:
+        fidx_t = torch.as_tensor(frame_index).to(device=dev, dtype=torch.int32)
+        if fidx_t.dim() == 1:
+            fidx_t = fidx_t.unsqueeze(0).expand(B, -1)
+        if fidx_t.dim() != 2 or fidx_t.shape[0] != B:
+            raise ValueError("frame_index must be [N] or [B,N]")
+        fidx_t = fidx_t.contiguous()
+        N = int(fidx_t.shape[1])
+    if value_map is not None:
+        vmap_t = torch.as_tensor(value_map).to(device=dev, dtype=torch.uint8)
+        if vmap_t.dim() == 1:
+            vmap_t = vmap_t.unsqueeze(0).expand(B, -1)
+        if tuple(vmap_t.shape) != (B, 256):
+            raise ValueError("value_map must be [256] or [B,256] uint8")
+        vmap_t = vmap_t.contiguous()
     group = num_bins * frames_per_bin
     if N < 1 or (N - 1) % group != 0:
         raise AssertionError(f"(N-1)={N - 1} must be a multiple of num_bins*frames_per_bin={group}")
@@ -195,12 +217,13 @@ def frames_to_voxel(frames: torch.Tensor, pos_thres, neg_thres, *, num_bins: int
     d.voxel = _ptr(store)
     d.voxel_row_stride, d.voxel_plane_stride = Wp, Hp * Wp
     d.frame_out, d.stats = _ptr(fr_t), _ptr(stats_t)
+    d.frame_index, d.raw_frames_per_clip, d.value_map = _ptr(fidx_t), (M if fidx_t is not None else 0), _ptr(vmap_t)
 
     s = stream if stream is not None else torch.cuda.current_stream(dev)
     with torch.cuda.device(dev):
         _lib.check(_lib.load().v2v_esim_frames_to_voxel(C.byref(d), C.c_void_p(s.cuda_stream)))
     if stream is not None:       # tensors created on the current stream but consumed on `stream`
-        for t in (frames, pos_t, neg_t, std_t, frac_t, hstd_t, u0_t, hot_t, g_t, pin_t, lut_t):
+        for t in (frames, pos_t, neg_t, std_t, frac_t, hstd_t, u0_t, hot_t, g_t, pin_t, lut_t, fidx_t, vmap_t):
             if t is not None:
                 t.record_stream(s)
     vox = store[..., :H, :W] if (Hp, Wp) != (H, W) else store
