@@ -113,6 +113,13 @@ int v2v_esim_frames_to_voxel(const v2v_esim_desc* desc, void* stream);
  * generator is checked against the CPU oracle. */
 int v2v_esim_philox_fields(const v2v_esim_desc* desc, double* u0, double* hot_noise, double* base_noise, void* stream);
 
+/* Audit hook for the generators themselves: writes (a) the Philox4x32-10 block of an arbitrary counter/key
+ * (known-answer tests of the published algorithm) to philox_out[4] and (b) the first `n_words` 32-bit outputs of the
+ * ESIM base-noise stream of (seed, clip_index, pixel group) — xoshiro128++ seeded as described in esim_common.cuh —
+ * to words_out[n_words].  Device pointers; either output may be NULL. */
+int v2v_rng_words(const uint32_t counter[4], const uint32_t key[2], uint32_t* philox_out, uint64_t seed, uint64_t clip_index,
+                  uint64_t pixel_group, int32_t n_words, uint32_t* words_out, void* stream);
+
 /* ======================================================================= *
  * 2. v2e-style frames -> voxel
  *    replaces  video_to_voxel / EventEmulator.generate_events

@@ -507,3 +507,46 @@ def degrade_video(imgs, kind, rs=np.random):
 def bgr_to_gray(img_stack):
     """data/v2v_datasets.py:19-22 (the float64 summation order is NumPy's / the BLAS kernel's: pinned by tests/golden)."""
     return np.dot(img_stack[..., :3], [0.5870, 0.1140, 0.2989]).astype(np.uint8)
+
+
+# ---- published generators, restated for the known-answer tests of the in-kernel RNG --------------------------------
+
+def philox4x32_10(counter, key):
+    """Philox4x32-10 (Salmon et al., "Parallel random numbers: as easy as 1, 2, 3", SC'11; Random123)."""
+    M0, M1, W0, W1 = 0xD2511F53, 0xCD9E8D57, 0x9E3779B9, 0xBB67AE85
+    c = [int(x) & 0xFFFFFFFF for x in counter]
+    k = [int(x) & 0xFFFFFFFF for x in key]
+    for _ in range(10):
+        p0, p1 = M0 * c[0], M1 * c[2]
+        c = [(p1 >> 32) ^ c[1] ^ k[0], p1 & 0xFFFFFFFF, (p0 >> 32) ^ c[3] ^ k[1], p0 & 0xFFFFFFFF]
+        k = [(k[0] + W0) & 0xFFFFFFFF, (k[1] + W1) & 0xFFFFFFFF]
+    return c
+
+
+def xoshiro128pp(state, n):
+    """First ``n`` outputs of xoshiro128++ 1.0 (Blackman & Vigna, 2019) from a 4-word state."""
+    s = [int(x) & 0xFFFFFFFF for x in state]
+    rotl = lambda x, r: ((x << r) | (x >> (32 - r))) & 0xFFFFFFFF
+    out = []
+    for _ in range(n):
+        out.append((rotl((s[0] + s[3]) & 0xFFFFFFFF, 7) + s[0]) & 0xFFFFFFFF)
+        t = (s[1] << 9) & 0xFFFFFFFF
+        s[2] ^= s[0]
+        s[3] ^= s[1]
+        s[1] ^= s[2]
+        s[0] ^= s[3]
+        s[2] ^= t
+        s[3] = rotl(s[3], 11)
+    return out
+
+
+def esim_noise_stream_words(seed, clip_index, pixel_group, n):
+    """The ESIM base-noise stream of one (clip, 4-pixel group): xoshiro128++ seeded with the Philox4x32-10 block of
+    counter (group lo32, 0, clip lo32, tag1 | group hi14 << 16 | clip hi16) under key (seed lo32, seed hi32)
+    (v2v_b200/csrc/esim_common.cuh)."""
+    ctr = [pixel_group & 0xFFFFFFFF, 0, clip_index & 0xFFFFFFFF,
+           0x40000000 | (((pixel_group >> 32) & 0x3FFF) << 16) | ((clip_index >> 32) & 0xFFFF)]
+    st = philox4x32_10(ctr, [seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF])
+    if not any(st):
+        st[0] = 0x9E3779B9
+    return xoshiro128pp(st, n)

@@ -422,3 +422,42 @@ def test_noise_field_distribution_and_independence(cuda_device):
     assert abs(corr(z[..., 3:-4:4], z[..., 4::4])) < lim                             # neighbouring groups (different streams)
     assert abs(corr(z[..., :-1, :], z[..., 1:, :])) < lim                            # neighbouring rows
     assert abs(corr(z[0], z[1])) < lim                                                # different clips, same seed
+
+
+def test_rng_known_answers_and_noise_chain(cuda_device):
+    """The device generators are the published algorithms (Philox4x32-10 KATs of Random123; the base-noise stream ==
+    Philox-seeded xoshiro128++ from the oracle's restatement), and the dumped noise field is the documented function of
+    those words (20-bit radius, 2048 tabulated directions) up to the SFU approximations."""
+    import ctypes as C
+    from v2v_b200 import _lib
+    from v2v_b200.esim import philox_fields
+    lib = _lib.load()
+    s = torch.cuda.current_stream(cuda_device).cuda_stream
+
+    def rng_words(counter, key, seed, clip, group, n):
+        po = torch.zeros(4, dtype=torch.int32, device=cuda_device)
+        wo = torch.zeros(max(n, 1), dtype=torch.int32, device=cuda_device)
+        _lib.check(lib.v2v_rng_words((C.c_uint32 * 4)(*counter), (C.c_uint32 * 2)(*key), C.c_void_p(po.data_ptr()), seed, clip, group, n,
+                                     C.c_void_p(wo.data_ptr()), C.c_void_p(s)))
+        u = lambda t: [int(x) & 0xFFFFFFFF for x in t.cpu().tolist()]
+        return u(po), u(wo)[:n]
+
+    for ctr, key in (([0] * 4, [0] * 2), ([0xffffffff] * 4, [0xffffffff] * 2),
+                     ([0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344], [0xa4093822, 0x299f31d0])):
+        assert rng_words(ctr, key, 0, 0, 0, 0)[0] == orc.philox4x32_10(ctr, key)
+    for seed, clip, group in ((0, 0, 0), (123, 5, 77), (2 ** 63 + 12345, 2 ** 40 + 3, 2 ** 33 + 9), (77, 1, 3071)):
+        assert rng_words([0] * 4, [0] * 2, seed, clip, group, 64)[1] == orc.esim_noise_stream_words(seed, clip, group, 64)
+    # the field: clip 1 of a 2-clip dump, every pixel group of a 96x128 frame, first 6 intervals
+    h, w, n, std, seed = 96, 128, 7, 0.37, 77
+    _, _, bn = philox_fields(n, h, w, base_noise_std=[std, std], hot_pixel_fraction=[0.0, 0.0], hot_pixel_std=[0.0, 0.0], seed=seed)
+    z = bn[1].cpu().numpy().reshape(n - 1, h * w)
+    for group in (0, 1, 500, 3071):
+        words = orc.esim_noise_stream_words(seed, 1, group, 4 * 3)
+        for pair in range(3):
+            for k in range(4):
+                wd = words[4 * pair + k]
+                u1 = 2.0 - (1.0 + ((wd << 2) & 0x7ffffc) / 2.0 ** 23)
+                r = std * np.sqrt(-2.0 * np.log(u1))
+                th = (2 * (wd >> 21) + 1) * np.pi / 2048
+                got = z[2 * pair: 2 * pair + 2, 4 * group + k]
+                assert np.allclose(got, [r * np.cos(th), r * np.sin(th)], rtol=2e-4, atol=2e-6 * std)

@@ -193,3 +193,14 @@ def test_events_to_voxel_np():
     c = golden("scatter").case("scat_voxel_np")
     out = orc.events_to_voxel_np(c["xs"], c["ys"], c["ts"], c["ps"], int(c["bins"]), (int(c["H"]), int(c["W"])))
     assert same(out, c["ref"])
+
+
+def test_rng_restatements_known_answers():
+    """Philox4x32-10 against the Random123 known-answer vectors; xoshiro128++ against the reference C implementation's
+    first outputs for the state {1,2,3,4}."""
+    import v2v_oracle as orc
+    assert orc.philox4x32_10([0, 0, 0, 0], [0, 0]) == [0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8]
+    assert orc.philox4x32_10([0xffffffff] * 4, [0xffffffff] * 2) == [0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd]
+    assert orc.philox4x32_10([0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344], [0xa4093822, 0x299f31d0]) == \
+        [0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1]
+    assert orc.xoshiro128pp([1, 2, 3, 4], 4) == [641, 1573767, 3222811527, 3517856514]

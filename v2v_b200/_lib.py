@@ -94,6 +94,7 @@ SYMBOLS = {
     "v2v_launch_count": (C.c_longlong, []),
     "v2v_esim_frames_to_voxel": (C.c_int, [C.POINTER(EsimDesc), _p]),
     "v2v_esim_philox_fields": (C.c_int, [C.POINTER(EsimDesc), _p, _p, _p, _p]),
+    "v2v_rng_words": (C.c_int, [C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), _p, C.c_uint64, C.c_uint64, C.c_uint64, C.c_int32, _p, _p]),
     "v2v_v2e_frames_to_voxel": (C.c_int, [C.POINTER(V2eDesc), _p]),
     "v2v_v2e_shot_scales": (C.c_int, [C.POINTER(V2eDesc), _p, _p, _p]),
     "v2v_v2e_philox_fields": (C.c_int, [C.POINTER(V2eDesc), _p, _p, _p, _p]),

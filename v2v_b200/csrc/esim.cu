@@ -343,6 +343,37 @@ __global__ void esim_philox_fields_kernel(const EsimArgs a, double* u0, double* 
 }  // namespace
 }  // namespace v2v
 
+namespace v2v {
+namespace {
+__global__ void rng_words_kernel(uint4 ctr, uint2 key, uint32_t* philox_out, EsimArgs a, uint64_t clip_index, uint64_t group, int n,
+                                 uint32_t* words_out) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  if (philox_out) {
+    const uint4 r = Philox::run(ctr, key);
+    philox_out[0] = r.x, philox_out[1] = r.y, philox_out[2] = r.z, philox_out[3] = r.w;
+  }
+  if (words_out) {
+    GroupStream gs = group_stream_init(group, make_noise_key(clip_index), a.rk);
+    for (int i = 0; i < n; ++i) words_out[i] = group_stream_next(gs);
+  }
+}
+}  // namespace
+}  // namespace v2v
+
+extern "C" int v2v_rng_words(const uint32_t counter[4], const uint32_t key[2], uint32_t* philox_out, uint64_t seed, uint64_t clip_index,
+                             uint64_t pixel_group, int32_t n_words, uint32_t* words_out, void* stream) {
+  using namespace v2v;
+  V2V_REQUIRE(n_words >= 0 && (philox_out == nullptr || (counter && key)), V2V_ERR_INVALID_ARG, "bad arguments");
+  EsimArgs a{};
+  Philox::round_keys(seed, a.rk);
+  const uint4 c = counter ? make_uint4(counter[0], counter[1], counter[2], counter[3]) : make_uint4(0, 0, 0, 0);
+  const uint2 k = key ? make_uint2(key[0], key[1]) : make_uint2(0, 0);
+  rng_words_kernel<<<1, 32, 0, static_cast<cudaStream_t>(stream)>>>(c, k, philox_out, a, clip_index, pixel_group, n_words, words_out);
+  count_launch();
+  V2V_CUDA(cudaGetLastError());
+  return V2V_OK;
+}
+
 extern "C" int v2v_esim_frames_to_voxel(const v2v_esim_desc* desc, void* stream) {
   using namespace v2v;
   V2V_REQUIRE(desc != nullptr, V2V_ERR_INVALID_ARG, "desc is NULL");
