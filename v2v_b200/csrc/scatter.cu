@@ -37,6 +37,7 @@ struct ScatterArgs {
   int rows_per_strip, num_strips;
   int packed16;        // h5 discrete: strips are sized for 2-byte cells
   int tile_bytes;      // bytes of the accumulator tile in dynamic shared memory (the two-tap hit list follows it)
+  int generic_scan;    // V2V_SCATTER_GENERIC=1: never take the 16-bit coordinate scan (A/B and tests)
   int num_splits;      // >1: each (window, bin, strip) is shared by this many CTAs, each scanning a slice of the bin's events
                        //     into a private tile and adding it to the (pre-zeroed) output with global atomics
   int64_t* bounds;     // [Wn, bins+2]: first event with bin_floor >= k for k = -1 .. bins (from the pre-pass), or NULL
@@ -288,6 +289,8 @@ __global__ void __launch_bounds__(kScatterThreads, 2) scatter_kernel(const Scatt
 
     long long ndrop = 0;
     constexpr int kU = 8;                                  // events per thread in flight
+    const bool fast16 = (d.xs_dtype == V2V_U16 || d.xs_dtype == V2V_I16) && (d.ys_dtype == V2V_U16 || d.ys_dtype == V2V_I16) &&
+                        H <= 32767 && W <= 32767 && !a.generic_scan;
     for (int64_t eb = lo; eb < hi; eb += kU * kScatterThreads) {
       // all loads of kU events are issued before any dependent work (one memory round-trip per trip)
       long long yv[kU], xv[kU];
@@ -297,6 +300,61 @@ __global__ void __launch_bounds__(kScatterThreads, 2) scatter_kernel(const Scatt
         if (threadIdx.x == 0) s_hits = 0;
         __syncthreads();
       }
+      if (fast16) {
+        // 16-bit coordinates (every h5 converter of the reference writes uint16 / int16): no dtype dispatch, 32-bit index
+        // math, negative int16 values read as >= 32768 and fall out of the sensor like any other out-of-range coordinate;
+        // two-tap modes append to the hit list once per warp (ballot + one shared atomic) instead of once per lane
+        const uint16_t* y16 = static_cast<const uint16_t*>(d.ys);
+        const uint16_t* x16 = static_cast<const uint16_t*>(d.xs);
+        int yq[kU], xq[kU];
+#pragma unroll
+        for (int u = 0; u < kU; ++u) {
+          const int64_t e = eb + u * kScatterThreads + threadIdx.x;
+          okv[u] = e < hi;
+          yq[u] = okv[u] ? static_cast<int>(y16[e]) : 0x7fffffff;
+          xq[u] = okv[u] ? static_cast<int>(x16[e]) : 0x7fffffff;
+          pv[u] = (okv[u] && !kTwoTap) ? load_f32(d.ps, d.ps_dtype, e) : 0.f;
+        }
+#pragma unroll
+        for (int u = 0; u < kU; ++u) {
+          const int ry = yq[u] - r0;
+          const bool inrow = static_cast<unsigned int>(ry) < static_cast<unsigned int>(rows);
+          const bool inx = static_cast<unsigned int>(xq[u]) < static_cast<unsigned int>(W);
+          const bool hit = inrow && inx;
+          // out-of-sensor events are reported once: rows by strip 0, columns by the strip that owns the row; for
+          // two-tap modes by the event's primary bin only (rare: a real branch)
+          if (okv[u] && ((strip == 0 && pass == 0 && !inrow && yq[u] >= H) || (inrow && !inx))) {
+            bool primary = true;
+            if (kTwoTap) { double co; primary = bin_floor<MODE>(d, wc, eb + u * kScatterThreads + threadIdx.x, &co) == static_cast<double>(bin); }
+            if (primary) ++ndrop;
+          }
+          const int cell = ry * W + xq[u];
+          if (kTwoTap) {
+            const unsigned int m = __ballot_sync(0xffffffffu, hit);
+            if (m) {
+              int base = 0;
+              if (lane == 0) base = atomicAdd(&s_hits, __popc(m));
+              base = __shfl_sync(0xffffffffu, base, 0);
+              if (hit) hit_list[base + __popc(m & ((1u << lane) - 1u))] = ((u * kScatterThreads + static_cast<int>(threadIdx.x)) << 16) | cell;
+            }
+            continue;
+          }
+          if (!hit) continue;
+          float pw;                                                                     // polarity -> weight
+          {
+            const float p = pv[u];
+            if (d.polarity_mode == V2V_POL_POS_ONLY) pw = p > 0.f ? 1.f : 0.f;          // event_utils.py:533
+            else if (d.polarity_mode == V2V_POL_NEG_ONLY) pw = p <= 0.f ? 1.f : 0.f;    // :534
+            else pw = kH5 ? (2.f * p - 1.f) : p;                                        // testh5.py:67
+          }
+          if (MODE == V2V_SCATTER_H5_DISCRETE) {                                        // testh5.py:73
+            if (packed) atomicAdd(&acc_i[cell >> 1], static_cast<int>(pw) * ((cell & 1) ? 65536 : 1));
+            else atomicAdd(&acc_i[cell], static_cast<int>(pw));
+          } else {
+            atomicAdd(&acc_f[cell], pw);                                                // event_utils.py:505
+          }
+        }
+      } else {
 #pragma unroll
       for (int u = 0; u < kU; ++u) {
         const int64_t e = eb + u * kScatterThreads + threadIdx.x;
@@ -348,6 +406,7 @@ __global__ void __launch_bounds__(kScatterThreads, 2) scatter_kernel(const Scatt
         } else {
           atomicAdd(&acc_f[cell], pw);                                                // event_utils.py:505
         }
+      }
       }
       if (kTwoTap) {
         __syncthreads();
@@ -529,6 +588,7 @@ extern "C" int v2v_events_to_voxel(const v2v_scatter_desc* desc, void* stream) {
   // few, large windows (e.g. the offline cache builder: one window of millions of events) cannot fill the GPU with
   // one CTA per (window, bin, strip): split every bin's event range over several CTAs
   a.num_splits = 1;
+  a.generic_scan = getenv("V2V_SCATTER_GENERIC") != nullptr;
   const int64_t ev_per_item = d.num_events / (static_cast<int64_t>(d.num_windows) * d.num_bins > 0 ? static_cast<int64_t>(d.num_windows) * d.num_bins : 1);
   if (items < 2LL * sms && ev_per_item > 16384) {
     int64_t k = (4LL * sms + items - 1) / items;
