@@ -459,9 +459,18 @@ __global__ void __launch_bounds__(kScatterThreads, 2) scatter_kernel(const Scatt
         if (packed) return static_cast<double>(static_cast<int>((static_cast<unsigned int>(acc_i[i >> 1]) >> ((i & 1) * 16)) & 0xffffu) - 32768);
         return kTorch ? static_cast<double>(acc_f[i]) : static_cast<double>(acc_i[i]);
       };
-      auto valuef = [&](int i) -> float {          // float32 outputs without 64-bit conversions where possible
-        if (kInterp) return static_cast<float>(value(i));
-        if (packed) return static_cast<float>(static_cast<int>((static_cast<unsigned int>(acc_i[i >> 1]) >> ((i & 1) * 16)) & 0xffffu) - 32768);
+      auto valuef = [&](int i) -> float {          // float32 outputs: stay off the conversion unit where possible
+        if (kInterp) {
+          const int h = acc_i[i];
+          const unsigned int l = reinterpret_cast<unsigned int*>(acc_lo)[i];
+          if ((static_cast<unsigned int>(h) | l) == 0u) return 0.f;                   // most cells of a strip hold no event
+          // h*2^-15 + l*2^-30 is exact in float64 (46 significant bits at most): one rounding, to float32
+          return static_cast<float>(__fma_rn(static_cast<double>(h), 1.0 / 32768.0, __dmul_rn(static_cast<double>(l), 1.0 / 1073741824.0)));
+        }
+        if (packed) {                               // count in [-32768, 32767]: 1.5*2^23 + n is exact and its bits are 0x4b400000 + n
+          const int n = static_cast<int>((static_cast<unsigned int>(acc_i[i >> 1]) >> ((i & 1) * 16)) & 0xffffu) - 32768;
+          return __fsub_rn(__int_as_float(0x4b400000 + n), 12582912.0f);
+        }
         return kTorch ? acc_f[i] : static_cast<float>(acc_i[i]);
       };
       if (K > 1) {                                   // partial tile: add the non-zero cells to the pre-zeroed output
