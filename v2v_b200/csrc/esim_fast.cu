@@ -1,18 +1,25 @@
 // ESIM frames -> voxel: the throughput kernel for the shipped configuration
-// (per-clip thresholds, frames_per_bin == 1, noise none or in-kernel Philox
-// applied to the potential; reference data/v2v_core_esim.py:26-69 with
-// put_noise_external=False, data/v2v_datasets.py:399-400 with fpb=1).
+// (per-clip thresholds, frames_per_bin == 1, noise none or generated in the
+// kernel and applied to the potential; reference data/v2v_core_esim.py:26-69
+// with put_noise_external=False, data/v2v_datasets.py:399-400 with fpb=1).
 //
 // Same arithmetic as the generic kernel in esim.cu, restructured so that the
 // warp issues as few instructions per pixel-interval as possible (the generic
 // kernel is instruction-issue bound at ~40 % of HBM bandwidth):
 //   * 4 pixels per lane, whole clip in registers, frames through a register
 //     ring of 2*PF words, voxels as one 128-bit streaming store per frame;
-//   * the LUT is replicated 16x in shared memory ([value][lane&15]) so the
-//     64-bit lookups of a half-warp never collide, whatever the pixel values;
-//   * a crossing by exactly one threshold (the common case) is handled with
-//     predicated float64 adds, no branch; only multi-threshold crossings take
-//     the divergent exact floor-division path.
+//   * the LUT is replicated 8x in shared memory ([value][lane&7]): a half-warp's
+//     64-bit lookups collide only between lanes l and l+8 on different values;
+//   * a crossing by exactly one threshold (the common case) is branch-free
+//     (select + add, or two FMAs with a 0/1 factor built from the predicate);
+//     only multi-threshold crossings take the divergent exact floor-division
+//     path, triggered by four FP64 compares chained through one predicate;
+//   * noise from one xoshiro128++ stream per 4-pixel group (seeded by Philox),
+//     8 normals per draw for a pair of intervals (esim_common.cuh);
+//   * statistics in registers, one pair of global reductions per warp at the
+//     end: no shared-memory stage and no CTA barrier after the loop;
+//   * optional pause gather / degrade of the dataset fused into the frame loads
+//     and the LUTs (frame_index, value_map).
 #include "esim_common.cuh"
 
 #include <cstdlib>
