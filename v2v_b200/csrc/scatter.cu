@@ -306,40 +306,36 @@ __global__ void __launch_bounds__(kScatterThreads, 2) scatter_kernel(const Scatt
         // two-tap modes append to the hit list once per warp (ballot + one shared atomic) instead of once per lane
         const uint16_t* y16 = static_cast<const uint16_t*>(d.ys);
         const uint16_t* x16 = static_cast<const uint16_t*>(d.xs);
+        const int rem = static_cast<int>(min(hi - eb, static_cast<int64_t>(kU * kScatterThreads)));   // events of this trip
+        const bool dropcheck = strip == 0 && pass == 0;
+        const int tid = static_cast<int>(threadIdx.x);
         int yq[kU], xq[kU];
 #pragma unroll
         for (int u = 0; u < kU; ++u) {
-          const int64_t e = eb + u * kScatterThreads + threadIdx.x;
-          okv[u] = e < hi;
-          yq[u] = okv[u] ? static_cast<int>(y16[e]) : 0x7fffffff;
-          xq[u] = okv[u] ? static_cast<int>(x16[e]) : 0x7fffffff;
-          pv[u] = (okv[u] && !kTwoTap) ? load_f32(d.ps, d.ps_dtype, e) : 0.f;
+          const int o = u * kScatterThreads + tid;
+          okv[u] = o < rem;
+          yq[u] = okv[u] ? static_cast<int>(y16[eb + o]) : 0x7fffffff;
+          xq[u] = okv[u] ? static_cast<int>(x16[eb + o]) : 0x7fffffff;
+          pv[u] = (okv[u] && !kTwoTap) ? load_f32(d.ps, d.ps_dtype, eb + o) : 0.f;
         }
+        // hot loop: range tests only; out-of-sensor events (rare) are collected in `bad` and counted after the loop
+        bool bad = false;
+        unsigned int hm[kTwoTap ? kU : 1];          // two-tap: ballots of the hits, one hit-list reservation per warp and trip
+        int tot = 0;
 #pragma unroll
         for (int u = 0; u < kU; ++u) {
           const int ry = yq[u] - r0;
           const bool inrow = static_cast<unsigned int>(ry) < static_cast<unsigned int>(rows);
           const bool inx = static_cast<unsigned int>(xq[u]) < static_cast<unsigned int>(W);
           const bool hit = inrow && inx;
-          // out-of-sensor events are reported once: rows by strip 0, columns by the strip that owns the row; for
-          // two-tap modes by the event's primary bin only (rare: a real branch)
-          if (okv[u] && ((strip == 0 && pass == 0 && !inrow && yq[u] >= H) || (inrow && !inx))) {
-            bool primary = true;
-            if (kTwoTap) { double co; primary = bin_floor<MODE>(d, wc, eb + u * kScatterThreads + threadIdx.x, &co) == static_cast<double>(bin); }
-            if (primary) ++ndrop;
-          }
-          const int cell = ry * W + xq[u];
+          bad = bad || (okv[u] && ((dropcheck && !inrow && yq[u] >= H) || (inrow && !inx)));
           if (kTwoTap) {
-            const unsigned int m = __ballot_sync(0xffffffffu, hit);
-            if (m) {
-              int base = 0;
-              if (lane == 0) base = atomicAdd(&s_hits, __popc(m));
-              base = __shfl_sync(0xffffffffu, base, 0);
-              if (hit) hit_list[base + __popc(m & ((1u << lane) - 1u))] = ((u * kScatterThreads + static_cast<int>(threadIdx.x)) << 16) | cell;
-            }
+            hm[kTwoTap ? u : 0] = __ballot_sync(0xffffffffu, hit);
+            tot += __popc(hm[kTwoTap ? u : 0]);
             continue;
           }
           if (!hit) continue;
+          const int cell = ry * W + xq[u];
           float pw;                                                                     // polarity -> weight
           {
             const float p = pv[u];
@@ -352,6 +348,37 @@ __global__ void __launch_bounds__(kScatterThreads, 2) scatter_kernel(const Scatt
             else atomicAdd(&acc_i[cell], static_cast<int>(pw));
           } else {
             atomicAdd(&acc_f[cell], pw);                                                // event_utils.py:505
+          }
+        }
+        if (kTwoTap && tot) {                        // warp-uniform
+          int base = 0;
+          if (lane == 0)                             // (inline PTX: the compiler would wrap its own warp aggregation around atomicAdd)
+            asm volatile("atom.shared.add.u32 %0, [%1], %2;" : "=r"(base) : "r"(static_cast<uint32_t>(__cvta_generic_to_shared(&s_hits))), "r"(tot) : "memory");
+          base = __shfl_sync(0xffffffffu, base, 0);
+          const unsigned int lt = (1u << lane) - 1u;
+#pragma unroll
+          for (int u = 0; u < kU; ++u) {
+            const unsigned int m = hm[kTwoTap ? u : 0];
+            if ((m >> lane) & 1u) hit_list[base + __popc(m & lt)] = ((u * kScatterThreads + tid) << 16) | ((yq[u] - r0) * W + xq[u]);
+            base += __popc(m);
+          }
+        }
+        if (bad) {
+          // out-of-sensor events are reported once: rows by strip 0, columns by the strip that owns the row; for
+          // two-tap modes by the event's primary bin only
+#pragma unroll 1
+          for (int u = 0; u < kU; ++u) {             // rolled, re-reading the coordinates: the register arrays stay statically indexed
+            const int o = u * kScatterThreads + tid;
+            if (o >= rem) break;
+            const int yy = static_cast<int>(y16[eb + o]), xx = static_cast<int>(x16[eb + o]);
+            const int ry = yy - r0;
+            const bool inrow = static_cast<unsigned int>(ry) < static_cast<unsigned int>(rows);
+            const bool inx = static_cast<unsigned int>(xx) < static_cast<unsigned int>(W);
+            if ((dropcheck && !inrow && yy >= H) || (inrow && !inx)) {
+              bool primary = true;
+              if (kTwoTap) { double co; primary = bin_floor<MODE>(d, wc, eb + o, &co) == static_cast<double>(bin); }
+              if (primary) ++ndrop;
+            }
           }
         }
       } else {
