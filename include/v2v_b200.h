@@ -54,7 +54,7 @@ long long v2v_launch_count(void);
 enum v2v_noise_mode {
   V2V_NOISE_NONE = 0,     /* no base noise, hot noise only if `hot_noise` given        */
   V2V_NOISE_EXPLICIT = 1, /* caller passes the reference's random fields (bit parity)  */
-  V2V_NOISE_PHILOX = 2    /* counter-based in-kernel generator (throughput mode)       */
+  V2V_NOISE_PHILOX = 2    /* in-kernel generator (throughput mode): Philox4x32-10 root, xoshiro128++ stream per (clip, 4-pixel group) */
 };
 
 enum v2v_threshold_mode {

@@ -93,7 +93,7 @@ def frames_to_voxel(frames: torch.Tensor, pos_thres, neg_thres, *, num_bins: int
     scalar, ``[B]`` (per clip, the ESIM core) or ``[B,H,W]`` (per-pixel maps).
     noise: "none" | "explicit" (u0, hot_noise ``[B,H,W]``, base_gauss
     ``[B,N-1,H,W]`` float64: the reference's random fields) | "philox"
-    (in-kernel counter-based generator keyed by ``seed``; clip ``b`` uses stream
+    (in-kernel generator keyed by ``seed``: Philox4x32-10 root + one xoshiro128++ stream per pixel group; clip ``b`` uses stream
     ``clip_index_base + b``).  ``num_bins*frames_per_bin`` must divide ``N-1``
     (data/v2v_datasets.py:365).  frame_out: None | "frames" (frames
     ``(t+1)*bins*fpb``) | "frames+first" (``t*bins*fpb``, t<=T;
