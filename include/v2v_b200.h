@@ -150,6 +150,11 @@ typedef struct v2v_v2e_desc {
   uint64_t seed, clip_index_base;
   float* voxel;                  /* [B,T,num_bins,H,W] float32                           */
   long long* stats;              /* [B,2] or NULL                                        */
+  /* optional fused frame-side packing, as in v2v_esim_desc (pause gather + HDR/LDR degrade of the dataset) */
+  const int32_t* frame_index;    /* [B,N] raw frame used as frame n (clamped to the clip), or NULL = identity            */
+  int32_t raw_frames_per_clip;   /* frames per clip in `frames` when frame_index is given; 0 = N                         */
+  int32_t reserved0;
+  const uint8_t* value_map;      /* [B,256] uint8 -> uint8 applied to every pixel before any use of its value, or NULL   */
 } v2v_v2e_desc;
 
 int v2v_v2e_frames_to_voxel(const v2v_v2e_desc* desc, void* stream);

@@ -72,3 +72,46 @@ def test_frame_index_is_clamped_and_validated(cuda_device):
         v2v.frames_to_voxel(fr, 0.2, 0.2, num_bins=5, frame_index=np.arange(5, dtype=np.int32))      # (N-1) % 5 != 0
     with pytest.raises(ValueError):
         v2v.frames_to_voxel(fr, 0.2, 0.2, num_bins=5, value_map=np.zeros(17, dtype=np.uint8))
+
+
+@pytest.mark.parametrize("fast", ["1", "0"])
+@pytest.mark.parametrize("noise", ["none", "philox"])
+def test_v2e_fused_pause_gather_and_degrade(cuda_device, monkeypatch, fast, noise):
+    """v2e kernels (throughput and generic, shot pre-pass, field dump): raw stack + frame_index + value_map == the same
+    run on gathered, degraded frames, bit for bit."""
+    import v2v_b200 as v2v
+    from v2v_b200.v2e import frames_to_voxel_v2e
+    if fast == "1":
+        monkeypatch.setenv("V2V_V2E_FAST", "1")
+    else:
+        monkeypatch.setenv("V2V_V2E_GENERIC", "1")
+    n, h, w, B = 13, 40, 64, 2
+    raws, idxs, maps, prepared, m_raw = [], [], [], [], 0
+    np.random.seed(11)
+    for b in range(B):
+        idx, cnt = v2v.sample_pause_indices(n, 0.3, 0.6)
+        raw = synth_video("walk", n, h, w, 70 + b)[:cnt]
+        scale = np.random.uniform(1, 3) if b == 0 else np.random.uniform(0.3, 1)
+        vmap = v2v.degrade_value_map("hdr" if b == 0 else "ldr", scale)
+        prepared.append(np.stack([vmap[raw[i]] for i in idx]))
+        raws.append(raw), idxs.append(idx), maps.append(vmap)
+        m_raw = max(m_raw, cnt)
+    stack = np.zeros((B, m_raw, h, w), dtype=np.uint8)
+    for b in range(B):
+        stack[b, :raws[b].shape[0]] = raws[b]
+    g = np.random.Generator(np.random.PCG64(6))
+    pos = np.clip(g.normal(0.2, 0.05, (B, h, w)), 0.01, None)
+    neg = np.clip(g.normal(0.2, 0.05, (B, h, w)), 0.01, None)
+    nrate = np.exp(np.log(10) * 0.1 * g.standard_normal((B, h, w)).astype(np.float32)).astype(np.float32)
+    kw = dict(fps=24, num_bins=3, frames_per_bin=2, cutoff_hz=30.0, leak_rate_hz=0.1, leak_jitter_fraction=0.1, noise_rate=nrate,
+              with_stats=True, noise=noise)
+    if noise == "philox":
+        kw.update(shot_noise_rate_hz=20.0, seed=4, return_fields=True)
+    fused = frames_to_voxel_v2e(torch.from_numpy(stack).to(cuda_device), pos, neg, frame_index=np.stack(idxs), value_map=np.stack(maps), **kw)
+    plain = frames_to_voxel_v2e(torch.from_numpy(np.stack(prepared)).to(cuda_device), pos, neg, **kw)
+    assert torch.equal(fused["voxel"], plain["voxel"]) and torch.equal(fused["stats"], plain["stats"])
+    assert int(fused["stats"].sum()) > 0
+    if noise == "philox":
+        assert torch.equal(fused["shot_scales"], plain["shot_scales"])
+        for k in ("leak_randn", "pos_shot", "neg_shot"):
+            assert torch.equal(fused["fields"][k], plain["fields"][k])

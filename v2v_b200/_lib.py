@@ -60,6 +60,7 @@ class V2eDesc(C.Structure):
         ("pos_thres_nominal", C.c_double), ("neg_thres_nominal", C.c_double),
         ("seed", C.c_uint64), ("clip_index_base", C.c_uint64),
         ("voxel", _p), ("stats", _p),
+        ("frame_index", _p), ("raw_frames_per_clip", C.c_int32), ("reserved0", C.c_int32), ("value_map", _p),
     ]
 
 

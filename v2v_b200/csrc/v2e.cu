@@ -37,8 +37,9 @@ __global__ void __launch_bounds__(kV2eThreads) v2e_kernel(const V2eArgs a) {
   const v2v_v2e_desc& d = a.d;
   if (LEAK && d.noise_mode == V2V_NOISE_PHILOX) fill_trig_table(trig_s);
   for (int i = threadIdx.x; i < 256; i += kV2eThreads) {
-    L.logv[i] = d.lut[i];
-    const double it = __ddiv_rn(__dadd_rn(static_cast<double>(i), 20.0), 275.0);
+    const int mv = v2e_mapped(a, blockIdx.y, i);                  // the degrade is a function of the pixel value: folded into the LUTs
+    L.logv[i] = d.lut[mv];
+    const double it = __ddiv_rn(__dadd_rn(static_cast<double>(mv), 20.0), 275.0);
     L.inten[i] = it;
     L.facf[i] = static_cast<float>(__dsub_rn(1.0, __dmul_rn(0.75, it)));
   }
@@ -69,9 +70,11 @@ __global__ void __launch_bounds__(kV2eThreads) v2e_kernel(const V2eArgs a) {
     }
   }
 
-  const uint8_t* fr = d.frames + static_cast<int64_t>(b) * N * HW + pix0;
-  auto load = [&](int i) -> uint32_t { return P == 4 ? load_pix4(fr + static_cast<int64_t>(i) * HW)
-                                                     : static_cast<uint32_t>(ld_stream_u8(fr + static_cast<int64_t>(i) * HW)); };
+  const uint8_t* fr = d.frames + static_cast<int64_t>(b) * a.Mraw * HW + pix0;
+  auto load = [&](int i) -> uint32_t {
+    const uint8_t* p = fr + static_cast<int64_t>(v2e_frame_number(a, b, i)) * HW;
+    return P == 4 ? load_pix4(p) : static_cast<uint32_t>(ld_stream_u8(p));
+  };
   {
     // first frame: lp = log_new; the filter runs with dt = 0 (eps = 0); base = lp   (:463-478)
     const uint32_t w0 = load(0);
@@ -225,8 +228,8 @@ __global__ void __launch_bounds__(256) v2e_shot_accum_kernel(const V2eArgs a, lo
   __shared__ double fac_s[256];
   __shared__ unsigned long long sacc[8][2][kShotChunk];      // one row per warp: lane 0 adds without atomics
   const v2v_v2e_desc& d = a.d;
-  for (int i = threadIdx.x; i < 256; i += 256) fac_s[i] = 1.0 - 0.75 * ((static_cast<double>(i) + 20.0) / 275.0);
   const int b = blockIdx.y;
+  for (int i = threadIdx.x; i < 256; i += 256) fac_s[i] = 1.0 - 0.75 * ((static_cast<double>(v2e_mapped(a, b, i)) + 20.0) / 275.0);
   const bool vec = (a.HW % 4 == 0) && aligned_dev(d.frames, 4);
   const int M = d.N - 1;
   for (int c0 = 0; c0 < M; c0 += kShotChunk) {
@@ -247,11 +250,11 @@ __global__ void __launch_bounds__(256) v2e_shot_accum_kernel(const V2eArgs a, lo
 #pragma unroll
       for (int k = 0; k < 4; ++k) lane_small = lane_small && pp[k] >= 0.0 && np_[k] >= 0.0 && pp[k] < 256.0 * kShotFix && np_[k] < 256.0 * kShotFix;
       const bool small = __all_sync(0xffffffffu, lane_small);      // warp-uniform: the lane sums stay below 2^46
-      const uint8_t* fr0 = d.frames + (static_cast<int64_t>(b) * d.N + c0 + 1) * a.HW + pix0;
+      const uint8_t* fr0 = d.frames + static_cast<int64_t>(b) * a.Mraw * a.HW + pix0;
       auto load = [&](int j) -> uint32_t {
         uint32_t w = 0;
         if (j < cn && pix0 < a.HW) {
-          const uint8_t* fr = fr0 + static_cast<int64_t>(j) * a.HW;
+          const uint8_t* fr = fr0 + static_cast<int64_t>(v2e_frame_number(a, b, c0 + 1 + j)) * a.HW;
           if (vec) w = ld_stream_u32(fr);
           else {
 #pragma unroll
@@ -357,7 +360,7 @@ __global__ void v2e_philox_fields_kernel(const V2eArgs a, double* leak_randn, in
     const int64_t o = (static_cast<int64_t>(b) * (d.N - 1) + (i - 1)) * a.HW + pix;
     if (leak_randn) leak_randn[o] = static_cast<double>(lz[j]);
     if (shot && pos_shot && neg_shot) {
-      const uint32_t v = d.frames[(static_cast<int64_t>(b) * d.N + i) * a.HW + pix];
+      const uint32_t v = v2e_mapped(a, b, d.frames[(static_cast<int64_t>(b) * a.Mraw + v2e_frame_number(a, b, i)) * a.HW + pix]);
       const double it = __ddiv_rn(__dadd_rn(static_cast<double>(v), 20.0), 275.0);
       const float fac = static_cast<float>(__dsub_rn(1.0, __dmul_rn(0.75, it)));
       const int64_t si = static_cast<int64_t>(b) * (d.N - 1) + (i - 1);
@@ -381,6 +384,9 @@ int validate(const v2v_v2e_desc& d, V2eArgs* a) {
   a->tau = d.cutoff_hz > 0.0 ? 1.0 / (3.141592653589793 * 2 * d.cutoff_hz) : 0.0;    // :162
   a->leak_hz_f32 = static_cast<float>(d.leak_rate_hz);
   Philox::round_keys(d.seed, a->rk);
+  V2V_REQUIRE(d.raw_frames_per_clip >= 0 && (d.frame_index || d.raw_frames_per_clip == 0 || d.raw_frames_per_clip == d.N),
+              V2V_ERR_INVALID_ARG, "raw_frames_per_clip=%d needs frame_index", d.raw_frames_per_clip);
+  a->Mraw = (d.frame_index && d.raw_frames_per_clip > 0) ? d.raw_frames_per_clip : d.N;
   return V2V_OK;
 }
 

@@ -11,7 +11,18 @@ struct V2eArgs {
   double tau;          // 1/(2*pi*cutoff)
   float leak_hz_f32;   // leak_rate_hz as the float32 it becomes in `leak_rate_hz*noise_rate_array`
   uint32_t rk[20];     // Philox round keys of d.seed (host-precomputed)
+  int32_t Mraw;        // frames per clip in d.frames (N, or raw_frames_per_clip with frame_index)
 };
+
+// frame n of clip b = raw frame frame_index[b][n] (clamped), or n itself (data/v2v_datasets.py:285-311)
+__device__ __forceinline__ int v2e_frame_number(const V2eArgs& a, int b, int n) {
+  const int32_t* fi = a.d.frame_index;
+  return fi ? min(max(fi[static_cast<int64_t>(b) * a.d.N + n], 0), a.Mraw - 1) : n;
+}
+// pixel value after the optional per-clip value map (HDR/LDR degrade, :473-483)
+__device__ __forceinline__ int v2e_mapped(const V2eArgs& a, int b, int v) {
+  return a.d.value_map ? a.d.value_map[static_cast<int64_t>(b) * 256 + v] : v;
+}
 
 // np.floor_divide(max(diff,0), thr) for a >= thr > 0 (the caller filters a < thr); the reciprocal is only
 // needed on the multi-threshold path

@@ -80,6 +80,7 @@ __global__ void __launch_bounds__(kThreads, 4) v2e_fast_kernel(const V2eArgs a) 
   float2* trig_s = reinterpret_cast<float2*>(dyn + kLutBytes + kFacBytes + kLogfBytes);
   double* rcp_s = reinterpret_cast<double*>(dyn + kLutBytes + kFacBytes + kLogfBytes + (LEAK && PHILOX ? kTrigBytes : 0));   // [4][2][kThreads] 1/thr
   IntervalRow* itab = reinterpret_cast<IntervalRow*>(reinterpret_cast<unsigned char*>(rcp_s) + (BF ? kRcpBytes : 0));
+  int* fnum_s = reinterpret_cast<int*>(itab + (a.d.N - 1));                          // raw frame number of every frame of the clip
 
   const v2v_v2e_desc& d = a.d;
   // float32-state variant: conversion unit 71 % busy in ncu -> integer rounding and int->float by FP64/FP32 adds instead;
@@ -88,11 +89,13 @@ __global__ void __launch_bounds__(kThreads, 4) v2e_fast_kernel(const V2eArgs a) 
   const int N = d.N, b = blockIdx.y;
   if (LEAK && PHILOX) fill_trig_table(trig_s);
   for (int i = threadIdx.x; i < 256; i += kThreads) {
-    const double it = __ddiv_rn(__dadd_rn(static_cast<double>(i), 20.0), 275.0);       // :190
-    lut2[i] = make_double2(static_cast<double>(d.lut[i]), it);
+    const int mv = v2e_mapped(a, b, i);                                                // degrade folded into the LUTs
+    const double it = __ddiv_rn(__dadd_rn(static_cast<double>(mv), 20.0), 275.0);      // :190
+    lut2[i] = make_double2(static_cast<double>(d.lut[mv]), it);
     facf_s[i] = static_cast<float>(__dsub_rn(1.0, __dmul_rn(0.75, it)));              // :90
-    logf_s[i] = d.lut[i];
+    logf_s[i] = d.lut[mv];
   }
+  for (int n = threadIdx.x; n < N; n += kThreads) fnum_s[n] = v2e_frame_number(a, b, n);
   for (int i = 1 + threadIdx.x; i < N; i += kThreads) {
     IntervalRow r;
     const double t_k = __ddiv_rn(static_cast<double>(i), d.fps);                       // :577
@@ -151,10 +154,11 @@ __global__ void __launch_bounds__(kThreads, 4) v2e_fast_kernel(const V2eArgs a) 
   thr2 = __dadd_rn(thr2, thr2);       // below 2*min(threshold) of this lane's pixels at most one threshold is crossed
   const float thr2f = __double2float_rd(thr2);
 
-  const uint8_t* fr = d.frames + static_cast<int64_t>(b) * N * HW + pix0;
+  const uint8_t* fr = d.frames + static_cast<int64_t>(b) * a.Mraw * HW + pix0;
+  auto frame_ptr = [&](int n) -> const uint8_t* { return fr + static_cast<int64_t>(fnum_s[n]) * HW; };
   {
     // first frame: lp = log_new; the filter runs with dt = 0 (eps = 0); base = lp   (:463-478)
-    const uint32_t w0 = ld_stream_u32(fr);
+    const uint32_t w0 = ld_stream_u32(frame_ptr(0));
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
       const double l0 = lut2[(w0 >> (8 * k)) & 0xffu].x;
@@ -315,14 +319,14 @@ __global__ void __launch_bounds__(kThreads, 4) v2e_fast_kernel(const V2eArgs a) 
   if (SHOT) {
     // ---- shot-noise variants: the step is ~600 instructions, so the loop stays rolled (one copy of the step: the unrolled
     //      form overflows the instruction cache); three frames in flight through a rotating register window ----
-    uint32_t w0 = ld_stream_u32(fr + HW), w1 = M > 1 ? ld_stream_u32(fr + 2 * HW) : 0u, w2 = M > 2 ? ld_stream_u32(fr + 3 * HW) : 0u;
+    uint32_t w0 = ld_stream_u32(frame_ptr(1)), w1 = M > 1 ? ld_stream_u32(frame_ptr(2)) : 0u, w2 = M > 2 ? ld_stream_u32(frame_ptr(3)) : 0u;
     float le[4] = {0.f, 0.f, 0.f, 0.f}, lo[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll 1
     for (int j = 0; j < M; ++j) {                // interval j = frames (j, j+1)
       const uint32_t w = w0;
       w0 = w1;
       w1 = w2;
-      if (j + 4 < N) w2 = ld_stream_u32(fr + static_cast<int64_t>(j + 4) * HW);
+      if (j + 4 < N) w2 = ld_stream_u32(frame_ptr(j + 4));
       float lz[4] = {0.f, 0.f, 0.f, 0.f};
       if (LEAK && PHILOX && leak_on) {
         if ((j & 1) == 0) v2e_leak_normals(gs, trig_s, le, lo);
@@ -339,14 +343,14 @@ __global__ void __launch_bounds__(kThreads, 4) v2e_fast_kernel(const V2eArgs a) 
   uint32_t cur[kPF], nxt[kPF];
   if (trips > 0) {
 #pragma unroll
-    for (int u = 0; u < kPF; ++u) cur[u] = ld_stream_u32(fr + static_cast<int64_t>(1 + u) * HW);
+    for (int u = 0; u < kPF; ++u) cur[u] = ld_stream_u32(frame_ptr(1 + u));
   }
   const float one4[4] = {1.f, 1.f, 1.f, 1.f};
   int i = 1;
   for (int t = 0; t < trips; ++t) {
     if (t + 1 < trips) {
 #pragma unroll
-      for (int u = 0; u < kPF; ++u) nxt[u] = ld_stream_u32(fr + static_cast<int64_t>(i + kPF + u) * HW);
+      for (int u = 0; u < kPF; ++u) nxt[u] = ld_stream_u32(frame_ptr(i + kPF + u));
     }
 #pragma unroll
     for (int h = 0; h < kPF / 2; ++h) {           // interval pairs (i-1+2h, i+2h)
@@ -365,7 +369,7 @@ __global__ void __launch_bounds__(kThreads, 4) v2e_fast_kernel(const V2eArgs a) 
       if (LEAK && PHILOX && leak_on && ((i - 1) & 1) == 0) v2e_leak_normals(gs, trig_s, le, lo);
 #pragma unroll
       for (int k = 0; k < 4; ++k) lz[k] = ((i - 1) & 1) ? lo[k] : le[k];
-      step(ld_stream_u32(fr + static_cast<int64_t>(i) * HW), i - 1, lz, one4, one4);
+      step(ld_stream_u32(frame_ptr(i)), i - 1, lz, one4, one4);
     }
   }
   }
@@ -394,7 +398,8 @@ __global__ void __launch_bounds__(kThreads, 4) v2e_fast_kernel(const V2eArgs a) 
 }
 
 size_t fast_smem_bytes(const V2eArgs& a, bool trig, bool bf) {
-  return kLutBytes + kFacBytes + kLogfBytes + (trig ? kTrigBytes : 0) + (bf ? kRcpBytes : 0) + static_cast<size_t>(a.d.N - 1) * sizeof(IntervalRow);
+  return kLutBytes + kFacBytes + kLogfBytes + (trig ? kTrigBytes : 0) + (bf ? kRcpBytes : 0) + static_cast<size_t>(a.d.N - 1) * sizeof(IntervalRow) +
+         static_cast<size_t>(a.d.N) * sizeof(int);
 }
 
 }  // namespace

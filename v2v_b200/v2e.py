@@ -59,8 +59,10 @@ def frames_to_voxel_v2e(frames: torch.Tensor, pos_thres, neg_thres, *, fps: floa
                         pos_thres_nominal: float = 0.2, neg_thres_nominal: float = 0.2, noise: str = "none",
                         leak_randn=None, pos_shot=None, neg_shot=None, seed: int = 0, clip_index_base: int = 0,
                         with_stats: bool = False, lut: Optional[np.ndarray] = None,
-                        return_fields: bool = False) -> dict:
-    """CUDA uint8 ``[B,N,H,W]`` + per-pixel threshold maps ``[B,H,W]`` -> float32 ``[B,T,bins,H,W]``."""
+                        return_fields: bool = False, frame_index=None, value_map=None) -> dict:
+    """CUDA uint8 ``[B,N,H,W]`` + per-pixel threshold maps ``[B,H,W]`` -> float32 ``[B,T,bins,H,W]``.
+    ``frame_index`` int32 ``[B,N]`` / ``value_map`` uint8 ``[B,256]``: the dataset's pause gather and HDR/LDR degrade fused
+    into the pass, as in ``frames_to_voxel`` (``frames`` is then the raw stack ``[B,M,H,W]``)."""
     if frames.dim() == 3:
         frames = frames.unsqueeze(0)
     if not frames.is_cuda or frames.dtype != torch.uint8:
@@ -68,6 +70,23 @@ def frames_to_voxel_v2e(frames: torch.Tensor, pos_thres, neg_thres, *, fps: floa
     frames = frames.contiguous()
     dev = frames.device
     B, N, H, W = frames.shape
+    M = N
+    fidx_t = vmap_t = None
+    if frame_index is not None:
+        fidx_t = torch.as_tensor(frame_index).to(device=dev, dtype=torch.int32)
+        if fidx_t.dim() == 1:
+            fidx_t = fidx_t.unsqueeze(0).expand(B, -1)
+        if fidx_t.dim() != 2 or fidx_t.shape[0] != B:
+            raise ValueError("frame_index must be [N] or [B,N]")
+        fidx_t = fidx_t.contiguous()
+        N = int(fidx_t.shape[1])
+    if value_map is not None:
+        vmap_t = torch.as_tensor(value_map).to(device=dev, dtype=torch.uint8)
+        if vmap_t.dim() == 1:
+            vmap_t = vmap_t.unsqueeze(0).expand(B, -1)
+        if tuple(vmap_t.shape) != (B, 256):
+            raise ValueError("value_map must be [256] or [B,256] uint8")
+        vmap_t = vmap_t.contiguous()
     group = num_bins * frames_per_bin
     if (N - 1) % group != 0:
         raise AssertionError(f"(N-1)={N - 1} must be a multiple of num_bins*frames_per_bin={group}")
@@ -96,6 +115,7 @@ def frames_to_voxel_v2e(frames: torch.Tensor, pos_thres, neg_thres, *, fps: floa
     d.pos_thres_nominal, d.neg_thres_nominal = float(pos_thres_nominal), float(neg_thres_nominal)
     d.seed, d.clip_index_base = int(seed) & 0xFFFFFFFFFFFFFFFF, int(clip_index_base)
     d.voxel, d.stats = _ptr(vox), _ptr(stats_t)
+    d.frame_index, d.raw_frames_per_clip, d.value_map = _ptr(fidx_t), (M if fidx_t is not None else 0), _ptr(vmap_t)
     s = torch.cuda.current_stream(dev)
     lib = _lib.load()
     scales = None
