@@ -316,7 +316,21 @@ __global__ void __launch_bounds__(kScatterThreads, 2) scatter_kernel(const Scatt
           okv[u] = o < rem;
           yq[u] = okv[u] ? static_cast<int>(y16[eb + o]) : 0x7fffffff;
           xq[u] = okv[u] ? static_cast<int>(x16[eb + o]) : 0x7fffffff;
-          pv[u] = (okv[u] && !kTwoTap) ? load_f32(d.ps, d.ps_dtype, eb + o) : 0.f;
+          pv[u] = 0.f;
+        }
+        if (!kTwoTap) {                            // polarity: the common dtypes without the per-load dispatch (an indirect branch each)
+          if (d.ps_dtype == V2V_U8) {
+            const uint8_t* p8 = static_cast<const uint8_t*>(d.ps);
+#pragma unroll
+            for (int u = 0; u < kU; ++u) if (okv[u]) pv[u] = static_cast<float>(p8[eb + u * kScatterThreads + tid]);
+          } else if (d.ps_dtype == V2V_F32) {
+            const float* pf = static_cast<const float*>(d.ps);
+#pragma unroll
+            for (int u = 0; u < kU; ++u) if (okv[u]) pv[u] = pf[eb + u * kScatterThreads + tid];
+          } else {
+#pragma unroll
+            for (int u = 0; u < kU; ++u) if (okv[u]) pv[u] = load_f32(d.ps, d.ps_dtype, eb + u * kScatterThreads + tid);
+          }
         }
         // hot loop: range tests only; out-of-sensor events (rare) are collected in `bad` and counted after the loop
         bool bad = false;
