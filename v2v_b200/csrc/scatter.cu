@@ -458,7 +458,8 @@ __global__ void __launch_bounds__(kScatterThreads, 2) scatter_kernel(const Scatt
           const int64_t e = eb + (ent >> 16);
           float pw;
           {
-            const float p = load_f32(d.ps, d.ps_dtype, e);
+            const float p = d.ps_dtype == V2V_U8 ? static_cast<float>(static_cast<const uint8_t*>(d.ps)[e])
+                          : d.ps_dtype == V2V_F32 ? static_cast<const float*>(d.ps)[e] : load_f32(d.ps, d.ps_dtype, e);
             if (d.polarity_mode == V2V_POL_POS_ONLY) pw = p > 0.f ? 1.f : 0.f;
             else if (d.polarity_mode == V2V_POL_NEG_ONLY) pw = p <= 0.f ? 1.f : 0.f;
             else pw = kH5 ? (2.f * p - 1.f) : p;
