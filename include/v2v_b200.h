@@ -54,13 +54,19 @@ long long v2v_launch_count(void);
 enum v2v_noise_mode {
   V2V_NOISE_NONE = 0,     /* no base noise, hot noise only if `hot_noise` given        */
   V2V_NOISE_EXPLICIT = 1, /* caller passes the reference's random fields (bit parity)  */
-  V2V_NOISE_PHILOX = 2    /* in-kernel generator (throughput mode): Philox4x32-10 root, xoshiro128++ stream per (clip, 4-pixel group) */
+  V2V_NOISE_PHILOX = 2    /* in-kernel generator (throughput mode): Philox4x32-10 root, one 64-bit LCG stream per (clip, 4-pixel group) */
 };
 
 enum v2v_threshold_mode {
   V2V_THRES_PER_CLIP = 0, /* pos_thres/neg_thres are [B]      (the ESIM core)          */
   V2V_THRES_PER_PIXEL = 1 /* pos_thres/neg_thres are [B,H,W]  (per-pixel maps)         */
 };
+
+/* v2v_esim_desc.kernel_flags: explicit per-call kernel selection instead of process-wide environment variables */
+#define V2V_ESIM_FLAG_GENERIC 1      /* always the generic kernel (esim.cu); tests compare the two paths bit for bit   */
+#define V2V_ESIM_FLAG_SMALL_FAST 2   /* launches below 148*2048 pixels: throughput kernel                             */
+#define V2V_ESIM_FLAG_SMALL_P1 4     /* launches below 148*2048 pixels: one pixel per thread                          */
+#define V2V_ESIM_FLAG_GEOM(g) (((g) & 0xf) << 8) /* CTA geometry index of the throughput kernel (tuning sweeps)       */
 
 typedef struct v2v_esim_desc {
   /* shapes */
@@ -100,7 +106,7 @@ typedef struct v2v_esim_desc {
    * `np.clip((img-127.5)*scale+127.5, 0, 255).astype(np.uint8)` (:473-483), a function of the pixel value alone */
   const int32_t* frame_index;    /* [B,N] raw frame used as frame n of the clip (clamped to the clip), or NULL = identity */
   int32_t raw_frames_per_clip;   /* frames per clip in `frames` when frame_index is given ([B,M,H,W]); 0 = N              */
-  int32_t reserved0;
+  int32_t kernel_flags;          /* 0 = library's choice; V2V_ESIM_FLAG_* (tests and tuning: kernel selection never changes results) */
   const uint8_t* value_map;      /* [B,256] uint8 -> uint8 applied to every pixel before the LUT and frame_out, or NULL   */
 } v2v_esim_desc;
 
@@ -115,8 +121,11 @@ int v2v_esim_philox_fields(const v2v_esim_desc* desc, double* u0, double* hot_no
 
 /* Audit hook for the generators themselves: writes (a) the Philox4x32-10 block of an arbitrary counter/key
  * (known-answer tests of the published algorithm) to philox_out[4] and (b) the first `n_words` 32-bit outputs of the
- * ESIM base-noise stream of (seed, clip_index, pixel group) — xoshiro128++ seeded as described in esim_common.cuh —
+ * ESIM base-noise stream of (seed, clip_index, pixel group) — the Philox-seeded 64-bit LCG of esim_common.cuh —
  * to words_out[n_words].  Device pointers; either output may be NULL. */
+/* Copies the generator's 2048-entry direction table to HOST memory: table_host[2k], table_host[2k+1] = high 32-bit
+ * words of double(cos t_k), double(sin t_k), t_k = (2k+1)*pi/2048 (low words are zero).  No GPU needed. */
+int v2v_noise_direction_table(uint32_t* table_host);
 int v2v_rng_words(const uint32_t counter[4], const uint32_t key[2], uint32_t* philox_out, uint64_t seed, uint64_t clip_index,
                   uint64_t pixel_group, int32_t n_words, uint32_t* words_out, void* stream);
 
@@ -128,6 +137,10 @@ int v2v_rng_words(const uint32_t counter[4], const uint32_t key[2], uint32_t* ph
  *              low_pass_filter :139-182, subtract_leak_current :192-211,
  *              compute_event_map :42-62, generate_shot_noise :65-105
  * ======================================================================= */
+
+#define V2V_V2E_FLAG_GENERIC 1       /* always the generic kernel (v2e.cu)                                          */
+#define V2V_V2E_FLAG_FAST 2          /* throughput kernel also below 148*2048 pixels per launch                     */
+#define V2V_V2E_FLAG_DIVERGENT_DIV 4 /* throughput kernel: single-crossing fast path + divergent exact division     */
 
 typedef struct v2v_v2e_desc {
   int32_t B, N, H, W;
@@ -153,7 +166,7 @@ typedef struct v2v_v2e_desc {
   /* optional fused frame-side packing, as in v2v_esim_desc (pause gather + HDR/LDR degrade of the dataset) */
   const int32_t* frame_index;    /* [B,N] raw frame used as frame n (clamped to the clip), or NULL = identity            */
   int32_t raw_frames_per_clip;   /* frames per clip in `frames` when frame_index is given; 0 = N                         */
-  int32_t reserved0;
+  int32_t kernel_flags;          /* 0 = library's choice; V2V_V2E_FLAG_* (tests and tuning: kernel selection never changes results) */
   const uint8_t* value_map;      /* [B,256] uint8 -> uint8 applied to every pixel before any use of its value, or NULL   */
 } v2v_v2e_desc;
 

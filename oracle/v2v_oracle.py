@@ -540,13 +540,122 @@ def xoshiro128pp(state, n):
     return out
 
 
+ESIM_LCG_MUL = 0xF9B25D65      # 32-bit multiplier for a 64-bit LCG (Steele & Vigna 2021), v2v_b200/csrc/esim_common.cuh
+
+
 def esim_noise_stream_words(seed, clip_index, pixel_group, n):
-    """The ESIM base-noise stream of one (clip, 4-pixel group): xoshiro128++ seeded with the Philox4x32-10 block of
-    counter (group lo32, 0, clip lo32, tag1 | group hi14 << 16 | clip hi16) under key (seed lo32, seed hi32)
-    (v2v_b200/csrc/esim_common.cuh)."""
+    """The ESIM base-noise stream of one (clip, 4-pixel group) (v2v_b200/csrc/esim_common.cuh): the Philox4x32-10 block
+    r of counter (group lo32, 0, clip lo32, tag1 | group hi14 << 16 | clip hi16) under key (seed lo32, seed hi32)
+    seeds the 64-bit linear congruential generator s' = s*0xf9b25d65 + c (mod 2^64) with s = r[1]<<32 | r[0] and
+    the odd increment c = r[3]<<32 | r[2] | 1; the outputs are the high words of the successive states."""
     ctr = [pixel_group & 0xFFFFFFFF, 0, clip_index & 0xFFFFFFFF,
            0x40000000 | (((pixel_group >> 32) & 0x3FFF) << 16) | ((clip_index >> 32) & 0xFFFF)]
-    st = philox4x32_10(ctr, [seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF])
-    if not any(st):
-        st[0] = 0x9E3779B9
-    return xoshiro128pp(st, n)
+    r = philox4x32_10(ctr, [seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF])
+    s, c = (r[1] << 32) | r[0], (r[3] << 32) | r[2] | 1
+    out = []
+    for _ in range(n):
+        s = (s * ESIM_LCG_MUL + c) & 0xFFFFFFFFFFFFFFFF
+        out.append(s >> 32)
+    return out
+
+
+def esim_direction_table():
+    """The generator's 2048 directions as float64 (cos, sin) pairs with 21 significant bits: entry k is the double whose
+    high word is the high word of cos/sin((2k+1)*pi/2048) rounded to nearest at bit 32 and whose low word is zero
+    (tools/gen_dir_table.py builds the library's copy the same way; a test compares the two)."""
+    t = (2 * np.arange(2048, dtype=np.float64) + 1) * (np.pi / 2048)
+    cs = np.stack([np.cos(t), np.sin(t)], axis=1)
+    bits = cs.view(np.uint64)
+    return (((bits + np.uint64(0x80000000)) >> np.uint64(32)) << np.uint64(32)).view(np.float64)
+
+
+def esim_noise_from_words(words, std, pixel_group, table=None):
+    """Documented word -> noise mapping of the in-kernel generator, evaluated in float64 (the device evaluates the radius
+    with the SFU's lg2 / sqrt approximations in float32, so this is a close, not a bit-exact, restatement): interval i
+    uses words 2i and 2i+1; a word gives the Box-Muller pair of two neighbouring pixels (word 2i -> pixels 0,1, word
+    2i+1 -> pixels 2,3): radius from its low 21 bits, u = (2^21 - low21) / 2^21, r = std*sqrt(-2 ln u); direction index
+    = (top 8 bits << 3) | (pixel_group & 7); even pixel r*cos, odd pixel r*sin.  Returns [len(words)//2, 4]."""
+    table = esim_direction_table() if table is None else table
+    w = np.asarray(words, dtype=np.uint64)
+    u = (2.0 ** 21 - (w & np.uint64(0x1FFFFF)).astype(np.float64)) / 2.0 ** 21
+    r = np.float64(np.float32(std)) * np.sqrt(-2.0 * np.log(u))
+    idx = (((w >> np.uint64(21)) & np.uint64(0x7F8)) | np.uint64(pixel_group & 7)).astype(np.int64)
+    pairs = r[:, None] * table[idx]                       # [n_words, 2]
+    return pairs.reshape(-1, 4)
+
+
+# ---- voxel-space augmentation of the cached-voxel dataset (SURVEY.md §8 f-3) -----------------------------------
+
+def add_noise_to_voxel(voxel, noise_std=1.0, noise_fraction=0.1, integer_noise=False, rs=np.random):
+    """data/esim_dataset.py:33-46.  Draw order on the legacy NumPy stream: integer noise = poisson(shape) then
+    randint(0,2,shape); Gaussian = randn(shape); then rand(shape) for the mask when noise_fraction < 1.  Returns
+    float64 ``voxel + noise`` (the caller's float32 array rounds it on assignment)."""
+    if integer_noise:
+        lmb = (-1 + np.sqrt(1 + 4 * noise_std ** 2)) / 2
+        y = rs.poisson(lam=lmb, size=voxel.shape)
+        sign = 2 * rs.randint(0, 2, size=voxel.shape) - 1
+        noise = y * sign
+    else:
+        noise = noise_std * rs.randn(*voxel.shape)
+    if noise_fraction < 1.0:
+        mask = rs.rand(*voxel.shape) >= noise_fraction
+        noise = np.where(mask, 0, noise)
+    return voxel + noise
+
+
+def hot_pixel_draws(H, W, hot_pixel_std, max_hot_pixel_fraction, integer_noise, rs=np.random, pyrand=None):
+    """The host draws of add_hot_pixels_to_voxels (data/esim_dataset.py:10-24): ``random.uniform`` for the fraction,
+    randint x (columns), randint y (rows), then the values.  With integer noise the reference REUSES the name ``y`` for
+    the Poisson draws (:19), so the rows the noise lands on are the Poisson values themselves — restated as is.
+    Returns (rows, cols, values)."""
+    import random as _random
+    pyrand = _random if pyrand is None else pyrand
+    frac = pyrand.uniform(0, max_hot_pixel_fraction)
+    num = int(frac * H * W)
+    x = rs.randint(0, W, num)
+    y = rs.randint(0, H, num)
+    if integer_noise:
+        lmb = (-1 + np.sqrt(1 + 4 * hot_pixel_std ** 2)) / 2
+        y = rs.poisson(lam=lmb, size=num)
+        sign = 2 * rs.randint(0, 2, size=num) - 1
+        val = y * sign
+    else:
+        val = rs.randn(num)
+        val *= hot_pixel_std
+    return y, x, val
+
+
+def add_hot_pixels_to_voxels(voxels, hot_pixel_std=1.0, max_hot_pixel_fraction=0.001, integer_noise=False, rs=np.random,
+                             pyrand=None):
+    """data/esim_dataset.py:7-30: one [H,W] noise map (np.add.at, float64) added in place to every [T,C] plane."""
+    T, C, H, W = voxels.shape
+    y, x, val = hot_pixel_draws(H, W, hot_pixel_std, max_hot_pixel_fraction, integer_noise, rs, pyrand)
+    noise = np.zeros((H, W))
+    np.add.at(noise, (y, x), val)
+    voxels += noise[np.newaxis, np.newaxis, ...]
+    return voxels
+
+
+def cached_sequence_item(all_frame, all_flow, all_voxel, sequence_length, proba_pause_when_running, proba_pause_when_paused,
+                         noise_std, noise_fraction, hot_pixel_std, max_hot_pixel_fraction, integer_noise, rs=np.random,
+                         pyrand=None):
+    """ESIMH5Dataset.__getitem__ after the crop / flip (data/esim_dataset.py:108-143): the pause sequence (one
+    ``rand()`` per step, drawn BEFORE that step's voxel noise; a paused step repeats the previous frame and leaves flow
+    and voxel zero), per-step add_noise_to_voxel, then add_hot_pixels_to_voxels on the whole sequence.  float32 in,
+    float32 out (the reference's arrays are the h5 file's float32).  Returns (frame, flow, voxel, source_index) where
+    source_index[t] is the cached sample used at step t, or -1 for a paused step."""
+    frame, flow, voxel = np.zeros_like(all_frame), np.zeros_like(all_flow), np.zeros_like(all_voxel)
+    src = np.full(sequence_length, -1, dtype=np.int64)
+    paused, k = False, 0
+    for t in range(sequence_length):
+        u = rs.rand()
+        paused = u < (proba_pause_when_paused if paused else proba_pause_when_running)
+        if t > 0 and paused:
+            frame[t] = frame[t - 1]
+        else:
+            frame[t], flow[t], voxel[t] = all_frame[k], all_flow[k], all_voxel[k]
+            src[t] = k
+            k += 1
+        voxel[t] = add_noise_to_voxel(voxel[t], noise_std, noise_fraction, integer_noise, rs)
+    voxel = add_hot_pixels_to_voxels(voxel, hot_pixel_std, max_hot_pixel_fraction, integer_noise, rs, pyrand)
+    return frame, flow, voxel, src

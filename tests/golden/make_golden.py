@@ -361,10 +361,62 @@ def gen_frames(dsets, out):
     out["bgr_to_gray"] = dict(img=img, ref=ref, n_sensitive=int(sens.sum()))
 
 
+def gen_augment(out):
+    """Voxel-space augmentation of the cached-voxel dataset: the reference's own add_noise_to_voxel /
+    add_hot_pixels_to_voxels / ESIMH5Dataset.__getitem__ (data/esim_dataset.py:7-46,84-153).  The dataset object is
+    built without its constructor and reads from a dict of arrays instead of an h5 file (the I/O is out of scope)."""
+    import random
+    import data.esim_dataset as ed
+    g = np.random.Generator(np.random.PCG64(99))
+    vox = g.integers(-3, 4, size=(6, 5, 24, 40)).astype(np.float32)
+    k = 0
+    for integer_noise in (False, True):
+        for frac in (0.1, 1.0):
+            np.random.seed(40 + k)
+            ref = ed.add_noise_to_voxel(vox[0].copy(), 0.7, frac, integer_noise)
+            np.random.seed(40 + k)
+            mine = orc.add_noise_to_voxel(vox[0].copy(), 0.7, frac, integer_noise)
+            assert same(ref, mine), "oracle != reference for add_noise_to_voxel"
+            out[f"noise_int{int(integer_noise)}_frac{frac}"] = dict(voxel=vox[0], noise_std=0.7, noise_fraction=frac,
+                                                                    integer_noise=int(integer_noise), seed=40 + k, ref=ref)
+            k += 1
+        np.random.seed(60 + k), random.seed(7 + k)
+        ref = ed.add_hot_pixels_to_voxels(vox.astype(np.float32).copy(), 2.0, 0.05, integer_noise)
+        np.random.seed(60 + k), random.seed(7 + k)
+        mine = orc.add_hot_pixels_to_voxels(vox.astype(np.float32).copy(), 2.0, 0.05, integer_noise)
+        assert same(ref, mine) and (ref != vox).any(), "oracle != reference for add_hot_pixels_to_voxels"
+        out[f"hot_int{int(integer_noise)}"] = dict(voxels=vox, hot_pixel_std=2.0, max_hot_pixel_fraction=0.05,
+                                                    integer_noise=int(integer_noise), np_seed=60 + k, py_seed=7 + k, ref=ref)
+    # the dataset item: crop and flip off (views), pause + noise + hot pixels as the reference runs them
+    S, T, Hh, Ww = 14, 10, 20, 28
+    frames = g.random((S, 1, Hh, Ww)).astype(np.float32)
+    flow = g.standard_normal((S, 2, Hh, Ww)).astype(np.float32)
+    events = g.integers(-4, 5, size=(S, 5, Hh, Ww)).astype(np.float32)
+    for case, (integer_noise, frac, pr, pp) in enumerate([(False, 1.0, 0.05, 0.9), (False, 0.3, 0.4, 0.6), (True, 1.0, 0.3, 0.9)]):
+        ds = ed.ESIMH5Dataset.__new__(ed.ESIMH5Dataset)
+        ds.h5_file = {"frames": frames, "flow": flow, "events": events}
+        ds.sequence_length, ds.samples = T, [(2, 2 + T)]
+        ds.proba_pause_when_running, ds.proba_pause_when_paused = pr, pp
+        ds.noise_std, ds.noise_fraction, ds.hot_pixel_std, ds.max_hot_pixel_fraction = 0.6, frac, 1.5, 0.03
+        ds.random_crop_size, ds.random_flip, ds.integer_noise, ds.data_source_idx = None, False, integer_noise, 0
+        np.random.seed(80 + case), random.seed(3 + case)
+        item = ds[0]
+        np.random.seed(80 + case), random.seed(3 + case)
+        fr, fl, vx, src = orc.cached_sequence_item(frames[2:2 + T], flow[2:2 + T], events[2:2 + T], T, pr, pp, 0.6, frac, 1.5,
+                                                   0.03, integer_noise)
+        assert same(item["frame"].numpy(), fr) and same(item["flow"].numpy(), fl) and same(item["events"].numpy(), vx), \
+            "oracle != reference for ESIMH5Dataset.__getitem__"
+        assert (src < 0).any() or case == 0
+        out[f"item_{case}"] = dict(frames=frames[2:2 + T], flow=flow[2:2 + T], events=events[2:2 + T], sequence_length=T,
+                                   proba_pause_when_running=pr, proba_pause_when_paused=pp, noise_std=0.6, noise_fraction=frac,
+                                   hot_pixel_std=1.5, max_hot_pixel_fraction=0.03, integer_noise=int(integer_noise),
+                                   np_seed=80 + case, py_seed=3 + case, ref_frame=fr, ref_flow=fl, ref_events=vx, src=src)
+
+
 def main():
     esim, v2e, dsets, testh5, eu = import_reference()
     only = sys.argv[sys.argv.index("--only") + 1].split(",") if "--only" in sys.argv else None
-    groups = {"esim": {}, "v2e": {}, "scatter": {}, "frames": {}}
+    groups = {"esim": {}, "v2e": {}, "scatter": {}, "frames": {}, "augment": {}}
     if only:
         groups = {k: v for k, v in groups.items() if k in only}
     if "esim" in groups:
@@ -375,6 +427,8 @@ def main():
         gen_scatter(testh5, eu, groups["scatter"])
     if "frames" in groups:
         gen_frames(dsets, groups["frames"])
+    if "augment" in groups:
+        gen_augment(groups["augment"])
     import torch
     meta = dict(numpy=np.__version__, torch=torch.__version__)
     for gname, cases in groups.items():

@@ -204,3 +204,51 @@ def test_rng_restatements_known_answers():
     assert orc.philox4x32_10([0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344], [0xa4093822, 0x299f31d0]) == \
         [0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1]
     assert orc.xoshiro128pp([1, 2, 3, 4], 4) == [641, 1573767, 3222811527, 3517856514]
+
+
+def test_direction_table_matches_library():
+    """The oracle's restatement of the generator's direction table == the table compiled into the library (host copy
+    through the C ABI; no GPU needed), and its entries are unit vectors to 21 bits."""
+    import ctypes as C
+    import v2v_oracle as orc
+    from v2v_b200 import _lib
+    buf = (C.c_uint32 * 4096)()
+    _lib.check(_lib.load().v2v_noise_direction_table(buf))
+    hi = np.frombuffer(buf, dtype=np.uint32).reshape(2048, 2).astype(np.uint64)
+    lib_tab = (hi << np.uint64(32)).view(np.float64)
+    tab = orc.esim_direction_table()
+    assert np.array_equal(lib_tab, tab)
+    assert np.abs(np.hypot(tab[:, 0], tab[:, 1]) - 1).max() < 2.0 ** -20
+    # the 64-bit LCG behind the noise streams, against a direct big-integer evaluation
+    w = orc.esim_noise_stream_words(123, 5, 77, 3)
+    r = orc.philox4x32_10([77, 0, 5, 0x40000000], [123, 0])
+    s, c = (r[1] << 32) | r[0], (r[3] << 32) | r[2] | 1
+    s1 = (s * 0xF9B25D65 + c) % 2 ** 64
+    s2 = (s1 * 0xF9B25D65 + c) % 2 ** 64
+    assert w[:2] == [s1 >> 32, s2 >> 32]
+
+
+def test_augment_oracle_vs_reference_goldens():
+    """oracle/ restatement of data/esim_dataset.py:7-46,84-153 == the reference's recorded outputs (same seeds)."""
+    import random
+    import v2v_oracle as orc
+    G = golden("augment")
+    for name in G.names("noise_"):
+        c = G.case(name)
+        np.random.seed(int(c["seed"]))
+        out = orc.add_noise_to_voxel(c["voxel"].copy(), float(c["noise_std"]), float(c["noise_fraction"]), bool(c["integer_noise"]))
+        assert same(out, c["ref"])
+    for name in G.names("hot_"):
+        c = G.case(name)
+        np.random.seed(int(c["np_seed"])), random.seed(int(c["py_seed"]))
+        out = orc.add_hot_pixels_to_voxels(c["voxels"].copy(), float(c["hot_pixel_std"]), float(c["max_hot_pixel_fraction"]),
+                                           bool(c["integer_noise"]))
+        assert same(out, c["ref"])
+    for name in G.names("item_"):
+        c = G.case(name)
+        np.random.seed(int(c["np_seed"])), random.seed(int(c["py_seed"]))
+        fr, fl, vx, src = orc.cached_sequence_item(c["frames"], c["flow"], c["events"], int(c["sequence_length"]),
+                                                   float(c["proba_pause_when_running"]), float(c["proba_pause_when_paused"]),
+                                                   float(c["noise_std"]), float(c["noise_fraction"]), float(c["hot_pixel_std"]),
+                                                   float(c["max_hot_pixel_fraction"]), bool(c["integer_noise"]))
+        assert same(fr, c["ref_frame"]) and same(fl, c["ref_flow"]) and same(vx, c["ref_events"]) and same(src, c["src"])

@@ -42,8 +42,16 @@ class EsimDesc(C.Structure):
         ("potential_in", _p), ("potential_out", _p),
         ("voxel", _p), ("voxel_row_stride", C.c_int64), ("voxel_plane_stride", C.c_int64),
         ("frame_out", _p), ("stats", _p),
-        ("frame_index", _p), ("raw_frames_per_clip", C.c_int32), ("reserved0", C.c_int32), ("value_map", _p),
+        ("frame_index", _p), ("raw_frames_per_clip", C.c_int32), ("kernel_flags", C.c_int32), ("value_map", _p),
     ]
+
+
+ESIM_FLAG_GENERIC, ESIM_FLAG_SMALL_FAST, ESIM_FLAG_SMALL_P1 = 1, 2, 4
+V2E_FLAG_GENERIC, V2E_FLAG_FAST, V2E_FLAG_DIVERGENT_DIV = 1, 2, 4
+
+
+def esim_flag_geom(g: int) -> int:
+    return (g & 0xF) << 8
 
 
 class V2eDesc(C.Structure):
@@ -60,7 +68,7 @@ class V2eDesc(C.Structure):
         ("pos_thres_nominal", C.c_double), ("neg_thres_nominal", C.c_double),
         ("seed", C.c_uint64), ("clip_index_base", C.c_uint64),
         ("voxel", _p), ("stats", _p),
-        ("frame_index", _p), ("raw_frames_per_clip", C.c_int32), ("reserved0", C.c_int32), ("value_map", _p),
+        ("frame_index", _p), ("raw_frames_per_clip", C.c_int32), ("kernel_flags", C.c_int32), ("value_map", _p),
     ]
 
 
@@ -95,6 +103,7 @@ SYMBOLS = {
     "v2v_launch_count": (C.c_longlong, []),
     "v2v_esim_frames_to_voxel": (C.c_int, [C.POINTER(EsimDesc), _p]),
     "v2v_esim_philox_fields": (C.c_int, [C.POINTER(EsimDesc), _p, _p, _p, _p]),
+    "v2v_noise_direction_table": (C.c_int, [C.POINTER(C.c_uint32)]),
     "v2v_rng_words": (C.c_int, [C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), _p, C.c_uint64, C.c_uint64, C.c_uint64, C.c_int32, _p, _p]),
     "v2v_v2e_frames_to_voxel": (C.c_int, [C.POINTER(V2eDesc), _p]),
     "v2v_v2e_shot_scales": (C.c_int, [C.POINTER(V2eDesc), _p, _p, _p]),

@@ -108,10 +108,10 @@ struct Philox {
   }
   __device__ static __forceinline__ uint4 run_rk(uint4 c, const uint32_t (&rk)[20]) {
 #pragma unroll
-    for (int r = 0; r < 10; ++r) {
-      const uint32_t hi0 = __umulhi(M0, c.x), lo0 = M0 * c.x;
-      const uint32_t hi1 = __umulhi(M1, c.z), lo1 = M1 * c.z;
-      c = make_uint4(hi1 ^ c.y ^ rk[2 * r], lo1, hi0 ^ c.w ^ rk[2 * r + 1], lo0);
+    for (int r = 0; r < 10; ++r) {                      // per round: two 32x32->64 multiplies and two 3-input XORs
+      const uint64_t p0 = static_cast<uint64_t>(M0) * c.x, p1 = static_cast<uint64_t>(M1) * c.z;
+      c = make_uint4(static_cast<uint32_t>(p1 >> 32) ^ c.y ^ rk[2 * r], static_cast<uint32_t>(p1),
+                     static_cast<uint32_t>(p0 >> 32) ^ c.w ^ rk[2 * r + 1], static_cast<uint32_t>(p0));
     }
     return c;
   }

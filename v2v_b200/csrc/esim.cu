@@ -11,7 +11,6 @@
 // 1 byte in + 4/frames_per_bin bytes out per pixel-interval.
 #include "esim_common.cuh"
 
-#include <cstdlib>
 
 namespace v2v {
 namespace {
@@ -34,8 +33,8 @@ struct PixWord<1> {
 template <int P, int NOISE, bool EXTERNAL, bool PERPIXEL, int PF, int LUTC>
 __global__ void __launch_bounds__(kThreads) esim_kernel(const EsimArgs a) {
   __shared__ double lut_s[256 * LUTC];
-  __shared__ float2 trig_s[NOISE == V2V_NOISE_PHILOX ? kTrigEntries : 1];
-  if (NOISE == V2V_NOISE_PHILOX) fill_trig_table(trig_s);
+  __shared__ uint2 dir_s[NOISE == V2V_NOISE_PHILOX ? kDirEntries : 1];
+  if (NOISE == V2V_NOISE_PHILOX) fill_dir_table(dir_s);
   const v2v_esim_desc& d = a.d;
   __shared__ float f255_s[256];                                    // (mapped value)/255 of the ground-truth frame output
   {
@@ -55,10 +54,9 @@ __global__ void __launch_bounds__(kThreads) esim_kernel(const EsimArgs a) {
   const int64_t clip_pix = static_cast<int64_t>(b) * HW + pix0;   // offset in [B,H,W] maps
   const uint64_t clip_id = d.clip_index_base + static_cast<uint64_t>(b);
   const NoiseKey nkey = make_noise_key(clip_id);
-  const float nc2 = noise_c2(static_cast<float>((NOISE != V2V_NOISE_NONE && d.base_noise_std) ? d.base_noise_std[b] : 0.0));
-  GroupStream gs{0u, 0u, 0u, 0u};          // base-noise stream of this lane's 4-pixel group (every lane of a group walks the same stream)
-  float nodd[4] = {0.f, 0.f, 0.f, 0.f};    // the odd interval's normals of the current pair
-  if (NOISE == V2V_NOISE_PHILOX) gs = group_stream_init(static_cast<uint64_t>(pix0) >> 2, nkey, a.rk);
+  const NoiseScale nsc = make_noise_scale(static_cast<float>((NOISE != V2V_NOISE_NONE && d.base_noise_std) ? d.base_noise_std[b] : 0.0));
+  NoiseStream gs{0u, 0u, 1u};                 // base-noise stream of this lane's 4-pixel group (every lane of a group walks the same stream)
+  if (NOISE == V2V_NOISE_PHILOX) gs = noise_stream_init(static_cast<uint64_t>(pix0) >> 2, nkey, a.rk);
 
   // ---- per-pixel / per-clip constants ----
   double pos[PERPIXEL ? P : 1], neg[PERPIXEL ? P : 1], rpos[PERPIXEL ? P : 1], rneg[PERPIXEL ? P : 1];
@@ -182,14 +180,12 @@ __global__ void __launch_bounds__(kThreads) esim_kernel(const EsimArgs a) {
             for (int k = 0; k < P; ++k) bn[k] = 0.0;
           }
         } else if (NOISE == V2V_NOISE_PHILOX) {
-          float nev[4] = {0.f, 0.f, 0.f, 0.f};
-          if (((i - 1) & 1) == 0) stream_noise8(gs, nc2, trig_s, nev, nodd);      // intervals are walked in order: one draw per pair
+          double b4[4];
+          stream_noise4(gs, nsc, dir_s, static_cast<uint32_t>(pix0 >> 2) & 7u, b4);   // intervals are walked in order: one draw each
 #pragma unroll
           for (int k = 0; k < P; ++k) {
             const int j = P == 4 ? k : static_cast<int>(pix0 & 3);
-            const float e = j == 0 ? nev[0] : j == 1 ? nev[1] : j == 2 ? nev[2] : nev[3];
-            const float o = j == 0 ? nodd[0] : j == 1 ? nodd[1] : j == 2 ? nodd[2] : nodd[3];
-            bn[k] = static_cast<double>(((i - 1) & 1) ? o : e);
+            bn[k] = j == 0 ? b4[0] : j == 1 ? b4[1] : j == 2 ? b4[2] : b4[3];
           }
         }
 
@@ -313,8 +309,8 @@ int dispatch_mode(const EsimArgs& a, cudaStream_t s) {
 // Materialise the Philox noise fields exactly as the simulation kernels draw them (test / audit hook):
 // feeding them back through V2V_NOISE_EXPLICIT (with base_noise_std = 1) must reproduce a PHILOX run bit for bit.
 __global__ void esim_philox_fields_kernel(const EsimArgs a, double* u0, double* hot, double* bn) {
-  __shared__ float2 trig_s[kTrigEntries];
-  fill_trig_table(trig_s);
+  __shared__ uint2 dir_s[kDirEntries];
+  fill_dir_table(dir_s);
   __syncthreads();
   const v2v_esim_desc& d = a.d;
   const int b = blockIdx.y;
@@ -327,15 +323,13 @@ __global__ void esim_philox_fields_kernel(const EsimArgs a, double* u0, double* 
   if (u0) u0[o] = u;
   if (hot) hot[o] = h;
   if (bn) {
-    const float nc2 = noise_c2(static_cast<float>(d.base_noise_std[b]));
-    GroupStream gs = group_stream_init(static_cast<uint64_t>(pix) >> 2, nkey, a.rk);
+    const NoiseScale nsc = make_noise_scale(static_cast<float>(d.base_noise_std[b]));
+    NoiseStream gs = noise_stream_init(static_cast<uint64_t>(pix) >> 2, nkey, a.rk);
     const int j = static_cast<int>(pix & 3);
-    float ev[4], od[4] = {0.f, 0.f, 0.f, 0.f};
     for (int i = 0; i < d.N - 1; ++i) {
-      if ((i & 1) == 0) stream_noise8(gs, nc2, trig_s, ev, od);
-      const float e = j == 0 ? ev[0] : j == 1 ? ev[1] : j == 2 ? ev[2] : ev[3];
-      const float o = j == 0 ? od[0] : j == 1 ? od[1] : j == 2 ? od[2] : od[3];
-      bn[(static_cast<int64_t>(b) * (d.N - 1) + i) * a.HW + pix] = static_cast<double>((i & 1) ? o : e);
+      double b4[4];
+      stream_noise4(gs, nsc, dir_s, static_cast<uint32_t>(pix >> 2) & 7u, b4);
+      bn[(static_cast<int64_t>(b) * (d.N - 1) + i) * a.HW + pix] = j == 0 ? b4[0] : j == 1 ? b4[1] : j == 2 ? b4[2] : b4[3];
     }
   }
 }
@@ -353,12 +347,25 @@ __global__ void rng_words_kernel(uint4 ctr, uint2 key, uint32_t* philox_out, Esi
     philox_out[0] = r.x, philox_out[1] = r.y, philox_out[2] = r.z, philox_out[3] = r.w;
   }
   if (words_out) {
-    GroupStream gs = group_stream_init(group, make_noise_key(clip_index), a.rk);
-    for (int i = 0; i < n; ++i) words_out[i] = group_stream_next(gs);
+    NoiseStream gs = noise_stream_init(group, make_noise_key(clip_index), a.rk);
+    for (int i = 0; i < n; ++i) words_out[i] = noise_stream_next(gs);
   }
 }
 }  // namespace
 }  // namespace v2v
+
+extern "C" int v2v_noise_direction_table(uint32_t* table_host) {
+  using namespace v2v;
+  V2V_REQUIRE(table_host != nullptr, V2V_ERR_INVALID_ARG, "table_host is NULL");
+  static const uint2 h_dir_table[kDirEntries] = {
+#include "dir_table.inc"
+  };
+  for (int k = 0; k < kDirEntries; ++k) {
+    table_host[2 * k] = h_dir_table[k].x;
+    table_host[2 * k + 1] = h_dir_table[k].y;
+  }
+  return V2V_OK;
+}
 
 extern "C" int v2v_rng_words(const uint32_t counter[4], const uint32_t key[2], uint32_t* philox_out, uint64_t seed, uint64_t clip_index,
                              uint64_t pixel_group, int32_t n_words, uint32_t* words_out, void* stream) {
@@ -425,11 +432,10 @@ extern "C" int v2v_esim_frames_to_voxel(const v2v_esim_desc* desc, void* stream)
   // small launches: one pixel per thread spreads the serial recurrence over more SMs (noise-free only: with
   // Philox the 4-pixel kernel shares one generator call between its pixels and wins at every size)
   const bool big = static_cast<int64_t>(d.B) * HW >= 148LL * 2048;
-  const char* force = getenv("V2V_ESIM_GENERIC");      // "1": generic kernel (tests compare the two paths bit for bit)
-  const char* small = getenv("V2V_ESIM_SMALL");        // tuning: "fast" / "p1" for small launches
-  const bool generic_only = force && force[0] == '1';
+  const bool generic_only = (d.kernel_flags & V2V_ESIM_FLAG_GENERIC) != 0;
   bool small_fast = d.noise_mode == V2V_NOISE_PHILOX;
-  if (small) small_fast = small[0] == 'f';
+  if (d.kernel_flags & V2V_ESIM_FLAG_SMALL_FAST) small_fast = true;
+  if (d.kernel_flags & V2V_ESIM_FLAG_SMALL_P1) small_fast = false;
   if (vec4 && !generic_only && esim_fast_eligible(a) && (big || small_fast)) return launch_esim_fast(a, s);
   if (!vec4 || !big) return dispatch_mode<1, 4, 1>(a, s);
   return dispatch_mode<4, 4, 1>(a, s);

@@ -3,68 +3,75 @@
 // kernel and applied to the potential; reference data/v2v_core_esim.py:26-69
 // with put_noise_external=False, data/v2v_datasets.py:399-400 with fpb=1).
 //
-// Same arithmetic as the generic kernel in esim.cu, restructured so that the
-// warp issues as few instructions per pixel-interval as possible (the generic
-// kernel is instruction-issue bound at ~40 % of HBM bandwidth):
+// Same arithmetic as the generic kernel in esim.cu.  The kernel is bound by
+// instruction issue, not by bytes, so everything here is about instructions
+// (and shared-memory wavefronts) per (4 pixels x interval):
 //   * 4 pixels per lane, whole clip in registers, frames through a register
-//     ring of 2*PF words, voxels as one 128-bit streaming store per frame;
-//   * the LUT is replicated 8x in shared memory ([value][lane&7]): a half-warp's
-//     64-bit lookups collide only between lanes l and l+8 on different values;
+//     ring of 2*kPF words, voxels as one 128-bit streaming store per frame;
+//   * the log LUT sits in shared memory as [value][lane] (32 copies, 64 KB per
+//     CTA): every 64-bit lookup of a warp is conflict-free, and because an entry
+//     row is 256 bytes the address is ONE byte-permute of the frame word into
+//     the lane's offset (PRMT) added to a uniform base by the load itself;
 //   * a crossing by exactly one threshold (the common case) is branch-free
-//     (select + add, or two FMAs with a 0/1 factor built from the predicate);
+//     (two FMAs with a 0/1 factor built from the predicate, or select + add);
 //     only multi-threshold crossings take the divergent exact floor-division
 //     path, triggered by four FP64 compares chained through one predicate;
-//   * noise from one xoshiro128++ stream per 4-pixel group (seeded by Philox),
-//     8 normals per draw for a pair of intervals (esim_common.cuh);
-//   * statistics in registers, one pair of global reductions per warp at the
-//     end: no shared-memory stage and no CTA barrier after the loop;
+//   * noise: one 64-bit LCG stream per 4-pixel group (seeded by Philox), one
+//     32-bit word per pair of normals (two neighbouring pixels), radius from
+//     the SFU, direction from a 2048-entry float64 table whose 16-byte entries
+//     a quarter warp fetches without bank conflicts; the noise enters the
+//     potential as x = fma(radius, direction, x) — the product is exact, so this
+//     is the reference's `potential += noise` without an FP32 multiply;
+//   * statistics with packed f32x2 adds, one pair of global reductions per warp
+//     at the end: no shared-memory stage and no CTA barrier after the loop;
 //   * optional pause gather / degrade of the dataset fused into the frame loads
 //     and the LUTs (frame_index, value_map).
 #include "esim_common.cuh"
 
-#include <cstdlib>
+#include <atomic>
 
 namespace v2v {
 namespace {
 
-constexpr int kPF = 4;        // frames per loop trip; 2*kPF frames in flight
-constexpr int kLutCopies = 8;
-constexpr int kFastThreads = 128;
-constexpr int kFlushTrips = 8;  // statistics: float partial sums cover 4*kPF*kFlushTrips pixel-intervals (exact for counts < 2^17 each)
+#ifndef V2V_KPF
+#define V2V_KPF 4
+#endif
+constexpr int kPF = V2V_KPF;    // frames per loop trip; 2*kPF frames in flight
+constexpr int kLutCopies = 32;  // one copy per lane
+constexpr int kLutBytes = 256 * kLutCopies * 8;
+// Shared-window address of the dynamic shared memory of a non-cluster CTA without static shared memory on sm_100a (the
+// first KB of the window is reserved; ptxas itself emits this constant when it forms the address).  With the base known at
+// compile time the table lookups below are `LDS [reg + immediate]`: no address add per lookup.  The kernel checks the
+// assumption once per CTA and traps if it ever does not hold.
+constexpr uint32_t kSmemWindowBase = 0x400u;
+constexpr int kFlushTrips = 32 / kPF;  // statistics: the packed counters are unpacked every 32 intervals
 
-// Exact multi-threshold crossing on the ORIGINAL potential x (data/v2v_core_esim.py:51-58).
-// Also correct for |x| below the threshold (count 0), so the caller's trigger may be conservative.
-__device__ __forceinline__ double multi_cross(double x, double pos, double neg, double rpos, double rneg, int* cnt) {
-  const bool down = x < 0.0;
-  const double a = fabs(x), thr = down ? neg : pos, rthr = down ? rneg : rpos;
-  if (a < thr) {
-    *cnt = 0;
-    return x;
-  }
-  const double q = floor_div_exact(a, thr, rthr);
-  const double an = __dsub_rn(a, __dmul_rn(q, thr));
-  *cnt = down ? -static_cast<int>(q) : static_cast<int>(q);
-  return down ? -an : an;
+// Exact multi-threshold crossing (data/v2v_core_esim.py:51-58) of a magnitude a >= thr: q = floor(a/thr) as a
+// mathematical quantity (np.floor_divide), remainder a - RN(q*thr).  rthr = RN(1/thr).
+__device__ __forceinline__ double multi_cross(double a, double thr, double rthr, double* q_out) {
+  double q = floor(__dmul_rn(a, rthr));          // off by at most one
+  const double r = __fma_rn(-q, thr, a);         // sign and size of the single-rounded residual are exact
+  q = r < 0.0 ? q - 1.0 : (r >= thr ? q + 1.0 : q);
+  *q_out = q;
+  return __dsub_rn(a, __dmul_rn(q, thr));
 }
 
-// The common case, branch-free: at most one threshold is crossed, so q*thr == thr exactly and
-// x - q*pos is one rounded subtraction (same value as the reference's separately rounded product
-// and difference because the product is exact).  Written as two predicated FP64 adds: the FP64 pipe
-// has slack, the ALU pipe (selects) does not.
-__device__ __forceinline__ void single_cross(double& x, float& ov, double pos, double mneg) {
+// The common case, branch-free: at most one threshold is crossed, so q*thr == thr exactly and x - q*pos is one rounded
+// subtraction.  qu in {0.0, 1.0}, qd in {0.0, -1.0}: fma(-thr, q, x) rounds once exactly like x -/+ q*thr (:57-58), and
+// a zero q adds -0.0, which leaves every x untouched.  Only the high words are selected (the low words are 0).
+__device__ __forceinline__ void single_cross(double& x, float& ov, uint32_t& hu_out, double pos, double mneg) {
   const bool up = x >= pos, dn = x <= mneg;                                 // :52,55
-  // qu in {0.0, 1.0}, qd in {0.0, -1.0}: q*thr is exact, so fma(-thr, q, x) rounds once exactly like x -/+ q*thr (:57-58),
-  // and a zero q adds -0.0, which leaves every x untouched.  Only the high words are selected (the low words are 0).
   const int hu = up ? 0x3ff00000 : 0, hd = dn ? static_cast<int>(0xbff00000u) : 0;
+  hu_out = static_cast<uint32_t>(hu);
   x = __fma_rn(-pos, __hiloint2double(hu, 0), x);
   x = __fma_rn(mneg, __hiloint2double(hd, 0), x);
   ov = __int_as_float((hu | hd) & static_cast<int>(0xbf800000u));           // +1.0f, -1.0f or 0.0f from the same words
 }
 
-// Select form of the same update (one FP64 add of {-pos, +neg, 0}): fewer registers; used by the noise-free
-// variants, which run at 64 registers / 8 CTAs per SM (the FMA form costs them registers: 1.20 vs 1.15 ms per 32 clips).
-__device__ __forceinline__ void single_cross_sel(double& x, float& ov, double pos, double mneg, double neg) {
+// Select form of the same update (one FP64 add of {-pos, +neg, 0}): fewer registers; used by the noise-free variants.
+__device__ __forceinline__ void single_cross_sel(double& x, float& ov, uint32_t& hu_out, double pos, double mneg, double neg) {
   const bool up = x >= pos, dn = x <= mneg;
+  hu_out = up ? 0x3ff00000u : 0u;
   double sel = up ? -pos : 0.0;
   sel = dn ? neg : sel;
   x = __dadd_rn(x, sel);
@@ -72,75 +79,100 @@ __device__ __forceinline__ void single_cross_sel(double& x, float& ov, double po
   ov = dn ? -1.0f : ov;
 }
 
-template <int NOISE, bool FRAMES, bool STATS, int CTAS>
-__global__ void __launch_bounds__(kFastThreads, CTAS) esim_fast_kernel(const EsimArgs a) {
-  extern __shared__ __align__(16) unsigned char dyn_smem[];     // [LUT copies 32 KB][trig table 32 KB, Philox only]
-  double* lut_s = reinterpret_cast<double*>(dyn_smem);
-  float2* trig_s = reinterpret_cast<float2*>(dyn_smem + 256 * kLutCopies * sizeof(double));
-  __shared__ float f255_s[FRAMES ? 256 : 1];                       // (mapped value)/255 of the ground-truth frame output
-  __shared__ double cta_rcp[2];                                    // 1/pos, 1/neg of this CTA's clip: only the rare path reads them
-  __shared__ float4 hot_s[NOISE == V2V_NOISE_PHILOX ? kFastThreads : 1];   // per-lane hot-pixel noise: read by the ~6 % of warps that own one
-  int* fnum_s = reinterpret_cast<int*>(dyn_smem + 256 * kLutCopies * sizeof(double) + (NOISE == V2V_NOISE_PHILOX ? kTrigEntries * sizeof(float2) : 0));
-  if (NOISE == V2V_NOISE_PHILOX) fill_trig_table(trig_s);
+template <int NOISE, bool FRAMES, bool GATHER, int THREADS>
+struct FastSmem {
+  static constexpr bool kPh = NOISE == V2V_NOISE_PHILOX;
+  static constexpr int lut = 0;
+  static constexpr int dir = lut + kLutBytes;
+  static constexpr int hot = dir + (kPh ? kDirEntries * 16 : 0);
+  static constexpr int f255 = hot + (kPh ? THREADS * 16 : 0);
+  static constexpr int rcp = f255 + (FRAMES ? 256 * 4 : 0);
+  static constexpr int fnum = rcp + 16;
+  static size_t bytes(int N) { return fnum + (GATHER ? static_cast<size_t>(N) * 4 : 0); }
+};
+
+template <int NOISE, bool FRAMES, bool STATS, bool GATHER, int THREADS, int CTAS>
+__global__ void __launch_bounds__(THREADS, CTAS) esim_fast_kernel(const EsimArgs a) {
+  using L = FastSmem<NOISE, FRAMES, GATHER, THREADS>;
+  constexpr bool kPh = NOISE == V2V_NOISE_PHILOX;
+  extern __shared__ __align__(16) unsigned char dyn_smem[];
+  float4* hot_s = reinterpret_cast<float4*>(dyn_smem + L::hot);        // per-lane hot-pixel noise: read by the ~6 % of warps that own one
+  float* f255_s = reinterpret_cast<float*>(dyn_smem + L::f255);        // (mapped value)/255 of the ground-truth frame output
+  double* cta_rcp = reinterpret_cast<double*>(dyn_smem + L::rcp);      // 1/pos, 1/neg of this CTA's clip: only the rare path reads them
+  uint32_t* fnum_s = reinterpret_cast<uint32_t*>(dyn_smem + L::fnum);  // raw frame number of frame n (pause gather)
   const v2v_esim_desc& d = a.d;
-  {
-    const int32_t* fidx = d.frame_index ? d.frame_index + static_cast<int64_t>(blockIdx.y) * d.N : nullptr;
-    for (int n = threadIdx.x; n < d.N; n += kFastThreads) fnum_s[n] = fidx ? min(max(fidx[n], 0), a.Mraw - 1) : n;
+  const uint32_t smem_base = static_cast<uint32_t>(__cvta_generic_to_shared(dyn_smem));
+  if (smem_base != kSmemWindowBase) __trap();
+  if (kPh) {                       // {double(cos), double(sin)} per direction: the table's high words over zero low words
+    uint4* dir_s = reinterpret_cast<uint4*>(dyn_smem + L::dir);
+    for (int k = threadIdx.x; k < kDirEntries; k += THREADS) dir_s[k] = make_uint4(0u, g_dir_table[k].x, 0u, g_dir_table[k].y);
+  }
+  if (GATHER) {
+    const int32_t* fidx = d.frame_index + static_cast<int64_t>(blockIdx.y) * d.N;
+    for (int n = threadIdx.x; n < d.N; n += THREADS) fnum_s[n] = static_cast<uint32_t>(min(max(fidx[n], 0), a.Mraw - 1));
   }
   if (threadIdx.x < 2) cta_rcp[threadIdx.x] = __drcp_rn(threadIdx.x ? d.neg_thres[blockIdx.y] : d.pos_thres[blockIdx.y]);
   {
     const uint8_t* vmap = d.value_map ? d.value_map + static_cast<int64_t>(blockIdx.y) * 256 : nullptr;   // degrade folded into the LUTs
-    for (int e = threadIdx.x; e < 256; e += kFastThreads) {
-      const int ev = vmap ? vmap[e] : e;
-      const double v = d.lut[ev];
-      if (FRAMES) f255_s[e] = __fdiv_rn(static_cast<float>(ev), 255.0f);
+    for (int j = threadIdx.x; j < 256 * 4; j += THREADS) {     // a quarter row (8 copies) per task, two copies per 128-bit store
+      const int v = j >> 2;
+      const int ev = vmap ? vmap[v] : v;
+      const double val = d.lut[ev];
+      const uint32_t at = smem_base + L::lut + j * 64;
 #pragma unroll
-      for (int c = 0; c < kLutCopies; ++c) lut_s[e * kLutCopies + c] = v;
+      for (int q = 0; q < 4; ++q) asm volatile("st.shared.v2.f64 [%0], {%1, %1};" ::"r"(at + q * 16), "d"(val) : "memory");
+      if (FRAMES && (j & 3) == 0) f255_s[v] = __fdiv_rn(static_cast<float>(ev), 255.0f);
     }
   }
   __syncthreads();
 
   const int b = blockIdx.y;
-  const int64_t pix0 = (static_cast<int64_t>(blockIdx.x) * kFastThreads + threadIdx.x) * 4;
+  const int64_t pix0 = (static_cast<int64_t>(blockIdx.x) * THREADS + threadIdx.x) * 4;
   const int64_t HW = a.HW;
+  const unsigned int full = __ballot_sync(0xffffffffu, pix0 < HW);   // the lanes that work: fixed before any divergence
   if (pix0 < HW) {
   const int N = d.N;
+  const uint32_t hw32 = static_cast<uint32_t>(HW);
   const int64_t clip_pix = static_cast<int64_t>(b) * HW + pix0;
   const NoiseKey nkey = make_noise_key(d.clip_index_base + static_cast<uint64_t>(b));
-  GroupStream gs{0u, 0u, 0u, 0u};
-  if (NOISE == V2V_NOISE_PHILOX) gs = group_stream_init(static_cast<uint64_t>(pix0) >> 2, nkey, a.rk);
+  NoiseStream gs{0u, 0u, 1u};
+  if (kPh) gs = noise_stream_init(static_cast<uint64_t>(pix0) >> 2, nkey, a.rk);
 
   const double pos = d.pos_thres[b], neg = d.neg_thres[b];
   const double mneg = -neg;
-  const double thr2 = __dadd_rn(fmin(pos, neg), fmin(pos, neg));   // below 2*min(pos,neg) at most one threshold is crossed
-  constexpr bool kFmaCross = NOISE == V2V_NOISE_PHILOX;            // which form of the single crossing (see single_cross*)
-  const float nc2 = NOISE == V2V_NOISE_PHILOX ? noise_c2(static_cast<float>(d.base_noise_std[b])) : 0.f;
-  // byte offset of this lane's LUT copy
-  const uint32_t lut_base = static_cast<uint32_t>(__cvta_generic_to_shared(dyn_smem)) + (threadIdx.x & (kLutCopies - 1)) * 8u;
-  auto lut_at = [&](uint32_t v) -> double {
+  const NoiseScale nsc = make_noise_scale(kPh ? static_cast<float>(d.base_noise_std[b]) : 0.f);
+  // LUT address = uniform base + (value << 8 | lane*8): the PRMT drops byte k of the frame word into byte 1 of the lane offset
+  const uint32_t lane8 = (threadIdx.x & 31u) * 8u;
+  auto lut_at = [&](uint32_t w, int k) -> double {
+    uint32_t off;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(off) : "r"(w), "r"(lane8), "r"(0x7604u | (static_cast<uint32_t>(k) << 4)));
     double r;
-    asm("ld.shared.f64 %0, [%1];" : "=d"(r) : "r"(lut_base + v * (kLutCopies * 8u)));
+    asm("ld.shared.f64 %0, [%1+%2];" : "=d"(r) : "r"(off), "n"(kSmemWindowBase + L::lut));
     return r;
   };
-  auto byte_of = [](uint32_t w, int k) -> uint32_t {      // one PRMT instead of shift+mask
-    uint32_t v;
-    asm("prmt.b32 %0, %1, 0, %2;" : "=r"(v) : "r"(w), "r"(0x4440u | static_cast<uint32_t>(k)));
-    return v;
-  };
 
-  // frame n of the clip = raw frame frame_index[b][n] (pause gather, data/v2v_datasets.py:285-311), or n itself: the
-  // per-clip table of raw frame numbers sits in shared memory (one broadcast LDS per load, no extra live registers)
+  // frame n of the clip = raw frame frame_index[b][n] (pause gather, data/v2v_datasets.py:285-311), or n itself
+  // (without the gather the loads walk a loop-carried pointer: ptxas would otherwise rebuild the address from the
+  // block and thread indices on every trip instead of holding two registers)
   const uint8_t* fr = d.frames + (static_cast<int64_t>(b) * a.Mraw) * HW + pix0;
-  auto frame_ptr = [&](int n) -> const uint8_t* { return fr + static_cast<int64_t>(fnum_s[n]) * HW; };
+  const uint8_t* fwalk = fr;
+  auto frame_ptr = [&](int n) -> const uint8_t* {
+    if (GATHER) return fr + static_cast<uint64_t>(fnum_s[n]) * hw32;            // one IMAD.WIDE.U32
+    const uint8_t* p = fwalk;                                                   // frames are requested in order
+#ifndef V2V_ABL_MEM
+    fwalk += hw32;
+#endif
+    return p;
+  };
   double pot[4], lprev[4];
   float hotf[4];            // Philox hot-pixel noise is double(float) by construction: keep the float (parked in smem)
   const uint32_t w0 = ld_stream_u32(frame_ptr(0));
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
-    lprev[k] = lut_at(byte_of(w0, k));
+    lprev[k] = lut_at(w0, k);
     hotf[k] = 0.f;
     double u = -1.0;
-    if (NOISE == V2V_NOISE_PHILOX) {
+    if (kPh) {
       double hk;
       philox_init_pixel(static_cast<uint64_t>(pix0 + k), nkey, a.rk, d.hot_pixel_fraction[b], static_cast<float>(d.hot_pixel_std[b]), &u, &hk);
       hotf[k] = static_cast<float>(hk);     // exact: hk was produced from a float
@@ -163,41 +195,84 @@ __global__ void __launch_bounds__(kFastThreads, CTAS) esim_fast_kernel(const Esi
     st_stream_f32x4(fout, f255_s[w0 & 0xffu], f255_s[(w0 >> 8) & 0xffu], f255_s[(w0 >> 16) & 0xffu], f255_s[w0 >> 24]);
     fout += HW;
   }
-  float net = 0.f, tot = 0.f;             // since the last flush: net = #pos - #neg, tot = #pos + #neg
+  // Event statistics without floating point: the crossing already holds, per pixel, hu in {0, 0x3ff00000} (up) and the
+  // output word ov in {0, 0x3f800000, 0xbf800000}.  Summed as plain integers (two 3-input adds each per interval),
+  // su = 1023*2^20 * #up and sv = 2^23 * (127*#up + 383*#down) modulo 2^32; 1023 and 383 are odd, so both counts come
+  // back exactly while #up < 4096 and #down < 512 per lane — they are unpacked every 32 intervals (<= 128 each).  A
+  // multi-threshold crossing has already contributed one event here; the exact path adds the other q-1.
+  uint32_t su = 0u, sv = 0u;
+  unsigned int xpos = 0u, xneg = 0u;      // extra events of the multi-threshold crossings since the last flush
   unsigned int wpos = 0u, wneg = 0u;      // this warp's event totals (the same value in every lane)
-  auto flush_stats = [&]() {              // float sums -> integers, added across the warp with one REDUX each; registers only
-    const unsigned int m = __activemask();       // (all active lanes of a warp run the same trip count)
-    wpos += __reduce_add_sync(m, static_cast<unsigned int>((tot + net) * 0.5f));
-    wneg += __reduce_add_sync(m, static_cast<unsigned int>((tot - net) * 0.5f));
-    net = tot = 0.f;
+  auto flush_stats = [&]() {              // unpack, add across the warp with one REDUX each; registers only
+    const uint32_t nu = ((su >> 20) * 3071u) & 4095u;                     // 1023 * 3071 = 1 (mod 4096)
+    const uint32_t nd = ((((sv >> 23) - 127u * nu) & 511u) * 127u) & 511u;   // 383 * 127 = 1 (mod 512)
+    wpos += __reduce_add_sync(full, nu + xpos);
+    wneg += __reduce_add_sync(full, nd + xneg);
+    su = sv = 0u;
+    xpos = xneg = 0u;
   };
 
   bool lane_hot = false;
 #pragma unroll
   for (int k = 0; k < 4; ++k) lane_hot = lane_hot || hotf[k] != 0.f;
   // warp-uniform: a real branch that 94 % of the warps never take (hot_pixel_fraction <= 1e-3)
-  const bool any_hot = __any_sync(__activemask(), lane_hot);
-  if (NOISE == V2V_NOISE_PHILOX) hot_s[threadIdx.x] = make_float4(hotf[0], hotf[1], hotf[2], hotf[3]);   // own slot: no barrier needed
+  // warp-uniform: the ~6 % of the warps that own a hot pixel (hot_pixel_fraction <= 1e-3) send EVERY interval through
+  // the exact path below, which adds the hot noise there (:49; x + 0.0 == x for everyone else): no hot-pixel code and no
+  // extra branch in the common path.  Below 2*min(pos,neg) at most one threshold is crossed.
+  const bool any_hot = kPh && __any_sync(full, lane_hot);
+  if (kPh) hot_s[threadIdx.x] = make_float4(hotf[0], hotf[1], hotf[2], hotf[3]);   // own slot: no barrier needed
+  const double thr2 = any_hot ? -1.0 : __dadd_rn(fmin(pos, neg), fmin(pos, neg));
 
-  auto step = [&](const uint32_t w, const float (&bnf)[4]) {
+  const uint32_t dir_lane = (threadIdx.x & 7u) * 16u;     // this lane's (= this group's) direction sub-table
+  const double pos2 = __dadd_rn(pos, pos), mneg2 = -__dadd_rn(neg, neg);
+  // Software pipeline of the generator: the radius (lg2, sqrt on the SFU) and the table offset of interval i+1 are
+  // produced while interval i is integrated, so their latency never sits in front of the potential's FP64 chain.
+  // The stream is consumed in the same order as in the generic kernel (two words per interval).
+  float nrad[2] = {0.f, 0.f};
+  uint32_t ndir[2] = {0u, 0u};
+  auto draw_next = [&]() {
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const uint32_t nw = noise_stream_next(gs);
+      nrad[h] = noise_word_radius(nw, nsc);
+      ndir[h] = ((nw >> 17) & 0x7f80u) | dir_lane;
+    }
+  };
+#ifndef V2V_EXP_NOPIPE
+  if (kPh) draw_next();
+#endif
+  auto step = [&](const uint32_t w) {
     float o[4];
+    uint32_t hu[4];
     double x0[4];
     bool rare = false;
+    double rad[2], dirv[4];
+#ifdef V2V_ABL_NOISE
+    if (kPh) { rad[0] = rad[1] = 0.01; dirv[0] = dirv[2] = 0.5; dirv[1] = dirv[3] = -0.25; }
+    if (false) {
+#else
+    if (kPh) {      // the four noise values of this interval from the two words drawn one interval ago, then the next draw
+#endif
+#pragma unroll
+#ifdef V2V_EXP_NOPIPE
+      draw_next();
+#endif
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        rad[h] = static_cast<double>(nrad[h]);
+        asm("ld.shared.v2.f64 {%0, %1}, [%2+%3];" : "=d"(dirv[2 * h]), "=d"(dirv[2 * h + 1]) : "r"(ndir[h]), "n"(kSmemWindowBase + L::dir));
+      }
+#ifndef V2V_EXP_NOPIPE
+      draw_next();
+#endif
+    }
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-      const double L = lut_at(byte_of(w, k));
-      double x = __dadd_rn(pot[k], __dsub_rn(L, lprev[k]));          // :42-43
-      lprev[k] = L;
-      if (NOISE == V2V_NOISE_PHILOX) x = __dadd_rn(x, static_cast<double>(bnf[k]));   // :46-48
+      const double Lk = lut_at(w, k);
+      double x = __dadd_rn(pot[k], __dsub_rn(Lk, lprev[k]));          // :42-43
+      lprev[k] = Lk;
+      if (kPh) x = __fma_rn(rad[k >> 1], dirv[k], x);                 // :46-48: the product is exact, one rounding
       x0[k] = x;
-    }
-    if (NOISE == V2V_NOISE_PHILOX && any_hot) {                       // :49; x + 0.0 == x: skipped by the warps without a hot pixel
-      asm volatile("" ::: "memory");                                  // keep this a (warp-uniform) branch
-      const float4 h = hot_s[threadIdx.x];
-      x0[0] = __dadd_rn(x0[0], static_cast<double>(h.x));
-      x0[1] = __dadd_rn(x0[1], static_cast<double>(h.y));
-      x0[2] = __dadd_rn(x0[2], static_cast<double>(h.z));
-      x0[3] = __dadd_rn(x0[3], static_cast<double>(h.w));
     }
     {   // trigger of the exact multi-threshold path: four FP64 compares chained through one predicate (no ALU-pipe work)
       unsigned int r;
@@ -213,28 +288,62 @@ __global__ void __launch_bounds__(kFastThreads, CTAS) esim_fast_kernel(const Esi
           : "=r"(r)
           : "d"(x0[0]), "d"(x0[1]), "d"(x0[2]), "d"(x0[3]), "d"(thr2));
       rare = r != 0;
+#ifdef V2V_ABL_TRIGGER
+      rare = false;
+#endif
     }
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
       double x = x0[k];
-      if (kFmaCross) single_cross(x, o[k], pos, mneg);
-      else single_cross_sel(x, o[k], pos, mneg, neg);                        // :51-58 with q in {0,1}
+#ifdef V2V_ABL_CROSS
+      o[k] = __int_as_float(__double2hiint(x) & 0x3f800000);
+      pot[k] = x;
+      continue;
+#endif
+#ifdef V2V_SEL_CROSS
+      if (false) single_cross(x, o[k], hu[k], pos, mneg);
+#else
+      if (kPh) single_cross(x, o[k], hu[k], pos, mneg);
+#endif
+      else single_cross_sel(x, o[k], hu[k], pos, mneg, neg);          // :51-58 with q in {0,1}
       pot[k] = x;
     }
-    if (rare) {                                                       // a few % of warp-steps on natural video
+#ifdef V2V_ABL_STATS
+    if (false) {
+#else
+    if (STATS) {            // from the single-crossing words (the exact path below only adds its surplus)
+#endif
+      su += hu[0] + hu[1];
+      su += hu[2] + hu[3];
+      sv += __float_as_uint(o[0]) + __float_as_uint(o[1]);
+      sv += __float_as_uint(o[2]) + __float_as_uint(o[3]);
+    }
+    if (rare) {                 // a multi-threshold crossing somewhere in the warp, or a warp that owns a hot pixel
+      float hk[4] = {0.f, 0.f, 0.f, 0.f};
+      if (any_hot) {
+        const float4 h = hot_s[threadIdx.x];
+        hk[0] = h.x, hk[1] = h.y, hk[2] = h.z, hk[3] = h.w;
+      }
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        if (fabs(x0[k]) >= thr2) {
-          int cnt;
-          pot[k] = multi_cross(x0[k], pos, neg, cta_rcp[0], cta_rcp[1], &cnt);   // conservative trigger: correct for any x
-          o[k] = static_cast<float>(cnt);
+      for (int k = 0; k < 4; ++k) {                                   // the exact conditions, only evaluated in here
+        const double xr = __dadd_rn(x0[k], static_cast<double>(hk[k]));                 // :49
+        if (xr >= pos2 || xr <= mneg2 || hk[k] != 0.f) {              // redo this pixel from x: exact for any x
+          const bool down = xr < 0.0;
+          double q;
+          const double an = multi_cross(fabs(xr), down ? neg : pos, cta_rcp[down ? 1 : 0], &q);
+          pot[k] = down ? -an : an;
+          o[k] = static_cast<float>(down ? -q : q);
+          if (STATS) {          // replace what the common path counted for this pixel (from x without the hot noise)
+            const int qi = static_cast<int>(q);
+            xpos += static_cast<unsigned int>((down ? 0 : qi) - (x0[k] >= pos ? 1 : 0));
+            xneg += static_cast<unsigned int>((down ? qi : 0) - (x0[k] <= mneg ? 1 : 0));
+          }
         }
       }
     }
-    if (STATS) {            // from the final counts; float sums are exact while below 2^24 (flushed every kFlushTrips trips)
-      net += (o[0] + o[1]) + (o[2] + o[3]);
-      tot += (fabsf(o[0]) + fabsf(o[1])) + (fabsf(o[2]) + fabsf(o[3]));
-    }
+#ifdef V2V_ABL_MEM
+    if (a.T < 0)
+#endif
     st_stream_f32x4(vox, o[0], o[1], o[2], o[3]);
     vox += a.plane_stride;
     if (FRAMES) {                                                     // data/v2v_datasets.py:329-338,352
@@ -255,58 +364,70 @@ __global__ void __launch_bounds__(kFastThreads, CTAS) esim_fast_kernel(const Esi
     for (int u = 0; u < kPF; ++u) cur[u] = ld_stream_u32(frame_ptr(1 + u));
   }
   int i = 1;
-  const float zero4[4] = {0.f, 0.f, 0.f, 0.f};
   for (int t = 0; t < trips; ++t) {
     if (t + 1 < trips) {
 #pragma unroll
       for (int u = 0; u < kPF; ++u) nxt[u] = ld_stream_u32(frame_ptr(i + kPF + u));
     }
-    if (NOISE == V2V_NOISE_PHILOX) {
-      // intervals i-1 .. i+2 = 4t .. 4t+3: two draws of the group's stream, 8 normals each
-      float e0[4], o0[4], e1[4], o1[4];
-      stream_noise8(gs, nc2, trig_s, e0, o0);
-      step(cur[0], e0);
-      step(cur[1], o0);
-      stream_noise8(gs, nc2, trig_s, e1, o1);
-      step(cur[2], e1);
-      step(cur[3], o1);
-    } else {
 #pragma unroll
-      for (int u = 0; u < kPF; ++u) step(cur[u], zero4);
-    }
+    for (int u = 0; u < kPF; ++u) step(cur[u]);
     i += kPF;
 #pragma unroll
     for (int u = 0; u < kPF; ++u) cur[u] = nxt[u];
     if (STATS && (t & (kFlushTrips - 1)) == kFlushTrips - 1) flush_stats();
   }
-  {
-    float tev[4] = {0.f, 0.f, 0.f, 0.f}, tod[4] = {0.f, 0.f, 0.f, 0.f};
-    for (; i < N; ++i) {                                              // ragged tail (< kPF intervals; starts at an even interval)
-      float bn1[4] = {0.f, 0.f, 0.f, 0.f};
-      if (NOISE == V2V_NOISE_PHILOX) {
-        if (((i - 1) & 1) == 0) stream_noise8(gs, nc2, trig_s, tev, tod);
-#pragma unroll
-        for (int k = 0; k < 4; ++k) bn1[k] = ((i - 1) & 1) ? tod[k] : tev[k];
-      }
-      step(ld_stream_u32(frame_ptr(i)), bn1);
-    }
-  }
+  for (; i < N; ++i) step(ld_stream_u32(frame_ptr(i)));               // ragged tail (< kPF intervals)
 
   if (d.potential_out) {
 #pragma unroll
     for (int k = 0; k < 4; ++k) d.potential_out[clip_pix + k] = pot[k];
   }
   if (STATS) {
-    // One pair of global reductions per warp, no CTA barrier and no shared-memory stage: a warp that is done leaves, and the
-    // kernel needs 94 instead of 114 registers (5 resident CTAs per SM instead of 4: -9 % on the Philox variant).  153 k
-    // fire-and-forget REDs per 32-clip launch on 64 addresses are invisible next to 2 ms of work.
+    // One pair of global reductions per warp, no CTA barrier and no shared-memory stage: a warp that is done leaves.
     flush_stats();
-    if ((threadIdx.x & 31) == (__ffs(__activemask()) - 1)) {
+    if ((threadIdx.x & 31) == (__ffs(full) - 1)) {
       if (wpos) atomicAdd(reinterpret_cast<unsigned long long*>(d.stats + 2 * blockIdx.y), static_cast<unsigned long long>(wpos));
       if (wneg) atomicAdd(reinterpret_cast<unsigned long long*>(d.stats + 2 * blockIdx.y) + 1, static_cast<unsigned long long>(wneg));
     }
   }
   }  // valid
+}
+
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a per-device attribute of each instantiation: set it on the first
+// launch on a device, not on every launch.
+template <int NOISE, bool FRAMES, bool STATS, bool GATHER, int THREADS, int CTAS>
+int launch_variant(const EsimArgs& a, cudaStream_t s) {
+  using L = FastSmem<NOISE, FRAMES, GATHER, THREADS>;
+  static std::atomic<uint64_t> configured{0};
+  int dev = 0;
+  V2V_CUDA(cudaGetDevice(&dev));
+  const uint64_t bit = 1ull << (dev & 63);
+  const size_t smem = L::bytes(a.d.N);
+  if (!(configured.load(std::memory_order_acquire) & bit)) {
+    V2V_CUDA(cudaFuncSetAttribute(esim_fast_kernel<NOISE, FRAMES, STATS, GATHER, THREADS, CTAS>,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    configured.fetch_or(bit, std::memory_order_release);
+  }
+  const int64_t groups = a.HW / 4;
+  dim3 grid(static_cast<unsigned int>((groups + THREADS - 1) / THREADS), static_cast<unsigned int>(a.d.B));
+  esim_fast_kernel<NOISE, FRAMES, STATS, GATHER, THREADS, CTAS><<<grid, THREADS, smem, s>>>(a);
+  count_launch();
+  V2V_CUDA(cudaGetLastError());
+  return V2V_OK;
+}
+
+template <int NOISE, int THREADS, int CTAS>
+int launch_geom(const EsimArgs& a, cudaStream_t s) {
+  const bool fr = a.d.frame_out_mode != 0, st = a.d.stats != nullptr, ga = a.d.frame_index != nullptr;
+#define V2V_V(FR, ST, GA) return launch_variant<NOISE, FR, ST, GA, THREADS, CTAS>(a, s)
+  if (fr) {
+    if (st) { if (ga) V2V_V(true, true, true); else V2V_V(true, true, false); }
+    else    { if (ga) V2V_V(true, false, true); else V2V_V(true, false, false); }
+  } else {
+    if (st) { if (ga) V2V_V(false, true, true); else V2V_V(false, true, false); }
+    else    { if (ga) V2V_V(false, false, true); else V2V_V(false, false, false); }
+  }
+#undef V2V_V
 }
 
 }  // namespace
@@ -316,43 +437,29 @@ bool esim_fast_eligible(const EsimArgs& a) {
   if (d.frames_per_bin != 1 || d.threshold_mode != V2V_THRES_PER_CLIP) return false;
   if (d.noise_mode == V2V_NOISE_EXPLICIT) return false;
   if (d.noise_mode == V2V_NOISE_PHILOX && d.put_noise_external) return false;
-  if (d.N > 16384) return false;          // the per-clip frame-number table lives in shared memory
+  if (d.N > 16384) return false;               // the per-clip frame-number table lives in shared memory
+  if (a.HW >= (1ll << 32)) return false;       // 32-bit plane size in the frame address multiply
   return true;
 }
 
+// Geometry (threads per CTA, CTAs per SM) per variant from same-box sweeps on B200 (profiles/r02_esim_geom_sweep.txt);
+// bits 8..11 of v2v_esim_desc.kernel_flags select another one for tuning.
 int launch_esim_fast(const EsimArgs& a, cudaStream_t s) {
-  const int64_t groups = a.HW / 4;
-  dim3 grid(static_cast<unsigned int>((groups + kFastThreads - 1) / kFastThreads), static_cast<unsigned int>(a.d.B));
-  const bool ph = a.d.noise_mode == V2V_NOISE_PHILOX, fr = a.d.frame_out_mode != 0, st = a.d.stats != nullptr;
-  // resident CTAs per SM the register allocator must allow (4 -> 128 regs, 6 -> 80, 8 -> 64), chosen per
-  // variant from same-box sweeps on B200 (profiles/r01_esim_minb_sweep.txt); V2V_ESIM_CTAS overrides for tuning.
-  // (Philox without statistics needs 96 registers: 5 CTAs are resident under the 4-CTA bound.)
-  int ctas = ph ? (st ? 6 : 4) : 8;
-  if (const char* e = getenv("V2V_ESIM_CTAS")) ctas = atoi(e);
-  const size_t smem = 256 * kLutCopies * sizeof(double) + (ph ? kTrigEntries * sizeof(float2) : 0) + static_cast<size_t>(a.d.N) * sizeof(int);
-#define V2V_G(NM, FR, ST, CT)                                                                                     \
-  do {                                                                                                            \
-    V2V_CUDA(cudaFuncSetAttribute(esim_fast_kernel<NM, FR, ST, CT>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem))); \
-    esim_fast_kernel<NM, FR, ST, CT><<<grid, kFastThreads, smem, s>>>(a);                                        \
-  } while (0)
-#define V2V_F(NM, FR, ST)                       \
-  do {                                          \
-    if (ctas <= 4) V2V_G(NM, FR, ST, 4);        \
-    else if (ctas <= 7) V2V_G(NM, FR, ST, 6);   \
-    else V2V_G(NM, FR, ST, 8);                  \
-  } while (0)
-  if (ph) {
-    if (fr) { if (st) V2V_F(V2V_NOISE_PHILOX, true, true); else V2V_F(V2V_NOISE_PHILOX, true, false); }
-    else    { if (st) V2V_F(V2V_NOISE_PHILOX, false, true); else V2V_F(V2V_NOISE_PHILOX, false, false); }
-  } else {
-    if (fr) { if (st) V2V_F(V2V_NOISE_NONE, true, true); else V2V_F(V2V_NOISE_NONE, true, false); }
-    else    { if (st) V2V_F(V2V_NOISE_NONE, false, true); else V2V_F(V2V_NOISE_NONE, false, false); }
+  const int geom = (a.d.kernel_flags >> 8) & 0xf;
+  if (a.d.noise_mode == V2V_NOISE_PHILOX) {
+    switch (geom) {
+      case 1: return launch_geom<V2V_NOISE_PHILOX, 512, 2>(a, s);
+      case 2: return launch_geom<V2V_NOISE_PHILOX, 320, 2>(a, s);
+      case 3: return launch_geom<V2V_NOISE_PHILOX, 768, 1>(a, s);
+      default: return launch_geom<V2V_NOISE_PHILOX, 384, 2>(a, s);
+    }
   }
-#undef V2V_F
-#undef V2V_G
-  count_launch();
-  V2V_CUDA(cudaGetLastError());
-  return V2V_OK;
+  switch (geom) {
+    case 1: return launch_geom<V2V_NOISE_NONE, 320, 3>(a, s);
+    case 2: return launch_geom<V2V_NOISE_NONE, 256, 3>(a, s);
+    case 3: return launch_geom<V2V_NOISE_NONE, 384, 2>(a, s);
+    default: return launch_geom<V2V_NOISE_NONE, 512, 2>(a, s);
+  }
 }
 
 }  // namespace v2v

@@ -408,7 +408,7 @@ extern "C" int v2v_v2e_frames_to_voxel(const v2v_v2e_desc* desc, void* stream) {
   if (d.noise_mode == V2V_NOISE_PHILOX && d.shot_noise_rate_hz > 0.0)
     V2V_REQUIRE(d.shot_pos_scale && d.shot_neg_scale, V2V_ERR_INVALID_ARG, "PHILOX shot noise needs the scales from v2v_v2e_shot_scales");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  if (v2e_fast_eligible(a) && !getenv("V2V_V2E_GENERIC")) return launch_v2e_fast(a, s);
+  if (v2e_fast_eligible(a) && !(d.kernel_flags & V2V_V2E_FLAG_GENERIC)) return launch_v2e_fast(a, s);
   const bool vec4 = (a.HW % 4 == 0) && aligned(d.frames, 4) && aligned(d.voxel, 16) &&
                     static_cast<int64_t>(d.B) * a.HW >= 148LL * 2048;
   const int P = vec4 ? 4 : 1;

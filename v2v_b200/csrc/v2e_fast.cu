@@ -411,7 +411,7 @@ bool v2e_fast_eligible(const V2eArgs& a) {
   if (d.N - 1 > kMaxIntervals) return false;
   const bool sh = d.shot_noise_rate_hz > 0.0 && d.noise_mode != V2V_NOISE_NONE;
   if (d.state_f32 && sh) return false;          // float32 state with shot noise: two float32 roundings per update, generic kernel
-  if (getenv("V2V_V2E_FAST")) return true;      // tests: force the fast kernel on small shapes
+  if (d.kernel_flags & V2V_V2E_FLAG_FAST) return true;      // tests: force the fast kernel on small shapes
   return static_cast<int64_t>(d.B) * a.HW >= 148LL * 2048;
 }
 
@@ -423,8 +423,7 @@ int launch_v2e_fast(const V2eArgs& a, cudaStream_t s) {
   const bool cut = d.cutoff_hz > 0.0, lk = d.leak_rate_hz > 0.0, sh = d.shot_noise_rate_hz > 0.0 && ph;
   const bool leak_variant = !d.state_f32 && (lk || !cut);      // the template's LEAK (a float64 state without cutoff runs the leak variant)
   // exact division for every pixel (default) or single-crossing fast path + divergent exact path (V2V_V2E_BF=0)
-  const char* e = getenv("V2V_V2E_BF");
-  const bool bf = e ? atoi(e) != 0 : true;
+  const bool bf = !(d.kernel_flags & V2V_V2E_FLAG_DIVERGENT_DIV);
   const size_t smem = fast_smem_bytes(a, leak_variant && ph, bf);
 #define V2V_KB(F32, CU, LK, SH, PH, BFV)                                                                                    \
   do {                                                                                                                      \

@@ -86,14 +86,15 @@ def frames_to_voxel(frames: torch.Tensor, pos_thres, neg_thres, *, num_bins: int
                     seed: int = 0, clip_index_base: int = 0, potential_in=None, return_potential: bool = False,
                     frame_out: Optional[str] = None, with_stats: bool = False, pad_multiple: int = 0,
                     out: Optional[torch.Tensor] = None, lut: Optional[np.ndarray] = None,
-                    stream: Optional[torch.cuda.Stream] = None, frame_index=None, value_map=None) -> EsimOutput:
+                    stream: Optional[torch.cuda.Stream] = None, frame_index=None, value_map=None,
+                    kernel_flags: int = 0) -> EsimOutput:
     """Simulate ``B`` clips in one launch.
 
     frames: CUDA uint8 ``[B,N,H,W]`` (or ``[N,H,W]``).  pos_thres / neg_thres:
     scalar, ``[B]`` (per clip, the ESIM core) or ``[B,H,W]`` (per-pixel maps).
     noise: "none" | "explicit" (u0, hot_noise ``[B,H,W]``, base_gauss
     ``[B,N-1,H,W]`` float64: the reference's random fields) | "philox"
-    (in-kernel generator keyed by ``seed``: Philox4x32-10 root + one xoshiro128++ stream per pixel group; clip ``b`` uses stream
+    (in-kernel generator keyed by ``seed``: Philox4x32-10 root + one 64-bit LCG stream per pixel group; clip ``b`` uses stream
     ``clip_index_base + b``).  ``num_bins*frames_per_bin`` must divide ``N-1``
     (data/v2v_datasets.py:365).  frame_out: None | "frames" (frames
     ``(t+1)*bins*fpb``) | "frames+first" (``t*bins*fpb``, t<=T;
@@ -105,6 +106,9 @@ def frames_to_voxel(frames: torch.Tensor, pos_thres, neg_thres, *, num_bins: int
     frame ``n`` of clip ``b`` the raw frame ``frames[b, frame_index[b,n]]`` (the dataset's pause gather; ``frames`` is
     then the raw stack ``[B,M,H,W]``); ``value_map`` uint8 ``[B,256]`` is applied to every pixel before the simulation and
     the ``frame_out`` (``degrade_value_map`` builds the HDR/LDR degrade).
+
+    ``kernel_flags``: ``_lib.ESIM_FLAG_*`` (explicit kernel selection for tests and tuning sweeps; results never depend
+    on it).  ``stream``: the launch and every allocation / conversion it depends on are ordered on that stream.
     """
     if frames.dim() == 3:
         frames = frames.unsqueeze(0)
@@ -218,8 +222,11 @@ def frames_to_voxel(frames: torch.Tensor, pos_thres, neg_thres, *, num_bins: int
     d.voxel_row_stride, d.voxel_plane_stride = Wp, Hp * Wp
     d.frame_out, d.stats = _ptr(fr_t), _ptr(stats_t)
     d.frame_index, d.raw_frames_per_clip, d.value_map = _ptr(fidx_t), (M if fidx_t is not None else 0), _ptr(vmap_t)
+    d.kernel_flags = int(kernel_flags) | _env_kernel_flags()
 
     s = stream if stream is not None else torch.cuda.current_stream(dev)
+    if stream is not None:       # conversions, zero fills and H2D copies above were enqueued on the current stream
+        stream.wait_stream(torch.cuda.current_stream(dev))
     with torch.cuda.device(dev):
         _lib.check(_lib.load().v2v_esim_frames_to_voxel(C.byref(d), C.c_void_p(s.cuda_stream)))
     if stream is not None:       # tensors created on the current stream but consumed on `stream`
@@ -229,6 +236,17 @@ def frames_to_voxel(frames: torch.Tensor, pos_thres, neg_thres, *, num_bins: int
     vox = store[..., :H, :W] if (Hp, Wp) != (H, W) else store
     return EsimOutput(voxel=vox, frames=fr_t, stats=stats_t, potential=pout_t,
                       padded=store if (Hp, Wp) != (H, W) else None)
+
+
+def _env_kernel_flags() -> int:
+    """Tuning knobs of the sweep tools (read here, in the Python host, per call; the C library reads no environment)."""
+    f = 0
+    g = os.environ.get("V2V_ESIM_GEOM")
+    if g:
+        f |= _lib.esim_flag_geom(int(g))
+    if os.environ.get("V2V_ESIM_GENERIC") == "1":
+        f |= _lib.ESIM_FLAG_GENERIC
+    return f
 
 
 def philox_fields(n_frames: int, height: int, width: int, *, base_noise_std, hot_pixel_fraction, hot_pixel_std,

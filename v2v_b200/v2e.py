@@ -15,8 +15,23 @@ from typing import Optional
 import numpy as np
 import torch
 
+import os
+
 from . import _lib
 from .esim import _as_dev, _ptr
+
+
+def _env_kernel_flags() -> int:
+    """Kernel-selection knobs of the tests and sweep tools (read in the Python host, per call; the C library reads no
+    environment): V2V_V2E_GENERIC=1, V2V_V2E_FAST=1, V2V_V2E_BF=0."""
+    f = 0
+    if os.environ.get("V2V_V2E_GENERIC"):
+        f |= _lib.V2E_FLAG_GENERIC
+    if os.environ.get("V2V_V2E_FAST"):
+        f |= _lib.V2E_FLAG_FAST
+    if os.environ.get("V2V_V2E_BF", "1") == "0":
+        f |= _lib.V2E_FLAG_DIVERGENT_DIV
+    return f
 
 _NOISE = {"none": _lib.NOISE_NONE, "explicit": _lib.NOISE_EXPLICIT, "philox": _lib.NOISE_PHILOX}
 TIME_INVARIANT_MODELS = ("pn_related", "spatial_independent")
@@ -116,6 +131,7 @@ def frames_to_voxel_v2e(frames: torch.Tensor, pos_thres, neg_thres, *, fps: floa
     d.seed, d.clip_index_base = int(seed) & 0xFFFFFFFFFFFFFFFF, int(clip_index_base)
     d.voxel, d.stats = _ptr(vox), _ptr(stats_t)
     d.frame_index, d.raw_frames_per_clip, d.value_map = _ptr(fidx_t), (M if fidx_t is not None else 0), _ptr(vmap_t)
+    d.kernel_flags = _env_kernel_flags()
     s = torch.cuda.current_stream(dev)
     lib = _lib.load()
     scales = None
