@@ -67,8 +67,27 @@ def ncu_traffic():
 # CPU baseline: NumPy port of the reference's ESIM core (oracle/), one clip per worker process
 # ----------------------------------------------------------------------------------------------
 
+def find_reference():
+    """The reference checkout, if this machine has one (the build container does, the GPU box does not): $V2V_REFERENCE,
+    baseline/_ref, /root/reference.  Returns its path or None."""
+    for p in (os.environ.get("V2V_REFERENCE"), os.path.join(ROOT, "baseline", "_ref"), "/root/reference"):
+        if p and os.path.isfile(os.path.join(p, "data", "v2v_core_esim.py")):
+            return p
+    return None
+
+
+def _reference_emulator(ref):
+    """data/v2v_core_esim.py imports only numpy: load the reference's own EventEmulator from its file."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("_ref_v2v_core_esim", os.path.join(ref, "data", "v2v_core_esim.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod.EventEmulator
+
+
 def _cpu_clip_job(args):
-    seed, n_frames, h, w = args
+    seed, n_frames, h, w = args[:4]
+    ref = args[4] if len(args) > 4 else None
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import v2v_oracle as orc
     g = np.random.Generator(np.random.PCG64(seed))
@@ -82,17 +101,24 @@ def _cpu_clip_job(args):
                                TRAIN_CFG["hot_pixel_std_range"])
     t0 = time.perf_counter()
     # the timed part is what the reference's imgs_to_voxels does: draws + simulation + binning + float32 cast
-    u0, hot, gs = orc.esim_draw_randomness(n_frames, h, w, p["hot_pixel_fraction"], p["hot_pixel_std"], rs)
-    iv = orc.esim_video_to_voxel(vid, p["pos_thres"], p["neg_thres"], p["base_noise_std"], u0, hot, gs, False)
-    vox = orc.bin_accumulate(iv, BINS, FPB).astype(np.float32)
+    if ref is not None:           # the reference's own code (data/v2v_core_esim.py:26-69, data/v2v_datasets.py:388-400)
+        np.random.seed(seed)
+        iv = _reference_emulator(ref)(pos_thres=p["pos_thres"], neg_thres=p["neg_thres"], base_noise_std=p["base_noise_std"],
+                                      hot_pixel_fraction=p["hot_pixel_fraction"], hot_pixel_std=p["hot_pixel_std"],
+                                      put_noise_external=False, seed=None).video_to_voxel(vid)
+        vox = iv.reshape(((n_frames - 1) // (BINS * FPB), BINS, FPB, h, w)).sum(axis=2).astype(np.float32)
+    else:
+        u0, hot, gs = orc.esim_draw_randomness(n_frames, h, w, p["hot_pixel_fraction"], p["hot_pixel_std"], rs)
+        iv = orc.esim_video_to_voxel(vid, p["pos_thres"], p["neg_thres"], p["base_noise_std"], u0, hot, gs, False)
+        vox = orc.bin_accumulate(iv, BINS, FPB).astype(np.float32)
     dt = time.perf_counter() - t0
     return dt, float(np.abs(vox).sum())
 
 
-def cpu_reference_run(n_frames, clips, procs):
+def cpu_reference_run(n_frames, clips, procs, ref=None):
     """Simulate `clips` clips of [n_frames,H,W] on `procs` processes; returns wall seconds."""
     import multiprocessing as mp
-    jobs = [(1000 + i, n_frames, H, W) for i in range(clips)]
+    jobs = [(1000 + i, n_frames, H, W, ref) for i in range(clips)]
     t0 = time.perf_counter()
     if procs == 1:
         res = [_cpu_clip_job(j) for j in jobs]
@@ -105,45 +131,68 @@ def cpu_reference_run(n_frames, clips, procs):
     return wall, res
 
 
+CPU_IMPL = {None: "NumPy oracle port of data/v2v_core_esim.py (oracle/v2v_oracle.py; bit-identical to the reference by "
+                  "tests/golden/make_golden.py) incl. MT19937 noise draws, binning, float32 cast"}
+
+
+def cpu_impl_name(ref):
+    return CPU_IMPL[None] if ref is None else (f"the reference's own EventEmulator.video_to_voxel ({ref}/data/v2v_core_esim.py) "
+                                               "+ the bin sum and float32 cast of data/v2v_datasets.py:399-400,340-349")
+
+
 def cpu_baseline(cores):
-    n_frames = 41                                                   # bounded sample: 1/3-length clips
-    wall, _ = cpu_reference_run(n_frames, cores, cores)
+    ref = find_reference()
+    n_frames = N_FRAMES                                             # full config-2 clips, one per host core
+    wall, _ = cpu_reference_run(n_frames, cores, cores, ref)
     pix = cores * (n_frames - 1) * H * W
-    return {"value": pix / wall / 1e6, "unit": "Mpix-frames/s", "cores": cores, "kind": "port",
-            "sample": f"{cores} clips uint8 [{n_frames},{H},{W}] (1/3-length config-2 clips), one per process, "
-                      f"NumPy oracle port of data/v2v_core_esim.py incl. MT19937 noise draws, binning, float32 cast",
+    return {"value": pix / wall / 1e6, "unit": "Mpix-frames/s", "cores": cores, "kind": "reference" if ref else "port",
+            "sample": f"{cores} clips uint8 [{n_frames},{H},{W}] (full config-2 clips), one per process: " + cpu_impl_name(ref),
             "clips_per_s_equiv": pix / wall / PIX_INTERVALS_PER_CLIP, "wall_s": wall}
 
 
 def run_reference_arm(args):
+    """`--impl reference`: the reference's CPU implementation of the same workload on all host cores (rank 0 only).
+    A step is a bounded sample of the workload — full [121,480,640] clips, one per host core — so that K+W steps end
+    within a few minutes; throughput is normalised per pixel-interval, so the sample size does not bias it."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     cores = os.cpu_count() or 1
-    n_frames = 21                                                   # bounded sample per step: 1/6-length clips
-    times = []
+    ref = find_reference()
     import multiprocessing as mp
     jobs_per_step = cores
+    n_frames = N_FRAMES
+    times = []
+    budget_s = float(os.environ.get("V2V_REF_BUDGET_S", "240"))
     with mp.get_context("spawn").Pool(cores) as pool:
-        pool.map(_cpu_clip_job, [(0, 6, 8, 8)] * cores)
-        for s in range(args.warmup + args.steps):
-            jobs = [(5000 + s * jobs_per_step + i, n_frames, H, W) for i in range(jobs_per_step)]
+        pool.map(_cpu_clip_job, [(0, 6, 8, 8, ref)] * cores)
+        # calibrate on one full-length step (it is also the first warm-up step): if K+W such steps would not fit the
+        # budget, keep the clips per step (= cores, the reference's DataLoader-worker parallelism) and shorten the clips
+        t0 = time.perf_counter()
+        pool.map(_cpu_clip_job, [(4000 + i, n_frames, H, W, ref) for i in range(jobs_per_step)])
+        t_full = time.perf_counter() - t0
+        total_steps = max(1, args.warmup - 1) + args.steps
+        if t_full * total_steps > budget_s:
+            n_frames = int(max(BINS * FPB * 2 + 1, ((N_FRAMES - 1) * budget_s / (t_full * total_steps)) // (BINS * FPB) * (BINS * FPB) + 1))
+        for s in range(max(0, args.warmup - 1) + args.steps):
+            jobs = [(5000 + s * jobs_per_step + i, n_frames, H, W, ref) for i in range(jobs_per_step)]
             t0 = time.perf_counter()
             pool.map(_cpu_clip_job, jobs)
-            if s >= args.warmup:
+            if s >= max(0, args.warmup - 1):
                 times.append(time.perf_counter() - t0)
     total = sum(times)
     pix = args.steps * jobs_per_step * (n_frames - 1) * H * W
     val = pix / total / 1e6
+    sample = (f"{args.steps} steps x {jobs_per_step} clips uint8 [{n_frames},{H},{W}]"
+              + ("" if n_frames == N_FRAMES else f" (clips shortened from {N_FRAMES} frames to fit {budget_s:.0f} s)")
+              + ", one clip per host process: " + cpu_impl_name(ref))
     line = {
         "impl": "reference", "metric": "video_to_voxel_throughput", "value": val, "unit": "Mpix-frames/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "clips_per_s": pix / total / PIX_INTERVALS_PER_CLIP,
-        "config": workload_config(jobs_per_step, f"step = {jobs_per_step} clips of [{n_frames},{H},{W}] on {cores} host processes"),
-        "cpu_baseline": {"value": val, "unit": "Mpix-frames/s", "cores": cores, "kind": "port",
-                         "sample": f"{args.steps} steps x {jobs_per_step} clips uint8 [{n_frames},{H},{W}], NumPy oracle "
-                                   "port of the reference ESIM path (the reference is pure Python/NumPy; nothing to compile)"},
+        "config": workload_config(args.clips),
+        "cpu_baseline": {"value": val, "unit": "Mpix-frames/s", "cores": cores, "kind": "reference" if ref else "port", "sample": sample},
         "e2e": {"value": val, "unit": "Mpix-frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -446,6 +495,37 @@ def run_ours(args):
                                          "d2h_bytes_per_step": 16,
                                          "note": "same pipeline without the voxel D2H: what the train loop sees (voxels consumed on the GPU)"}
 
+    if e2e is not None:
+        # what the host link allows: pinned H2D and D2H copies of 1 GiB, best of 3 (PCIe Gen5 x16 on the HGX boards)
+        hb = torch.empty(1 << 30, dtype=torch.uint8).pin_memory()
+        db = torch.empty(1 << 30, dtype=torch.uint8, device=dev)
+        link = {}
+        for name, (dst, src) in (("h2d", (db, hb)), ("d2h", (hb, db))):
+            best = 0.0
+            for _ in range(3):
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                barrier()
+                a.record()
+                dst.copy_(src, non_blocking=True)
+                b.record()
+                torch.cuda.synchronize(dev)
+                best = max(best, (1 << 30) / (a.elapsed_time(b) * 1e-3) / 1e9)
+            link[name + "_gbs"] = best
+        del hb, db
+        per_clip_s = max(N_FRAMES * H * W / (link["h2d_gbs"] * 1e9), T * BINS * H * W * 4 / (link["d2h_gbs"] * 1e9))
+        link["ceiling_clips_per_s_per_gpu"] = 1.0 / per_clip_s
+        link["note"] = ("measured on this rank while all ranks copy at the same time; ceiling = 1 / max(frame bytes / h2d, voxel bytes / d2h) "
+                        "per clip (full duplex): the float32 voxels are 80 % of the bytes")
+        e2e["host_link"] = link
+        e2e["frac_of_host_link_ceiling"] = e2e["clips_per_s"] / world / link["ceiling_clips_per_s_per_gpu"]
+
+    secondary = None
+    if rank == 0 and world == 1 and not args.no_secondary:
+        del out, frames
+        torch.cuda.empty_cache()
+        from tools.bench_configs import secondary_configs
+        secondary = secondary_configs(dev, cpu_arm=not args.no_cpu_baseline)
+
     if rank == 0:
         peak, peak_src = measured_peak()
         total_pix = world * args.steps * B * PIX_INTERVALS_PER_CLIP
@@ -466,6 +546,135 @@ def run_ours(args):
             "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
             "ms_per_step_per_rank": per_rank,
             "event_stats": vdist.stats_dict(job),
+            "secondary": secondary,
+        }
+        print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def run_config5(args):
+    """BASELINE config 5: clip-sharded 1080p 5-bin voxel generation feeding an E2VID forward, 10 k clips on the GPUs of one box.
+    Clip i of the job goes to rank i % world (v2v_b200.dist.shard_indices, the DistributedSampler rule); a step is one
+    batch of clips per GPU: frames [b,26,1080,1920] (a resident pool of synthetic clips, re-used round robin) -> fused
+    kernel writing voxels straight into the /16-padded consumer layout [b,5,5,1088,1920] + ground-truth frames + stats ->
+    E2VID-shaped recurrent U-Net forward over the 5 voxels on the same stream (tools/e2vid_consumer.py, cuDNN).  `--steps`
+    steps are timed per rank (the whole 10 k-clip job is `--c5-clips / (world * --c5-batch)` such steps); one NCCL
+    all-reduce of the statistics vector closes the timed region."""
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    import torch
+    import v2v_b200 as v2v
+    from v2v_b200 import dist as vdist
+    from tools.e2vid_consumer import E2VIDShaped
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=dev)
+            dist.barrier()
+            torch.cuda.synchronize(dev)
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved, 1)
+            os.close(saved)
+    n5, h5, w5, b5 = 26, 1080, 1920, args.c5_batch
+    mine = vdist.shard_indices(args.c5_clips, rank, world)
+    vz = v2v.V2VVoxelizer(TRAIN_CFG, device=dev)
+    params = vz.sample_batch_params(b5, rs=np.random.RandomState(99))
+    g = torch.Generator(device=dev)
+    g.manual_seed(7)
+    pool = torch.empty((2 * b5, n5, h5, w5), dtype=torch.uint8, device=dev)          # resident pool of clips
+    for b in range(2 * b5):
+        base = torch.randint(0, 256, (h5, w5), generator=g, device=dev, dtype=torch.int16)
+        st = torch.randint(-6, 7, (n5, h5, w5), generator=g, device=dev, dtype=torch.int16)
+        st[0] = 0
+        pool[b] = (base[None] + torch.cumsum(st, 0)).clamp_(0, 255).to(torch.uint8)
+    store = torch.zeros((b5, 5, 5, 1088, 1920), dtype=torch.float32, device=dev)     # pads written once, here
+    net = E2VIDShaped().to(dev).eval()
+    stats_total = torch.zeros(2, dtype=torch.int64, device=dev)
+
+    def sim(i):
+        fr = pool[(i % 2) * b5:(i % 2 + 1) * b5]
+        return vz.batch_to_tensors(fr, params, seed=args.seed, clip_index_base=mine[(i * b5) % max(len(mine), 1)] if mine else 0,
+                                   pad_multiple=16, with_stats=True, out=store)
+
+    def step(i, with_model=True):
+        o = sim(i)
+        stats_total.add_(o["stats"].sum(dim=0))
+        if with_model:
+            return net.forward_sequence(o["events_padded"])
+        return None
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def timed(k, with_model):
+        barrier()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for i in range(k):
+            step(i, with_model)
+        b.record()
+        barrier()
+        ms = a.elapsed_time(b)
+        if dist is not None:
+            t = torch.tensor([ms], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms
+
+    for i in range(max(3, args.warmup)):
+        step(i)
+    sampler = ClockSampler(local, args.clock_period)
+    if rank == 0:
+        sampler.start()
+    stats_total.zero_()
+    t0 = time.perf_counter()
+    ms = timed(args.steps, True)
+    job = vdist.pack_stats(stats_total.view(1, 2), args.steps * b5 * 25 * h5 * w5, args.steps * b5, device=dev)
+    vdist.allreduce_stats(job)
+    torch.cuda.synchronize(dev)
+    t1 = time.perf_counter()
+    clocks = sampler.stop(t0, t1) if rank == 0 else None
+    ms_sim = timed(args.steps, False)                      # the simulator alone (same launches, no consumer)
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    for i, (a, b) in enumerate(evs):
+        a.record()
+        sim(i)
+        b.record()
+    torch.cuda.synchronize(dev)
+    launch_ms = float(np.median([a.elapsed_time(b) for a, b in evs]))
+    if rank == 0:
+        peak, peak_src = measured_peak()
+        by = b5 * h5 * w5 * (n5 + 25 * 4 + 5 * 4)          # frames in, voxels out, ground-truth frames out
+        clips_s = world * args.steps * b5 / (ms * 1e-3)
+        line = {
+            "metric": "video_to_voxel_throughput", "value": world * args.steps * b5 * 25 * h5 * w5 / (ms * 1e-3) / 1e6, "unit": "Mpix-frames/s",
+            "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64 (simulator) / f32 (consumer)", "data": "synthetic",
+            "config": {"workload": "BASELINE config 5: clip-sharded 1080p 5-bin voxel generation feeding an E2VID-shaped forward "
+                                   f"({args.c5_clips} clips sharded rank::world; clips uint8 [26,1080,1920] -> 5 voxels of 5 bins in the /16-padded "
+                                   "layout [5,5,1088,1920] + 5 ground-truth frames + statistics, in-kernel Philox noise, then the recurrent U-Net "
+                                   "forward over the 5 voxels, cuDNN)",
+                       "clips_per_step_per_gpu": b5, "frames": n5, "height": h5, "width": w5, "num_bins": 5, "job_clips": args.c5_clips,
+                       "job_steps_per_gpu": -(-len(mine) // b5), "l2": "each step moves 1.3 GB of frames and voxels (> 126 MB L2)"},
+            "clips_per_s": clips_s, "job_seconds_estimate": args.c5_clips / clips_s,
+            "simulator_only": {"ms_per_step": ms_sim / args.steps, "clips_per_s": world * args.steps * b5 / (ms_sim * 1e-3),
+                               "share_of_step": ms_sim / ms},
+            "roofline": {"bound": "hbm", "achieved": by / (launch_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                         "frac": by / (launch_ms * 1e-3) / 1e9 / peak, "traffic": None, "peak_source": peak_src,
+                         "kernel": "esim_fast_kernel<PHILOX, frames, stats> (v2v_b200/csrc/esim_fast.cu)", "launch_ms": launch_ms,
+                         "algorithmic_bytes_per_launch": by},
+            "gpu_launches": args.steps, "clocks": clocks, "event_stats": vdist.stats_dict(job),
         }
         print(json.dumps(line))
     if dist is not None:
@@ -484,6 +693,11 @@ def main():
     ap.add_argument("--e2e-chunk", type=int, default=2)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the secondary block (BASELINE configs 1, 3, 4, 5-shape, train batch)")
+    ap.add_argument("--config", default="c2", choices=["c2", "c5"],
+                    help="c2: BASELINE config 2 (the headline); c5: config 5, clip-sharded 1080p voxel generation feeding an E2VID-shaped forward")
+    ap.add_argument("--c5-clips", type=int, default=10000, help="config 5: clips of the whole job (sharded rank::world)")
+    ap.add_argument("--c5-batch", type=int, default=4, help="config 5: clips per step per GPU")
     ap.add_argument("--no-graph", action="store_true", help="launch every timed step from Python instead of replaying CUDA graphs")
     ap.add_argument("--graph-steps", type=int, default=100)
     ap.add_argument("--no-clocks", action="store_true", help="(experiments) do not sample clocks during the timed region")
@@ -492,6 +706,8 @@ def main():
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":
         run_reference_arm(args)
+    elif args.config == "c5":
+        run_config5(args)
     else:
         run_ours(args)
 

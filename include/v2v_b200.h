@@ -283,6 +283,21 @@ int v2v_bgr_to_gray(const uint8_t* img, int32_t channels, uint8_t* gray, int64_t
 
 int v2v_voxel_add_map(float* voxel, int64_t planes, int64_t hw, const double* map, void* stream);
 
+/* ======================================================================= *
+ * 7. Consumer side of the voxel tensor
+ *    replaces  normalize_batch_voxel                 model/train_utils.py:147-166
+ *              per-bin |count| sums of the statistics vector
+ * ======================================================================= */
+/* sums[b] += sum over g, e of |voxel[g, b, e]| for a contiguous float32 [groups, bins, plane_elems] batch (float64
+ * accumulation: exact for integer-valued voxels).  `sums` [bins] device float64, accumulated into (zero it first). */
+int v2v_voxel_bin_abs_sums(const float* voxel, int64_t groups, int32_t bins, int64_t plane_elems, double* sums, void* stream);
+/* hist[c, v + 255] += number of elements of clip c equal to the integer v, |v| <= 255; hist[c, 511] += number of elements
+ * that are not such integers.  `hist` [clips, 512] device int64, accumulated into.  One read of the voxel batch: the
+ * order statistics of normalize_batch_voxel (kthvalue at 1 % / 99 %) follow exactly from it when hist[c, 511] == 0. */
+int v2v_voxel_value_hist(const float* voxel, int32_t clips, int64_t elems_per_clip, long long* hist, void* stream);
+/* In place: voxel[c, e] = voxel > 0 ? voxel / pos_max[c] : voxel / neg_max[c]  (float32 division, :165). */
+int v2v_voxel_normalize(float* voxel, int32_t clips, int64_t elems_per_clip, const float* pos_max, const float* neg_max, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -36,9 +36,16 @@ def _worker(rank, world, port, n_clips, q):
     mine = vd.shard_indices(n_clips, rank, world)
     # fake per-clip statistics that depend on the global clip index only
     stats = torch.tensor([[3 * i + 1, 2 * i] for i in mine], dtype=torch.int64).reshape(-1, 2)
-    vec = vd.pack_stats(stats, pixel_intervals=100 * len(mine), clips=len(mine))
+    # the full vector of SURVEY §8(e): totals, per-bin |count| sums, per-pixel event-count map
+    bins = torch.tensor([float(sum(mine)) * (b + 1) for b in range(5)], dtype=torch.float64)
+    cmap = torch.full((3, 4), len(mine), dtype=torch.int64)
+    vec = vd.pack_stats(stats, pixel_intervals=100 * len(mine), clips=len(mine), bin_abs_sums=bins, count_map=cmap)
+    assert vec.numel() == 4 + 5 + 12
     vd.allreduce_stats(vec)
-    q.put((rank, vd.stats_dict(vec)))
+    u = vd.unpack_stats(vec, num_bins=5, map_shape=(3, 4))
+    d = vd.stats_dict(vec)
+    d["bin_abs_sums"], d["count_map"] = u["bin_abs_sums"].tolist(), u["count_map"].tolist()
+    q.put((rank, d))
     dist.destroy_process_group()
 
 
@@ -55,7 +62,8 @@ def test_allreduce_stats_gloo_world2():
         p.join(timeout=60)
         assert p.exitcode == 0
     expect = {"positive_events": sum(3 * i + 1 for i in range(n_clips)), "negative_events": sum(2 * i for i in range(n_clips)),
-              "pixel_intervals": 100 * n_clips, "clips": n_clips}
+              "pixel_intervals": 100 * n_clips, "clips": n_clips,
+              "bin_abs_sums": [sum(range(n_clips)) * (b + 1) for b in range(5)], "count_map": [[n_clips] * 4] * 3}
     assert all(d == expect for _, d in out)
 
 

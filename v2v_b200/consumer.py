@@ -1,0 +1,91 @@
+"""Consumer side of the voxel tensor: ``normalize_batch_voxel`` and the per-bin sums of the
+statistics vector, on CUDA float32 voxels.
+
+``normalize_batch_voxel`` mirrors model/train_utils.py:147-166 (same name, argument and result).  The reference finds the
+1 % / 99 % order statistics of every clip with ``torch.kthvalue`` over ``T*C*H*W`` elements; voxels of the frame path are
+small integers, so one histogram pass (``v2v_voxel_value_hist``) gives the same k-th values exactly, and when both come
+out <= 1 — every clip whose event rate is below 1 % per polarity, and every clip whose 99th percentile is a single
+event — the normalisation is the identity and no second pass runs.  Non-integer voxels (external noise, cached voxels
+with Gaussian noise) take the reference's ``torch.kthvalue`` for the order statistics and the same scale kernel.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+
+_K = 255
+
+
+def _p(t):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def voxel_value_hist(voxel: torch.Tensor) -> torch.Tensor:
+    """int64 ``[B, 512]``: counts of the integer values -255..255 per clip (index v+255) and, at index 511, of every other
+    value."""
+    if not voxel.is_cuda or voxel.dtype != torch.float32 or not voxel.is_contiguous():
+        raise _lib.V2VError(-1, "voxel must be a contiguous CUDA float32 tensor (no CPU fallback)")
+    B = voxel.shape[0]
+    hist = torch.zeros((B, 2 * _K + 2), dtype=torch.int64, device=voxel.device)
+    if voxel.numel():
+        with torch.cuda.device(voxel.device):
+            _lib.check(_lib.load().v2v_voxel_value_hist(_p(voxel), B, voxel.numel() // B, _p(hist),
+                                                        C.c_void_p(torch.cuda.current_stream(voxel.device).cuda_stream)))
+    return hist
+
+
+def kth_from_hist(hist_row: np.ndarray, k: int) -> float:
+    """k-th smallest value (1-indexed, like torch.kthvalue) of a clip whose exact histogram over -255..255 is given."""
+    cum = np.cumsum(hist_row[: 2 * _K + 1])
+    return float(int(np.searchsorted(cum, k, side="left")) - _K)
+
+
+def normalize_batch_voxel(voxel: torch.Tensor, inplace: bool = False) -> torch.Tensor:
+    """model/train_utils.py:147-166 on a CUDA float32 ``[B,T,C,H,W]`` batch."""
+    assert len(voxel.shape) == 5
+    if not voxel.is_cuda or voxel.dtype != torch.float32:
+        raise _lib.V2VError(-1, "voxel must be a CUDA float32 tensor (no CPU fallback)")
+    B = voxel.shape[0]
+    v = voxel if voxel.is_contiguous() else voxel.contiguous()
+    n = v.numel() // max(B, 1)
+    max_k, min_k = int(0.99 * n), int(0.01 * n)                     # :153-154
+    if min_k < 1:
+        raise RuntimeError("kthvalue(): selected number k out of range for dimension 1")      # what torch.kthvalue raises
+    hist = voxel_value_hist(v).cpu().numpy()
+    pos_max, neg_max = np.empty(B, dtype=np.float32), np.empty(B, dtype=np.float32)
+    flat = None
+    for b in range(B):
+        if hist[b, 2 * _K + 1] == 0:
+            pos_max[b], neg_max[b] = kth_from_hist(hist[b], max_k), -kth_from_hist(hist[b], min_k)
+        else:                                                        # not integer valued: the reference's own way
+            flat = v.reshape(B, -1) if flat is None else flat
+            pos_max[b] = float(torch.kthvalue(flat[b], max_k).values)
+            neg_max[b] = -float(torch.kthvalue(flat[b], min_k).values)
+    pos_max, neg_max = np.maximum(pos_max, 1), np.maximum(neg_max, 1)       # :161-162
+    if (pos_max == 1).all() and (neg_max == 1).all():
+        return v if inplace else v.clone()                           # x / 1 == x: nothing to do
+    out = v if inplace else v.clone()
+    pm, nm = torch.from_numpy(pos_max).to(v.device), torch.from_numpy(neg_max).to(v.device)
+    with torch.cuda.device(v.device):
+        _lib.check(_lib.load().v2v_voxel_normalize(_p(out), B, n, _p(pm), _p(nm),
+                                                   C.c_void_p(torch.cuda.current_stream(v.device).cuda_stream)))
+    return out
+
+
+def bin_abs_sums(voxel: torch.Tensor) -> torch.Tensor:
+    """float64 ``[bins]``: sum of |voxel| per temporal bin of a CUDA float32 ``[..., bins, H, W]`` batch (exact for
+    integer-valued voxels) — the per-bin event totals of the statistics vector."""
+    if not voxel.is_cuda or voxel.dtype != torch.float32 or not voxel.is_contiguous() or voxel.dim() < 3:
+        raise _lib.V2VError(-1, "voxel must be a contiguous CUDA float32 [..., bins, H, W] tensor")
+    bins, plane = voxel.shape[-3], voxel.shape[-2] * voxel.shape[-1]
+    groups = voxel.numel() // max(bins * plane, 1)
+    sums = torch.zeros(bins, dtype=torch.float64, device=voxel.device)
+    if voxel.numel():
+        with torch.cuda.device(voxel.device):
+            _lib.check(_lib.load().v2v_voxel_bin_abs_sums(_p(voxel), groups, bins, plane, _p(sums),
+                                                          C.c_void_p(torch.cuda.current_stream(voxel.device).cuda_stream)))
+    return sums

@@ -242,3 +242,116 @@ extern "C" int v2v_voxel_add_map(float* voxel, int64_t planes, int64_t hw, const
   V2V_CUDA(cudaGetLastError());
   return V2V_OK;
 }
+
+// ---------------------------------------------------------------------------------------------
+// Consumer-side helpers of the voxel tensor
+//   per-bin |count| sums of a [planes, bins, plane_elems] voxel batch (statistics vector of the all-reduce)
+//   normalize_batch_voxel            model/train_utils.py:147-166
+// ---------------------------------------------------------------------------------------------
+namespace v2v {
+namespace {
+
+constexpr int kHistK = 255;                 // integer voxel values -255..255 are histogrammed exactly
+
+// sums[b] += sum |voxel[g, b, :]| over all groups g: double accumulation (exact for integer-valued voxels), one atomic per CTA
+__global__ void bin_abs_sums_kernel(const float* __restrict__ voxel, int64_t groups, int bins, int64_t plane, double* sums) {
+  const int b = blockIdx.y;
+  double acc = 0.0;
+  const int64_t per_bin = groups * plane;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < per_bin; i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int64_t g = i / plane, e = i - g * plane;
+    acc += fabs(static_cast<double>(voxel[(g * bins + b) * plane + e]));
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  __shared__ double part[8];
+  if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int w = 0; w < static_cast<int>(blockDim.x >> 5); ++w) t += part[w];
+    if (t != 0.0) atomicAdd(sums + b, t);
+  }
+}
+
+// hist[b, v + K] += #elements of clip b equal to the integer v (|v| <= K); hist[b, 2K+1] += #elements that are not
+__global__ void value_hist_kernel(const float* __restrict__ voxel, int64_t per_clip, long long* hist) {
+  __shared__ unsigned int h_s[2 * kHistK + 2];
+  for (int i = threadIdx.x; i < 2 * kHistK + 2; i += blockDim.x) h_s[i] = 0u;
+  __syncthreads();
+  const float* v = voxel + static_cast<int64_t>(blockIdx.y) * per_clip;
+  unsigned int zeros = 0u;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < per_clip; i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const float x = v[i];
+    if (x == 0.f) { ++zeros; continue; }                 // the bulk: counted in a register
+    const float r = rintf(x);
+    const bool ok = r == x && fabsf(x) <= static_cast<float>(kHistK);
+    atomicAdd(&h_s[ok ? static_cast<int>(r) + kHistK : 2 * kHistK + 1], 1u);
+  }
+  zeros = __reduce_add_sync(0xffffffffu, zeros);
+  if ((threadIdx.x & 31) == 0 && zeros) atomicAdd(&h_s[kHistK], zeros);
+  __syncthreads();
+  for (int i = threadIdx.x; i < 2 * kHistK + 2; i += blockDim.x)
+    if (h_s[i]) atomicAdd(reinterpret_cast<unsigned long long*>(hist + static_cast<int64_t>(blockIdx.y) * (2 * kHistK + 2) + i), static_cast<unsigned long long>(h_s[i]));
+}
+
+// norm = where(voxel > 0, voxel / pos_max[b], voxel / neg_max[b]) in float32 (model/train_utils.py:165), in place
+__global__ void normalize_kernel(float* voxel, int64_t per_clip, const float* pos_max, const float* neg_max) {
+  const float pm = pos_max[blockIdx.y], nm = neg_max[blockIdx.y];
+  float* v = voxel + static_cast<int64_t>(blockIdx.y) * per_clip;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < per_clip; i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const float x = v[i];
+    if (x != 0.f) v[i] = x > 0.f ? __fdiv_rn(x, pm) : __fdiv_rn(x, nm);
+  }
+}
+
+}  // namespace
+}  // namespace v2v
+
+extern "C" int v2v_voxel_bin_abs_sums(const float* voxel, int64_t groups, int32_t bins, int64_t plane_elems, double* sums, void* stream) {
+  using namespace v2v;
+  V2V_REQUIRE(groups >= 0 && bins >= 1 && bins <= 65535 && plane_elems >= 0, V2V_ERR_INVALID_ARG, "bad sizes");
+  if (groups == 0 || plane_elems == 0) return V2V_OK;
+  V2V_REQUIRE(voxel && sums, V2V_ERR_INVALID_ARG, "NULL pointer");
+  int64_t blocks = (groups * plane_elems + 256 * 16 - 1) / (256 * 16);
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  if (blocks < 1) blocks = 1;
+  bin_abs_sums_kernel<<<dim3(static_cast<unsigned int>(blocks), static_cast<unsigned int>(bins)), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      voxel, groups, bins, plane_elems, sums);
+  count_launch();
+  V2V_CUDA(cudaGetLastError());
+  return V2V_OK;
+}
+
+extern "C" int v2v_voxel_value_hist(const float* voxel, int32_t clips, int64_t elems_per_clip, long long* hist, void* stream) {
+  using namespace v2v;
+  V2V_REQUIRE(clips >= 0 && clips <= 65535 && elems_per_clip >= 0, V2V_ERR_INVALID_ARG, "bad sizes");
+  if (clips == 0 || elems_per_clip == 0) return V2V_OK;
+  V2V_REQUIRE(voxel && hist, V2V_ERR_INVALID_ARG, "NULL pointer");
+  int64_t blocks = (elems_per_clip + 256 * 32 - 1) / (256 * 32);
+  const int64_t cap = (148 * 16 + clips - 1) / clips;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  value_hist_kernel<<<dim3(static_cast<unsigned int>(blocks), static_cast<unsigned int>(clips)), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      voxel, elems_per_clip, hist);
+  count_launch();
+  V2V_CUDA(cudaGetLastError());
+  return V2V_OK;
+}
+
+extern "C" int v2v_voxel_normalize(float* voxel, int32_t clips, int64_t elems_per_clip, const float* pos_max, const float* neg_max,
+                                   void* stream) {
+  using namespace v2v;
+  V2V_REQUIRE(clips >= 0 && clips <= 65535 && elems_per_clip >= 0, V2V_ERR_INVALID_ARG, "bad sizes");
+  if (clips == 0 || elems_per_clip == 0) return V2V_OK;
+  V2V_REQUIRE(voxel && pos_max && neg_max, V2V_ERR_INVALID_ARG, "NULL pointer");
+  int64_t blocks = (elems_per_clip + 256 * 16 - 1) / (256 * 16);
+  const int64_t cap = (148 * 16 + clips - 1) / clips;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  normalize_kernel<<<dim3(static_cast<unsigned int>(blocks), static_cast<unsigned int>(clips)), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      voxel, elems_per_clip, pos_max, neg_max);
+  count_launch();
+  V2V_CUDA(cudaGetLastError());
+  return V2V_OK;
+}
