@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define V2V_ABI_VERSION 1
+#define V2V_ABI_VERSION 2
 
 /* ---- error codes ------------------------------------------------------- */
 #define V2V_OK 0
@@ -203,7 +203,9 @@ enum v2v_scatter_mode {
 enum v2v_polarity_mode {
   V2V_POL_SIGNED = 0,  /* weight = p (torch modes) or 2p-1 (h5 modes, p in {0,1})          */
   V2V_POL_POS_ONLY = 1,/* weight = 1[p>0]   (events_to_neg_pos_voxel_torch, pos half)      */
-  V2V_POL_NEG_ONLY = 2 /* weight = 1[p<=0]                                                */
+  V2V_POL_NEG_ONLY = 2,/* weight = 1[p<=0]                                                */
+  V2V_POL_SPLIT = 3    /* both of the above in one launch: voxel is [Wn,2,num_bins,H,W], slot 0 = POS_ONLY, slot 1 = NEG_ONLY
+                        * (events_to_neg_pos_voxel_torch; the caller concatenates them to 2B channels, data/dataset.py:331-333) */
 };
 
 typedef struct v2v_scatter_desc {
@@ -221,11 +223,27 @@ typedef struct v2v_scatter_desc {
   const void* ts;
   const void* ps;
   const int64_t* window_offsets; /* [Wn+1] ascending event offsets; window w = [off[w], off[w+1]) */
-  void* voxel;                   /* [Wn,num_bins,H,W]; fully written (zeros where no event) */
+  void* voxel;                   /* [Wn,num_bins,H,W] ([Wn,2,num_bins,H,W] for V2V_POL_SPLIT); fully written (zeros where no event) */
   long long* dropped;            /* [1] += events skipped (out-of-sensor / out-of-range bin), or NULL */
-  void* workspace;               /* optional scratch, >= Wn*((num_bins+2)*8+64) bytes: enables the bin-boundary pre-pass */
+  void* workspace;               /* optional scratch, 16-byte aligned.  >= Wn*((num_bins+2)*8+64) bytes enables the bin-boundary
+                                  * pre-pass; >= v2v_scatter_workspace_bytes(desc) additionally enables the one-visit path of
+                                  * the interpolated mode (counting sort by strip: any event order, 8 bytes per event)          */
   int64_t workspace_bytes;
+  long long* unsorted;           /* [1] += positions where a timestamp decreases inside a window, or NULL = not checked.  The
+                                  * discrete and torch modes need non-decreasing timestamps inside every window (their result is
+                                  * undefined otherwise: check this counter); the interpolated mode on the one-visit path does not */
+  int32_t kernel_flags;          /* 0 = library's choice; V2V_SCATTER_FLAG_* (tests and tuning)                                */
+  int32_t tuning_splits;         /* 0 = library's choice; CTAs sharing one (window, bin, strip) of a few, very large windows   */
+  int32_t tuning_smem_kb;        /* 0 = library's choice; shared-memory budget of one accumulator tile in KB                   */
+  int32_t reserved0;
 } v2v_scatter_desc;
+
+#define V2V_SCATTER_FLAG_RANGES 1        /* interpolated mode: contiguous-range kernel even when the workspace allows the one-visit path */
+#define V2V_SCATTER_FLAG_GENERIC_SCAN 2  /* never take the 16-bit coordinate scan                                                       */
+#define V2V_SCATTER_FLAG_NO_PACKED16 4   /* discrete mode: 32-bit instead of packed 16-bit counters                                      */
+
+/* Bytes of `workspace` that enable every path for this descriptor (sizes and mode are read; pointers are not). */
+int64_t v2v_scatter_workspace_bytes(const v2v_scatter_desc* desc);
 
 int v2v_events_to_voxel(const v2v_scatter_desc* desc, void* stream);
 

@@ -33,7 +33,7 @@ def test_every_declared_symbol_is_exported_and_bound(lib):
     assert set(names) <= exported, sorted(set(names) - exported)
     assert set(names) == set(lib.SYMBOLS), (sorted(set(names) ^ set(lib.SYMBOLS)))
     h = lib.load()
-    assert h.v2v_abi_version() == 1
+    assert h.v2v_abi_version() == 2
     assert h.v2v_launch_count() >= 0
 
 

@@ -83,9 +83,9 @@ def test_windows_vs_oracle(cuda_device, bins, interp):
     ts, xs, ys, ps, off = synth_stream(200_000, h, w, wn, 17, hot_frac=0.01)
     off[5] = off[4]                                   # an empty window
     off = np.sort(off)
-    got, dropped = v2v.voxelize_windows(xs, ys, ts, ps, off, bins, h, w, mode="h5_interp" if interp else "h5_discrete",
-                                        return_dropped=True)
-    assert int(dropped) == 0
+    got, dropped, unsorted = v2v.voxelize_windows(xs, ys, ts, ps, off, bins, h, w, mode="h5_interp" if interp else "h5_discrete",
+                                                  return_dropped=True)
+    assert int(dropped) == 0 and int(unsorted) == 0
     got = got.cpu().numpy()
     for k in range(wn):
         s = slice(off[k], off[k + 1])
@@ -123,7 +123,7 @@ def test_out_of_sensor_events_are_dropped_and_counted(cuda_device):
     xs = np.array([0, 1, 50, 2, 3, 4], dtype=np.int16)
     ys = np.array([0, 1, 1, -1, 3, 40], dtype=np.int16)
     ps = np.ones(6, dtype=np.uint8)
-    v, dropped = v2v.voxelize_windows(xs, ys, ts, ps, [0, 6], 5, 8, 8, return_dropped=True)
+    v, dropped, _ = v2v.voxelize_windows(xs, ys, ts, ps, [0, 6], 5, 8, 8, return_dropped=True)
     assert int(dropped) == 3 and float(v.sum()) == 3.0
 
 
@@ -178,7 +178,7 @@ def test_split_bins_across_ctas(cuda_device, mode):
     base = v2v.voxelize_windows(xs, ys, tsx, ps, [0, ne], 5, h, w, mode=mode).cpu().numpy()
     os.environ["V2V_SCATTER_SPLITS"] = "7"
     try:
-        split, dropped = v2v.voxelize_windows(xs, ys, tsx, ps, [0, ne], 5, h, w, mode=mode, return_dropped=True)
+        split, dropped, _ = v2v.voxelize_windows(xs, ys, tsx, ps, [0, ne], 5, h, w, mode=mode, return_dropped=True)
     finally:
         del os.environ["V2V_SCATTER_SPLITS"]
     assert int(dropped) == 0
@@ -261,3 +261,80 @@ def test_numpy_events_to_voxel_golden(cuda_device):
     assert got.dtype == np.float64 and np.allclose(got, c["ref"], rtol=1e-9, atol=1e-9)
     with pytest.raises(NotImplementedError):
         v2v.events_to_voxel(c["xs"], c["ys"], c["ts"], c["ps"], 5, temporal_bilinear=False)
+
+
+def test_interp_paths_agree_and_take_any_event_order(cuda_device):
+    """The interpolated mode has two kernels: the one-visit path (counting sort by strip; default whenever the workspace
+    is there) and the contiguous-range path.  Both equal the oracle on sorted windows; on a SHUFFLED window the one-visit
+    path still equals the reference (np.add.at does not care about order, data/testh5.py:74-80, as long as the first and
+    the last event stay in place: they define the time axis, :68,76), because every event's bin comes from its own
+    timestamp."""
+    import v2v_b200 as v2v
+    from v2v_b200 import _lib
+    h, w, wn = 260, 346, 9
+    ts, xs, ys, ps, off = synth_stream(120_000, h, w, wn, 5, hot_frac=0.02)
+    a = v2v.voxelize_windows(xs, ys, ts, ps, off, 5, h, w, mode="h5_interp", out_dtype=torch.float64)
+    b = v2v.voxelize_windows(xs, ys, ts, ps, off, 5, h, w, mode="h5_interp", out_dtype=torch.float64,
+                             kernel_flags=_lib.SCATTER_FLAG_RANGES)
+    assert torch.allclose(a, b, rtol=0, atol=2e-6)          # (items of <= 255 records accumulate in 2^-23 units)
+    for k in range(wn):
+        s = slice(off[k], off[k + 1])
+        assert np.allclose(a[k].cpu().numpy(), orc.make_voxel(ts[s], xs[s], ys[s], ps[s], 5, h, w, True), **TOL)
+    # shuffle the interior of every window
+    g = np.random.Generator(np.random.PCG64(1))
+    perm = np.arange(len(ts))
+    for k in range(wn):
+        if off[k + 1] - off[k] > 2:
+            seg = perm[off[k] + 1: off[k + 1] - 1]
+            g.shuffle(seg)
+    tsu, xsu, ysu, psu = ts[perm], xs[perm], ys[perm], ps[perm]
+    u = v2v.voxelize_windows(xsu, ysu, tsu, psu, off, 5, h, w, mode="h5_interp", out_dtype=torch.float64)
+    assert torch.equal(u, a)                                # integer accumulation: independent of the event order
+    for k in (0, 4):
+        s = slice(off[k], off[k + 1])
+        assert np.allclose(u[k].cpu().numpy(), orc.make_voxel(tsu[s], xsu[s], ysu[s], psu[s], 5, h, w, True), **TOL)
+
+
+def test_unsorted_windows_raise_in_contiguous_range_modes(cuda_device):
+    """The discrete and torch modes assign bins as contiguous ranges: unsorted timestamps must not silently mis-bin.
+    The device-side check (default on) raises; a decrease exactly at a window boundary is legitimate."""
+    import v2v_b200 as v2v
+    h, w = 32, 40
+    ts, xs, ys, ps, off = synth_stream(5000, h, w, 4, 9)
+    v2v.voxelize_windows(xs, ys, ts, ps, off, 5, h, w, mode="h5_discrete")             # sorted: fine
+    ts2 = ts.copy()
+    ts2[off[1]:off[2]] -= 10.0                                                        # window 1 starts earlier than window 0 ends
+    v2v.voxelize_windows(xs, ys, ts2, ps, off, 5, h, w, mode="h5_discrete")
+    bad = ts.copy()
+    i = off[2] + 7
+    bad[i], bad[i + 1] = bad[i + 1], bad[i]
+    assert bad[i] != bad[i + 1]
+    for mode in ("h5_discrete", "torch_discrete", "torch_bilinear"):
+        t = bad if mode.startswith("h5") else bad.astype(np.float32)
+        p = ps if mode.startswith("h5") else ps.astype(np.float32) * 2 - 1
+        with pytest.raises(ValueError):
+            v2v.voxelize_windows(xs, ys, t, p, off, 5, h, w, mode=mode)
+        _, _, unsorted = v2v.voxelize_windows(xs, ys, t, p, off, 5, h, w, mode=mode, return_dropped=True)
+        assert int(unsorted) == 1
+    v2v.voxelize_windows(xs, ys, bad, ps, off, 5, h, w, mode="h5_interp")              # any order
+
+
+def test_neg_pos_voxel_single_launch(cuda_device):
+    """events_to_neg_pos_voxel_torch is one launch (V2V_POL_SPLIT) and equals the two one-polarity launches."""
+    import v2v_b200 as v2v
+    g = np.random.Generator(np.random.PCG64(12))
+    ne, h, w = 30_000, 60, 80
+    xs, ys = g.integers(0, w, ne).astype(np.float32), g.integers(0, h, ne).astype(np.float32)
+    ts = np.sort(g.random(ne)).astype(np.float32)
+    ps = ((g.random(ne) < 0.5).astype(np.float32) * 2 - 1)
+    for bil in (True, False):
+        n0 = v2v.launch_count()
+        pos, neg = v2v.events_to_neg_pos_voxel_torch(xs, ys, ts, ps, 5, sensor_size=(h, w), temporal_bilinear=bil)
+        launches = v2v.launch_count() - n0
+        mode = "torch_bilinear" if bil else "torch_discrete"
+        p1 = v2v.voxelize_windows(xs, ys, ts, ps, [0, ne], 5, h, w, mode=mode, polarity="pos")[0]
+        n1 = v2v.voxelize_windows(xs, ys, ts, ps, [0, ne], 5, h, w, mode=mode, polarity="neg")[0]
+        assert torch.allclose(pos, p1, **TOL) and torch.allclose(neg, n1, **TOL)
+        assert launches <= 3                         # sortedness check + bin boundaries + ONE scatter launch
+        rp, rn = orc.events_to_neg_pos_voxel_f32(xs, ys, ts, ps, 5, (h, w), bil)
+        assert np.allclose(pos.cpu().numpy(), rp, **TOL) and np.allclose(neg.cpu().numpy(), rn, **TOL)

@@ -16,7 +16,7 @@ NOISE_NONE, NOISE_EXPLICIT, NOISE_PHILOX = 0, 1, 2
 THRES_PER_CLIP, THRES_PER_PIXEL = 0, 1
 U8, I8, U16, I16, I32, I64, F32, F64 = range(8)
 SCATTER_H5_DISCRETE, SCATTER_H5_INTERP, SCATTER_TORCH_DISCRETE, SCATTER_TORCH_BILINEAR = range(4)
-POL_SIGNED, POL_POS_ONLY, POL_NEG_ONLY = range(3)
+POL_SIGNED, POL_POS_ONLY, POL_NEG_ONLY, POL_SPLIT = range(4)
 
 ERR_NAMES = {0: "OK", -1: "INVALID_ARG", -2: "SHAPE", -3: "ALIGNMENT", -4: "CUDA", -5: "UNSUPPORTED", -6: "NO_DEVICE"}
 
@@ -82,7 +82,12 @@ class ScatterDesc(C.Structure):
         ("xs", _p), ("ys", _p), ("ts", _p), ("ps", _p),
         ("window_offsets", _p), ("voxel", _p), ("dropped", _p),
         ("workspace", _p), ("workspace_bytes", C.c_int64),
+        ("unsorted", _p), ("kernel_flags", C.c_int32), ("tuning_splits", C.c_int32), ("tuning_smem_kb", C.c_int32),
+        ("reserved0", C.c_int32),
     ]
+
+
+SCATTER_FLAG_RANGES, SCATTER_FLAG_GENERIC_SCAN, SCATTER_FLAG_NO_PACKED16 = 1, 2, 4
 
 
 class ImageDesc(C.Structure):
@@ -109,6 +114,7 @@ SYMBOLS = {
     "v2v_v2e_shot_scales": (C.c_int, [C.POINTER(V2eDesc), _p, _p, _p]),
     "v2v_v2e_philox_fields": (C.c_int, [C.POINTER(V2eDesc), _p, _p, _p, _p]),
     "v2v_events_to_voxel": (C.c_int, [C.POINTER(ScatterDesc), _p]),
+    "v2v_scatter_workspace_bytes": (C.c_int64, [C.POINTER(ScatterDesc)]),
     "v2v_events_to_image": (C.c_int, [C.POINTER(ImageDesc), _p]),
     "v2v_voxel_add_noise": (C.c_int, [_p, C.c_int64, _p, _p, C.c_double, C.c_double, C.c_int, C.c_int, C.c_uint64, C.c_uint64, _p]),
     "v2v_voxel_add_map": (C.c_int, [_p, C.c_int64, C.c_int64, _p, _p]),
@@ -136,8 +142,8 @@ def load():
         fn = getattr(lib, name)
         fn.restype = res
         fn.argtypes = args
-    if lib.v2v_abi_version() != 1:
-        raise V2VError(-5, f"ABI version {lib.v2v_abi_version()} != 1")
+    if lib.v2v_abi_version() != 2:
+        raise V2VError(-5, f"ABI version {lib.v2v_abi_version()} != 2")
     _lib = lib
     return lib
 

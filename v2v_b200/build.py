@@ -16,7 +16,7 @@ PKG = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG, "csrc")
 LIBDIR = os.path.join(PKG, "lib")
 LIB = os.path.join(LIBDIR, "libv2v_b200.so")
-SOURCES = ["api.cu", "aux.cu", "esim.cu", "esim_fast.cu", "scatter.cu", "v2e.cu", "v2e_fast.cu"]
+SOURCES = ["api.cu", "aux.cu", "esim.cu", "esim_fast.cu", "scatter.cu", "scatter_sorted.cu", "v2e.cu", "v2e_fast.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-lineinfo", "-std=c++17",

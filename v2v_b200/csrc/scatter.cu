@@ -20,18 +20,15 @@
 //   h5 interp    : fixed point, round(w*2^30) split in two int32 words
 //                  (reference: sequential float64) -> |err| <= n*2^-31 per cell;
 //   torch modes  : float32 shared atomics (reference: sequential float32).
-#include "common.cuh"
+#include "scatter_common.cuh"
 
-#include <cstdlib>
 
 namespace v2v {
 namespace {
 
 constexpr int kScatterThreads = 512;
 constexpr int kSmemBudget = 100 * 1024;   // two CTAs per SM
-constexpr int kFixShift = 30, kLoBits = 15;
 
-struct WinConst;
 struct ScatterArgs {
   v2v_scatter_desc d;
   int rows_per_strip, num_strips;
@@ -43,105 +40,6 @@ struct ScatterArgs {
   int64_t* bounds;     // [Wn, bins+2]: first event with bin_floor >= k for k = -1 .. bins (from the pre-pass), or NULL
   struct WinConst* wcs; // [Wn] window constants from the pre-pass (valid when bounds != NULL)
 };
-
-__device__ __forceinline__ long long load_int(const void* p, int dtype, int64_t i, bool* ok) {
-  switch (dtype) {
-    case V2V_U8: return static_cast<const uint8_t*>(p)[i];
-    case V2V_I8: return static_cast<const int8_t*>(p)[i];
-    case V2V_U16: return static_cast<const uint16_t*>(p)[i];
-    case V2V_I16: return static_cast<const int16_t*>(p)[i];
-    case V2V_I32: return static_cast<const int32_t*>(p)[i];
-    case V2V_I64: return static_cast<const int64_t*>(p)[i];
-    case V2V_F32: {   // .long() / .to(int): truncation toward zero
-      float f = static_cast<const float*>(p)[i];
-      if (!(fabsf(f) < 1.0e9f)) { *ok = false; return 0; }
-      return static_cast<long long>(f);
-    }
-    case V2V_F64: {
-      double f = static_cast<const double*>(p)[i];
-      if (!(fabs(f) < 1.0e9)) { *ok = false; return 0; }
-      return static_cast<long long>(f);
-    }
-  }
-  *ok = false;
-  return 0;
-}
-
-__device__ __forceinline__ float load_f32(const void* p, int dtype, int64_t i) {
-  switch (dtype) {
-    case V2V_U8: return static_cast<float>(static_cast<const uint8_t*>(p)[i]);
-    case V2V_I8: return static_cast<float>(static_cast<const int8_t*>(p)[i]);
-    case V2V_F32: return static_cast<const float*>(p)[i];
-    case V2V_F64: return static_cast<float>(static_cast<const double*>(p)[i]);
-    case V2V_I32: return static_cast<float>(static_cast<const int32_t*>(p)[i]);
-    case V2V_I64: return static_cast<float>(static_cast<const int64_t*>(p)[i]);
-    case V2V_U16: return static_cast<float>(static_cast<const uint16_t*>(p)[i]);
-    case V2V_I16: return static_cast<float>(static_cast<const int16_t*>(p)[i]);
-  }
-  return 0.f;
-}
-
-// µs since the window start, exactly as ((ts - ts[0]) * 1e6).astype(int64)
-// evaluates in the dtype of the stored timestamps (data/testh5.py:68).
-__device__ __forceinline__ long long tau_us(const void* ts, int dtype, int64_t i, int64_t i0) {
-  if (dtype == V2V_F64) {
-    const double* t = static_cast<const double*>(ts);
-    return static_cast<long long>(__dmul_rn(__dsub_rn(t[i], t[i0]), 1e6));
-  }
-  const float* t = static_cast<const float*>(ts);
-  return static_cast<long long>(__fmul_rn(__fsub_rn(t[i], t[i0]), 1e6f));
-}
-
-// Bin index of event e in its window (the quantity that orders the events of a window: timestamps are
-// non-decreasing inside a window, so "bin(e) >= b" is a monotone predicate and every bin owns a contiguous range).
-struct WinConst {
-  double h5_tpb, h5_den;
-  float t_first, t_span, t_tpb;
-  int64_t e0;
-};
-
-template <int MODE>
-__device__ __forceinline__ WinConst window_constants(const v2v_scatter_desc& d, int64_t e0, int64_t e1) {
-  WinConst c;
-  c.e0 = e0;
-  c.h5_tpb = c.h5_den = 0.0;
-  c.t_first = c.t_span = c.t_tpb = 0.f;
-  const int B = d.num_bins;
-  if (MODE == V2V_SCATTER_H5_DISCRETE || MODE == V2V_SCATTER_H5_INTERP) {
-    const long long tl = tau_us(d.ts, d.ts_dtype, e1 - 1, e0);
-    c.h5_tpb = __ddiv_rn(__dadd_rn(static_cast<double>(tl), 0.001), static_cast<double>(B));       // testh5.py:71
-    c.h5_den = __dadd_rn(static_cast<double>(tl), 0.0001);                                         // :76-77 (ts[0]==0)
-  } else {
-    c.t_first = load_f32(d.ts, d.ts_dtype, e0);
-    c.t_span = __fsub_rn(load_f32(d.ts, d.ts_dtype, e1 - 1), c.t_first);                           // event_utils.py:489
-    c.t_tpb = __fdiv_rn(__fadd_rn(c.t_span, 0.001f), static_cast<float>(B));                       // :503
-  }
-  return c;
-}
-
-// floor of the (possibly fractional) bin coordinate of event e; *frac_coord receives the coordinate for the
-// interpolating modes.  Same expressions, same dtypes as the reference.
-template <int MODE>
-__device__ __forceinline__ double bin_floor(const v2v_scatter_desc& d, const WinConst& c, int64_t e, double* coord) {
-  const int B = d.num_bins;
-  if (MODE == V2V_SCATTER_H5_DISCRETE) {
-    const long long tau = tau_us(d.ts, d.ts_dtype, e, c.e0);
-    return floor(__ddiv_rn(static_cast<double>(tau), c.h5_tpb));                                   // testh5.py:72
-  } else if (MODE == V2V_SCATTER_H5_INTERP) {
-    const long long tau = tau_us(d.ts, d.ts_dtype, e, c.e0);
-    const double tn = __dmul_rn(__ddiv_rn(static_cast<double>(tau), c.h5_den), static_cast<double>(B - 1));   // :77
-    *coord = tn;
-    return floor(tn);
-  } else if (MODE == V2V_SCATTER_TORCH_DISCRETE) {
-    const float rel = __fsub_rn(load_f32(d.ts, d.ts_dtype, e), c.t_first);
-    return static_cast<double>(floorf(__fdiv_rn(rel, c.t_tpb)));                                   // event_utils.py:504
-  } else {
-    const float rel = __fsub_rn(load_f32(d.ts, d.ts_dtype, e), c.t_first);
-    const float tn = __fmul_rn(__fdiv_rn(rel, c.t_span), static_cast<float>(B - 1));               // :490
-    *coord = static_cast<double>(tn);
-    return static_cast<double>(floorf(tn));
-  }
-}
 
 // first event in [lo,hi) whose bin_floor is >= target, or hi (32-ary search by one warp)
 template <int MODE>
@@ -221,10 +119,15 @@ __global__ void __launch_bounds__(kScatterThreads, 2) scatter_kernel(const Scatt
   // work item = (window, bin, strip of rows); items of one window are adjacent so its events stay in L2
   const int K = a.num_splits;
   const int64_t per_win = static_cast<int64_t>(B) * a.num_strips * K;
-  const int64_t items = static_cast<int64_t>(d.num_windows) * per_win;
+  // V2V_POL_SPLIT: every window is done twice, as output slot 2w with the positive-only weights and as slot 2w+1 with
+  // the negative-only weights (events_to_neg_pos_voxel_torch in one launch)
+  const bool psplit = d.polarity_mode == V2V_POL_SPLIT;
+  const int64_t items = static_cast<int64_t>(d.num_windows) * per_win * (psplit ? 2 : 1);
   for (int64_t item = blockIdx.x; item < items; item += gridDim.x) {
-    const int win = static_cast<int>(item / per_win);
-    int rem = static_cast<int>(item - static_cast<int64_t>(win) * per_win);
+    const int vwin = static_cast<int>(item / per_win);                  // output slot
+    const int win = psplit ? vwin >> 1 : vwin;                          // window of the event stream
+    const int polm = psplit ? ((vwin & 1) ? V2V_POL_NEG_ONLY : V2V_POL_POS_ONLY) : d.polarity_mode;
+    int rem = static_cast<int>(item - static_cast<int64_t>(vwin) * per_win);
     const int split = rem % K;
     rem /= K;
     const int bin = rem / a.num_strips, strip = rem - bin * a.num_strips;
@@ -250,7 +153,7 @@ __global__ void __launch_bounds__(kScatterThreads, 2) scatter_kernel(const Scatt
         }
         if (lane == 0) s_wc = wc;
         // events whose bin falls outside [0, B) are dropped: counted once per window
-        if (lane == 0 && strip == 0 && split == 0 && d.dropped) {
+        if (lane == 0 && strip == 0 && split == 0 && d.dropped && !(psplit && (vwin & 1))) {
           long long nd = 0;
           if (bin == 0 && !kTwoTap) nd += lo - e0;                    // bin < 0 (unsorted / negative timestamps)
           if (bin == B - 1) nd += e1 - hi;                            // bin >= B
@@ -353,8 +256,8 @@ __global__ void __launch_bounds__(kScatterThreads, 2) scatter_kernel(const Scatt
           float pw;                                                                     // polarity -> weight
           {
             const float p = pv[u];
-            if (d.polarity_mode == V2V_POL_POS_ONLY) pw = p > 0.f ? 1.f : 0.f;          // event_utils.py:533
-            else if (d.polarity_mode == V2V_POL_NEG_ONLY) pw = p <= 0.f ? 1.f : 0.f;    // :534
+            if (polm == V2V_POL_POS_ONLY) pw = p > 0.f ? 1.f : 0.f;          // event_utils.py:533
+            else if (polm == V2V_POL_NEG_ONLY) pw = p <= 0.f ? 1.f : 0.f;    // :534
             else pw = kH5 ? (2.f * p - 1.f) : p;                                        // testh5.py:67
           }
           if (MODE == V2V_SCATTER_H5_DISCRETE) {                                        // testh5.py:73
@@ -437,8 +340,8 @@ __global__ void __launch_bounds__(kScatterThreads, 2) scatter_kernel(const Scatt
         float pw;                                                                     // polarity -> weight
         {
           const float p = pv[u];
-          if (d.polarity_mode == V2V_POL_POS_ONLY) pw = p > 0.f ? 1.f : 0.f;          // event_utils.py:533
-          else if (d.polarity_mode == V2V_POL_NEG_ONLY) pw = p <= 0.f ? 1.f : 0.f;    // :534
+          if (polm == V2V_POL_POS_ONLY) pw = p > 0.f ? 1.f : 0.f;          // event_utils.py:533
+          else if (polm == V2V_POL_NEG_ONLY) pw = p <= 0.f ? 1.f : 0.f;    // :534
           else pw = kH5 ? (2.f * p - 1.f) : p;                                        // testh5.py:67
         }
         if (MODE == V2V_SCATTER_H5_DISCRETE) {                                        // testh5.py:73
@@ -460,8 +363,8 @@ __global__ void __launch_bounds__(kScatterThreads, 2) scatter_kernel(const Scatt
           {
             const float p = d.ps_dtype == V2V_U8 ? static_cast<float>(static_cast<const uint8_t*>(d.ps)[e])
                           : d.ps_dtype == V2V_F32 ? static_cast<const float*>(d.ps)[e] : load_f32(d.ps, d.ps_dtype, e);
-            if (d.polarity_mode == V2V_POL_POS_ONLY) pw = p > 0.f ? 1.f : 0.f;
-            else if (d.polarity_mode == V2V_POL_NEG_ONLY) pw = p <= 0.f ? 1.f : 0.f;
+            if (polm == V2V_POL_POS_ONLY) pw = p > 0.f ? 1.f : 0.f;
+            else if (polm == V2V_POL_NEG_ONLY) pw = p <= 0.f ? 1.f : 0.f;
             else pw = kH5 ? (2.f * p - 1.f) : p;
           }
           double tnd;
@@ -491,7 +394,7 @@ __global__ void __launch_bounds__(kScatterThreads, 2) scatter_kernel(const Scatt
     // stream the strip out once: [win, bin, r0 + r, x]
     {
       const int cells = rows * W;
-      const int64_t out_base = ((static_cast<int64_t>(win) * B + bin) * H + r0) * W;
+      const int64_t out_base = ((static_cast<int64_t>(vwin) * B + bin) * H + r0) * W;
       auto value = [&](int i) -> double {          // float64 outputs (drop-in make_voxel)
         if (kInterp) {
           const long long tot = static_cast<long long>(acc_i[i]) * (1 << kLoBits) +
@@ -588,6 +491,37 @@ __global__ void image_kernel(const ImageArgs a) {
   if (d.dropped && ndrop) atomicAdd(reinterpret_cast<unsigned long long*>(d.dropped), static_cast<unsigned long long>(ndrop));
 }
 
+// Contiguous-range modes need non-decreasing timestamps inside every window.  One pass over the timestamps (8 bytes per
+// event, ~1 % of the scatter's traffic): status[0] += number of positions where ts[e+1] < ts[e] inside a window.
+__global__ void __launch_bounds__(256) sorted_check_kernel(const v2v_scatter_desc d, long long* status) {
+  long long bad = 0;
+  const int64_t first = d.num_windows > 0 ? d.window_offsets[0] : 0, last = d.num_windows > 0 ? d.window_offsets[d.num_windows] : 0;
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  auto is_window_start = [&](int64_t e) {            // rare: a decrease onto the first event of a window is legitimate
+    int lo = 0, hi = d.num_windows;
+    while (hi - lo > 1) {
+      const int mid = (lo + hi) >> 1;
+      if (d.window_offsets[mid] <= e) lo = mid; else hi = mid;
+    }
+    return d.window_offsets[lo] == e;
+  };
+  if (d.ts_dtype == V2V_F64) {
+    const double* t = static_cast<const double*>(d.ts);
+    for (int64_t e0 = first + (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) * 4; e0 + 1 < last; e0 += stride * 4) {
+      double v[5];                                   // four comparisons per trip, the five loads in flight together
+#pragma unroll
+      for (int k = 0; k < 5; ++k) v[k] = e0 + k < last ? t[e0 + k] : 0.0;
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        if (e0 + k + 1 < last && v[k + 1] < v[k] && !is_window_start(e0 + k + 1)) ++bad;
+    }
+  } else {
+    for (int64_t e = first + static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; e + 1 < last; e += stride)
+      if (load_f32(d.ts, d.ts_dtype, e + 1) < load_f32(d.ts, d.ts_dtype, e) && !is_window_start(e + 1)) ++bad;
+  }
+  if (bad) atomicAdd(reinterpret_cast<unsigned long long*>(status), static_cast<unsigned long long>(bad));
+}
+
 bool coord_dtype_ok(int t) { return t == V2V_U16 || t == V2V_I16 || t == V2V_I32 || t == V2V_I64 || t == V2V_F32 || t == V2V_F64 || t == V2V_U8; }
 
 }  // namespace
@@ -600,7 +534,7 @@ extern "C" int v2v_events_to_voxel(const v2v_scatter_desc* desc, void* stream) {
   V2V_REQUIRE(d.num_events >= 0 && d.num_windows >= 0 && d.num_bins >= 1 && d.H >= 0 && d.W >= 0, V2V_ERR_INVALID_ARG,
               "bad sizes Ne=%lld Wn=%d bins=%d H=%d W=%d", static_cast<long long>(d.num_events), d.num_windows, d.num_bins, d.H, d.W);
   V2V_REQUIRE(d.mode >= 0 && d.mode <= 3, V2V_ERR_INVALID_ARG, "bad mode %d", d.mode);
-  V2V_REQUIRE(d.polarity_mode >= 0 && d.polarity_mode <= 2, V2V_ERR_INVALID_ARG, "bad polarity_mode %d", d.polarity_mode);
+  V2V_REQUIRE(d.polarity_mode >= 0 && d.polarity_mode <= 3, V2V_ERR_INVALID_ARG, "bad polarity_mode %d", d.polarity_mode);
   V2V_REQUIRE(d.out_dtype == V2V_F32 || d.out_dtype == V2V_F64, V2V_ERR_INVALID_ARG, "out_dtype must be F32 or F64");
   if (d.num_windows == 0 || d.H == 0 || d.W == 0) return V2V_OK;
   V2V_REQUIRE(d.window_offsets && d.voxel, V2V_ERR_INVALID_ARG, "window_offsets and voxel must be non-NULL");
@@ -611,15 +545,21 @@ extern "C" int v2v_events_to_voxel(const v2v_scatter_desc* desc, void* stream) {
   V2V_REQUIRE(h5 || d.ts_dtype == V2V_F32 || d.ts_dtype == V2V_F64, V2V_ERR_INVALID_ARG, "torch modes need float timestamps");
   V2V_REQUIRE(d.ps_dtype == V2V_U8 || d.ps_dtype == V2V_I8 || d.ps_dtype == V2V_F32, V2V_ERR_INVALID_ARG, "bad polarity dtype");
 
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  // h5 interpolated mode with enough workspace: counting sort by strip, one visit per event, any event order
+  if (scatter_sorted_eligible(d) && !(d.kernel_flags & V2V_SCATTER_FLAG_RANGES)) return launch_scatter_sorted(d, s);
+  if (d.unsorted && d.num_events > 1) {          // the kernels below assume sorted windows: report violations
+    sorted_check_kernel<<<148 * 8, 256, 0, s>>>(d, d.unsorted);
+    count_launch();
+  }
+
   ScatterArgs a;
   a.d = d;
   // one tile = one bin x a strip of rows; sized so that two CTAs share an SM
-  a.packed16 = d.mode == V2V_SCATTER_H5_DISCRETE;
-  if (const char* e = getenv("V2V_SCATTER_PACKED16")) a.packed16 = a.packed16 && atoi(e) != 0;
+  a.packed16 = d.mode == V2V_SCATTER_H5_DISCRETE && !(d.kernel_flags & V2V_SCATTER_FLAG_NO_PACKED16);
   const int cell_bytes = d.mode == V2V_SCATTER_H5_INTERP ? 8 : (a.packed16 ? 2 : 4);
   const int64_t row_bytes = static_cast<int64_t>(d.W) * cell_bytes;
-  int budget = kSmemBudget;
-  if (const char* e = getenv("V2V_SCATTER_SMEM_KB")) budget = atoi(e) * 1024;
+  int budget = d.tuning_smem_kb > 0 ? d.tuning_smem_kb * 1024 : kSmemBudget;
   const bool two_tap = d.mode == V2V_SCATTER_H5_INTERP || d.mode == V2V_SCATTER_TORCH_BILINEAR;
   const int list_bytes = two_tap ? 8 * kScatterThreads * 4 : 0;        // one scan trip: 8 events per thread, 4 bytes each
   budget -= list_bytes;
@@ -632,14 +572,15 @@ extern "C" int v2v_events_to_voxel(const v2v_scatter_desc* desc, void* stream) {
   // (the 32-bit fallback of a packed strip uses two passes of ceil(R/2) rows: one extra row of slack)
   a.tile_bytes = static_cast<int>((static_cast<size_t>(a.rows_per_strip + (a.packed16 ? 1 : 0)) * row_bytes + 31) / 16 * 16);
   const size_t smem = static_cast<size_t>(a.tile_bytes) + list_bytes;
-  int64_t items = static_cast<int64_t>(d.num_windows) * d.num_bins * a.num_strips;
+  const int vw = d.polarity_mode == V2V_POL_SPLIT ? 2 : 1;          // output slots per window
+  int64_t items = static_cast<int64_t>(d.num_windows) * vw * d.num_bins * a.num_strips;
   int dev = 0, sms = 148;
   V2V_CUDA(cudaGetDevice(&dev));
   V2V_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   // few, large windows (e.g. the offline cache builder: one window of millions of events) cannot fill the GPU with
   // one CTA per (window, bin, strip): split every bin's event range over several CTAs
   a.num_splits = 1;
-  a.generic_scan = getenv("V2V_SCATTER_GENERIC") != nullptr;
+  a.generic_scan = (d.kernel_flags & V2V_SCATTER_FLAG_GENERIC_SCAN) != 0;
   const int64_t ev_per_item = d.num_events / (static_cast<int64_t>(d.num_windows) * d.num_bins > 0 ? static_cast<int64_t>(d.num_windows) * d.num_bins : 1);
   if (items < 2LL * sms && ev_per_item > 16384) {
     int64_t k = (4LL * sms + items - 1) / items;
@@ -648,10 +589,9 @@ extern "C" int v2v_events_to_voxel(const v2v_scatter_desc* desc, void* stream) {
     if (k > 64) k = 64;
     if (k > 1) a.num_splits = static_cast<int>(k);
   }
-  if (const char* e = getenv("V2V_SCATTER_SPLITS")) a.num_splits = atoi(e) > 0 ? atoi(e) : 1;
+  if (d.tuning_splits > 0) a.num_splits = d.tuning_splits;
   items *= a.num_splits;
   const int grid = static_cast<int>(items < 4LL * sms ? items : 4LL * sms);
-  cudaStream_t s = static_cast<cudaStream_t>(stream);
   a.bounds = nullptr;
   a.wcs = nullptr;
   const size_t nb = static_cast<size_t>(d.num_windows) * (d.num_bins + 2) * sizeof(int64_t);
@@ -661,7 +601,7 @@ extern "C" int v2v_events_to_voxel(const v2v_scatter_desc* desc, void* stream) {
     a.wcs = reinterpret_cast<WinConst*>(static_cast<char*>(d.workspace) + nb);
   }
   if (a.num_splits > 1)
-    V2V_CUDA(cudaMemsetAsync(d.voxel, 0, static_cast<size_t>(d.num_windows) * d.num_bins * d.H * d.W * (d.out_dtype == V2V_F64 ? 8 : 4), s));
+    V2V_CUDA(cudaMemsetAsync(d.voxel, 0, static_cast<size_t>(d.num_windows) * vw * d.num_bins * d.H * d.W * (d.out_dtype == V2V_F64 ? 8 : 4), s));
 #define V2V_LAUNCH(M)                                                                                      \
   do {                                                                                                     \
     if (a.bounds) {                                                                                        \
@@ -682,6 +622,15 @@ extern "C" int v2v_events_to_voxel(const v2v_scatter_desc* desc, void* stream) {
   count_launch();
   V2V_CUDA(cudaGetLastError());
   return V2V_OK;
+}
+
+extern "C" int64_t v2v_scatter_workspace_bytes(const v2v_scatter_desc* desc) {
+  using namespace v2v;
+  if (!desc || desc->num_windows < 0 || desc->num_bins < 1) return 0;
+  int R = 0, S = 0;
+  const size_t ranges = static_cast<size_t>(desc->num_windows) * ((desc->num_bins + 2) * 8 + sizeof(WinConst)) + 64;
+  const size_t sorted = desc->mode == V2V_SCATTER_H5_INTERP ? scatter_sorted_workspace_bytes(*desc, &R, &S) : 0;
+  return static_cast<int64_t>(sorted > ranges ? sorted : ranges);
 }
 
 extern "C" int v2v_events_to_image(const v2v_image_desc* desc, void* stream) {

@@ -16,6 +16,7 @@ runs through the C ABI (include/v2v_b200.h); there is no CPU path.
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import Optional, Sequence
 
 import numpy as np
@@ -54,10 +55,27 @@ def _dt(t: torch.Tensor) -> int:
         raise TypeError(f"unsupported event dtype {t.dtype}")
 
 
+def _env_int(name: str) -> int:
+    v = os.environ.get(name)
+    return int(v) if v else 0
+
+
+def _env_flags() -> int:
+    """Tuning / test knobs, read here in the Python host per call (the C library reads no environment)."""
+    f = 0
+    if os.environ.get("V2V_SCATTER_RANGES"):
+        f |= _lib.SCATTER_FLAG_RANGES
+    if os.environ.get("V2V_SCATTER_GENERIC"):
+        f |= _lib.SCATTER_FLAG_GENERIC_SCAN
+    if os.environ.get("V2V_SCATTER_PACKED16") == "0":
+        f |= _lib.SCATTER_FLAG_NO_PACKED16
+    return f
+
+
 def voxelize_windows(xs, ys, ts, ps, window_offsets, num_bins: int, height: int, width: int, *,
                      mode: str = "h5_discrete", polarity: str = "signed", out_dtype=torch.float32,
                      device="cuda", out: Optional[torch.Tensor] = None, return_dropped: bool = False,
-                     validate: bool = False, stream: Optional[torch.cuda.Stream] = None):
+                     validate: Optional[bool] = None, stream: Optional[torch.cuda.Stream] = None, kernel_flags: int = 0):
     """Scatter ``Wn`` windows of one event stream into ``[Wn,bins,H,W]`` in one launch.
 
     window_offsets: ``[Wn+1]`` ascending event indices (e.g. the ``event_idx``
@@ -66,13 +84,17 @@ def voxelize_windows(xs, ys, ts, ps, window_offsets, num_bins: int, height: int,
     or float32, ps in {0,1}) | "torch_discrete" | "torch_bilinear"
     (utils/event_utils.py:490-505; float32 arithmetic, ps = signed weights).
 
-    Precondition (include/v2v_b200.h): timestamps are non-decreasing inside every window, as in every h5 file the
-    reference's converters write.  ``validate=True`` checks it (one extra pass, a device->host sync) and raises.
+    Event order: "h5_interp" takes any order (every event's bin comes from its own timestamp, as in the reference's
+    ``np.add.at``).  The other modes assign every bin a contiguous range of the window and need timestamps that are
+    non-decreasing inside every window (true for every h5 file the reference's converters write); the library counts
+    violations on the device in the same call.  ``validate`` (default: on, unless ``return_dropped`` hands the counters
+    back for the caller to check without a sync here) reads that counter and raises ``ValueError`` for unsorted input
+    instead of returning mis-binned voxels.  With ``return_dropped`` the result is ``(out, dropped, unsorted)``.
     """
     dev = torch.device(device)
     modes = {"h5_discrete": _lib.SCATTER_H5_DISCRETE, "h5_interp": _lib.SCATTER_H5_INTERP,
              "torch_discrete": _lib.SCATTER_TORCH_DISCRETE, "torch_bilinear": _lib.SCATTER_TORCH_BILINEAR}
-    pols = {"signed": _lib.POL_SIGNED, "pos": _lib.POL_POS_ONLY, "neg": _lib.POL_NEG_ONLY}
+    pols = {"signed": _lib.POL_SIGNED, "pos": _lib.POL_POS_ONLY, "neg": _lib.POL_NEG_ONLY, "split": _lib.POL_SPLIT}
     xs_t, ys_t, ts_t, ps_t = (_to_dev(a, dev) for a in (xs, ys, ts, ps))
     ne = xs_t.numel()
     if not (ys_t.numel() == ne and ts_t.numel() == ne and ps_t.numel() == ne):
@@ -86,20 +108,15 @@ def voxelize_windows(xs, ys, ts, ps, window_offsets, num_bins: int, height: int,
     wn = off_t.numel() - 1
     if wn < 0:
         raise ValueError("window_offsets needs at least one entry")
-    if validate and ne > 1:
-        bad = ts_t[1:] < ts_t[:-1]
-        if wn > 0:                                   # a decrease exactly at a window boundary is fine
-            edges = off_t[1:-1]
-            edges = edges[(edges > 0) & (edges < ne)]
-            bad[edges - 1] = False
-        if bool(bad.any()):
-            raise ValueError("timestamps must be non-decreasing inside every window")
+    if validate is None:
+        validate = not return_dropped
+    oshape = (wn, 2, num_bins, height, width) if polarity == "split" else (wn, num_bins, height, width)
     if out is None:
-        out = torch.empty((wn, num_bins, height, width), dtype=out_dtype, device=dev)
-    elif tuple(out.shape) != (wn, num_bins, height, width) or not out.is_contiguous() or not out.is_cuda:
+        out = torch.empty(oshape, dtype=out_dtype, device=dev)
+    elif tuple(out.shape) != oshape or not out.is_contiguous() or not out.is_cuda:
         raise ValueError("out has the wrong shape / layout")
-    dropped = torch.zeros(1, dtype=torch.int64, device=dev)
-    work = torch.empty(wn * (num_bins + 2 + 8), dtype=torch.int64, device=dev)  # bin-boundary table of the pre-pass
+    counters = torch.zeros(2, dtype=torch.int64, device=dev)          # [dropped, unsorted]
+    dropped, unsorted = counters[0:1], counters[1:2]
 
     d = _lib.ScatterDesc()
     d.num_events, d.num_windows = ne, wn
@@ -109,14 +126,20 @@ def voxelize_windows(xs, ys, ts, ps, window_offsets, num_bins: int, height: int,
     d.out_dtype = {torch.float32: _lib.F32, torch.float64: _lib.F64}[out.dtype]
     d.xs, d.ys, d.ts, d.ps = _ptr(xs_t), _ptr(ys_t), _ptr(ts_t), _ptr(ps_t)
     d.window_offsets, d.voxel, d.dropped = _ptr(off_t), _ptr(out), _ptr(dropped)
+    d.unsorted = _ptr(unsorted)
+    d.kernel_flags, d.tuning_splits, d.tuning_smem_kb = int(kernel_flags) | _env_flags(), _env_int("V2V_SCATTER_SPLITS"), _env_int("V2V_SCATTER_SMEM_KB")
+    work = torch.empty((int(_lib.load().v2v_scatter_workspace_bytes(C.byref(d))) + 15) // 16 * 2, dtype=torch.int64, device=dev)
     d.workspace, d.workspace_bytes = _ptr(work), work.numel() * 8
     s = stream if stream is not None else torch.cuda.current_stream(dev)
     with torch.cuda.device(dev):
         _lib.check(_lib.load().v2v_events_to_voxel(C.byref(d), C.c_void_p(s.cuda_stream)))
-    for t in (xs_t, ys_t, ts_t, ps_t, off_t):
+    for t in (xs_t, ys_t, ts_t, ps_t, off_t, work, counters):
         t.record_stream(s)
+    if validate and int(unsorted.item()) != 0:
+        raise ValueError(f"timestamps decrease at {int(unsorted.item())} positions inside windows: mode {mode!r} needs "
+                         "non-decreasing timestamps inside every window")
     if return_dropped:
-        return out, dropped
+        return out, dropped, unsorted
     return out
 
 
@@ -168,11 +191,9 @@ def events_to_neg_pos_voxel_torch(xs, ys, ts, ps, B, device=None, sensor_size=(1
         device = xs.device if isinstance(xs, torch.Tensor) and xs.is_cuda else "cuda"
     n = len(xs)
     mode = "torch_bilinear" if temporal_bilinear else "torch_discrete"
-    pos = voxelize_windows(xs, ys, ts, ps, [0, n], B, sensor_size[0], sensor_size[1], mode=mode, polarity="pos",
-                           device=device)[0]
-    neg = voxelize_windows(xs, ys, ts, ps, [0, n], B, sensor_size[0], sensor_size[1], mode=mode, polarity="neg",
-                           device=device)[0]
-    return pos, neg
+    both = voxelize_windows(xs, ys, ts, ps, [0, n], B, sensor_size[0], sensor_size[1], mode=mode, polarity="split",
+                            device=device)             # one launch: [1, 2, B, H, W]
+    return both[0, 0], both[0, 1]
 
 
 def _image(xs, ys, ps, sensor_size, bilinear, padding, clip, out_dtype, device):
