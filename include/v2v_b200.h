@@ -168,6 +168,10 @@ typedef struct v2v_v2e_desc {
   int32_t raw_frames_per_clip;   /* frames per clip in `frames` when frame_index is given; 0 = N                         */
   int32_t kernel_flags;          /* 0 = library's choice; V2V_V2E_FLAG_* (tests and tuning: kernel selection never changes results) */
   const uint8_t* value_map;      /* [B,256] uint8 -> uint8 applied to every pixel before any use of its value, or NULL   */
+  int32_t thres_per_interval;    /* 1: pos_thres / neg_thres are [B,N-1,H,W], the maps in force at frame i = interval i-1
+                                  * (threshold_model "spatial_temporal_independent", data/v2v_core_v2e.py:417-421; noise_mode
+                                  * NONE or EXPLICIT: the host draws the maps in the reference's order)                   */
+  int32_t reserved1;
 } v2v_v2e_desc;
 
 int v2v_v2e_frames_to_voxel(const v2v_v2e_desc* desc, void* stream);

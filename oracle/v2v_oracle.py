@@ -213,9 +213,9 @@ def v2e_video_to_voxel(video, fps, params, rs=np.random, lut=None, record=None, 
     n, h, w = video.shape
     shape = (h, w)
     model = params["threshold_model"]
-    if model not in ("pn_related", "spatial_independent"):
-        raise NotImplementedError("oracle covers the time-invariant threshold models; "
-                                  "see DESIGN.md for the per-frame models")
+    if model not in ("pn_related", "spatial_independent", "spatial_temporal_independent"):
+        raise NotImplementedError("spatial_independent_temporal_changing: see DESIGN.md")
+    per_frame = model == "spatial_temporal_independent"       # thresholds re-drawn on every frame (:417-421)
     cutoff = params["cutoff_hz"]
     leak_hz = params["leak_rate_hz"]
     shot_hz = params["shot_noise_rate_hz"]
@@ -223,7 +223,7 @@ def v2e_video_to_voxel(video, fps, params, rs=np.random, lut=None, record=None, 
     if lut is None:
         lut = v2e_log_lut()
     if record is not None:
-        record.update({"leak_randn": [], "pos_shot": [], "neg_shot": []})
+        record.update({"leak_randn": [], "pos_shot": [], "neg_shot": [], "pos_thres_frames": [], "neg_thres_frames": []})
     vid_idx = video.astype(np.int64)
     out = np.empty((n - 1, h, w), dtype=np.float64)
     t_prev = 0.0
@@ -231,6 +231,13 @@ def v2e_video_to_voxel(video, fps, params, rs=np.random, lut=None, record=None, 
     for k in range(n):
         t_k = k / fps
         dt = t_k - t_prev                                             # :442
+        if per_frame and maps is None:                                # :417-421, before anything else, on EVERY frame
+            a = rs.normal(loc=params["thres_mean_mean"], scale=params["thres_mean_std"], size=shape)
+            b = rs.normal(loc=params["thres_mean_mean"], scale=params["thres_mean_std"], size=shape)
+            pos_thr, neg_thr, pos_pp, neg_pp = _v2e_thresholds(params, a, b)
+            if record is not None and k > 0:
+                record["pos_thres_frames"].append(pos_thr)
+                record["neg_thres_frames"].append(neg_thr)
         frame = video[k].astype(np.float64)
         log_new = lut[vid_idx[k]]                                     # float32, :447
         inten01 = None
@@ -258,7 +265,7 @@ def v2e_video_to_voxel(video, fps, params, rs=np.random, lut=None, record=None, 
                 b = rs.normal(loc=params["thres_diff_mean"], scale=params["thres_diff_std"], size=shape)
             else:
                 b = rs.normal(loc=params["thres_mean_mean"], scale=params["thres_mean_std"], size=shape)
-            pos_thr, neg_thr, pos_pp, neg_pp = _v2e_thresholds(params, a, b)
+            pos_thr, neg_thr, pos_pp, neg_pp = _v2e_thresholds(params, a, b)      # (per-frame model: replaced on the next frame)
             nr = rs.randn(*shape).astype(np.float32)                  # :348
             noise_rate = np.exp(math.log(10) * params["noise_rate_cov_decades"] * nr)   # :349 (float32)
             if record is not None:

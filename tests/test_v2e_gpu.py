@@ -22,8 +22,10 @@ def test_v2e_golden_replay(cuda_device, name):
     c = golden("v2e").case(name)
     p = params_of(c)
     fr = torch.from_numpy(c["video"]).to(cuda_device)
+    per_frame = "pos_thres_frames" in c        # spatial_temporal_independent: the maps in force at every frame
     out = frames_to_voxel_v2e(
-        fr, c["pos_thres"][None], c["neg_thres"][None], fps=float(c["fps"]), cutoff_hz=p["cutoff_hz"],
+        fr, c["pos_thres_frames" if per_frame else "pos_thres"][None], c["neg_thres_frames" if per_frame else "neg_thres"][None],
+        fps=float(c["fps"]), cutoff_hz=p["cutoff_hz"],
         leak_rate_hz=p["leak_rate_hz"], shot_noise_rate_hz=p["shot_noise_rate_hz"],
         leak_jitter_fraction=p["leak_jitter_fraction"], noise_rate=c["noise_rate"][None],
         pos_thres_nominal=p["thres_mean_mean"] + p["thres_diff_mean"] / 2,

@@ -69,6 +69,7 @@ class V2eDesc(C.Structure):
         ("seed", C.c_uint64), ("clip_index_base", C.c_uint64),
         ("voxel", _p), ("stats", _p),
         ("frame_index", _p), ("raw_frames_per_clip", C.c_int32), ("kernel_flags", C.c_int32), ("value_map", _p),
+        ("thres_per_interval", C.c_int32), ("reserved1", C.c_int32),
     ]
 
 

@@ -59,10 +59,11 @@ __global__ void __launch_bounds__(kV2eThreads) v2e_kernel(const V2eArgs a) {
 
   double pth[P], nth[P], lp[P], base[P];
   float nrate[LEAK ? P : 1], ppf[SHOT ? P : 1], npf[SHOT ? P : 1];
+  const bool thr_pi = d.thres_per_interval != 0;      // maps re-drawn on every frame (:417-421): reloaded per interval below
 #pragma unroll
   for (int k = 0; k < P; ++k) {
-    pth[k] = d.pos_thres[mp + k];
-    nth[k] = d.neg_thres[mp + k];
+    pth[k] = thr_pi ? 1.0 : d.pos_thres[mp + k];
+    nth[k] = thr_pi ? 1.0 : d.neg_thres[mp + k];
     if (LEAK) nrate[LEAK ? k : 0] = d.noise_rate ? d.noise_rate[mp + k] : 1.0f;
     if (SHOT) {                                                                    // :396-399
       ppf[SHOT ? k : 0] = v2e_pre_prob(d.pos_thres_nominal, pth[k]);
@@ -111,6 +112,13 @@ __global__ void __launch_bounds__(kV2eThreads) v2e_kernel(const V2eArgs a) {
       t_prev = t_k;
       const double qdt = CUTOFF ? __ddiv_rn(dt, a.tau) : 0.0;           // :167
       const int64_t fo = (static_cast<int64_t>(b) * (N - 1) + (i - 1)) * HW + pix0;
+      if (thr_pi) {
+#pragma unroll
+        for (int k = 0; k < P; ++k) {
+          pth[k] = d.pos_thres[fo + k];
+          nth[k] = d.neg_thres[fo + k];
+        }
+      }
       float sps = 0.f, sns = 0.f;
       if (SHOT && philox) {
         const int64_t si = static_cast<int64_t>(b) * (N - 1) + (i - 1);
@@ -403,6 +411,8 @@ extern "C" int v2v_v2e_frames_to_voxel(const v2v_v2e_desc* desc, void* stream) {
   if (d.B == 0 || a.HW == 0 || d.N == 1) return V2V_OK;
   V2V_REQUIRE(d.frames && d.lut && d.pos_thres && d.neg_thres && d.voxel, V2V_ERR_INVALID_ARG,
               "frames, lut, pos_thres, neg_thres and voxel must be non-NULL");
+  V2V_REQUIRE(!d.thres_per_interval || d.noise_mode != V2V_NOISE_PHILOX, V2V_ERR_UNSUPPORTED,
+              "per-interval threshold maps come with host-drawn fields (noise_mode NONE or EXPLICIT)");
   V2V_REQUIRE(!(d.state_f32 && (d.cutoff_hz > 0.0 || d.leak_rate_hz > 0.0)), V2V_ERR_INVALID_ARG,
               "state_f32 is only meaningful with cutoff_hz<=0 and leak_rate_hz<=0");
   if (d.noise_mode == V2V_NOISE_PHILOX && d.shot_noise_rate_hz > 0.0)

@@ -406,7 +406,7 @@ size_t fast_smem_bytes(const V2eArgs& a, bool trig, bool bf) {
 
 bool v2e_fast_eligible(const V2eArgs& a) {
   const v2v_v2e_desc& d = a.d;
-  if (d.noise_mode == V2V_NOISE_EXPLICIT) return false;
+  if (d.noise_mode == V2V_NOISE_EXPLICIT || d.thres_per_interval) return false;
   if (a.HW % 4 != 0 || !aligned(d.frames, 4) || !aligned(d.voxel, 16) || !aligned(d.pos_thres, 16) || !aligned(d.neg_thres, 16)) return false;
   if (d.N - 1 > kMaxIntervals) return false;
   const bool sh = d.shot_noise_rate_hz > 0.0 && d.noise_mode != V2V_NOISE_NONE;

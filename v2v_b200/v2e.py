@@ -35,6 +35,7 @@ def _env_kernel_flags() -> int:
 
 _NOISE = {"none": _lib.NOISE_NONE, "explicit": _lib.NOISE_EXPLICIT, "philox": _lib.NOISE_PHILOX}
 TIME_INVARIANT_MODELS = ("pn_related", "spatial_independent")
+PER_FRAME_MODEL = "spatial_temporal_independent"
 
 
 def v2e_log_lut() -> np.ndarray:
@@ -52,13 +53,13 @@ def threshold_maps(threshold_model, thres_mean_mean, thres_mean_std, thres_diff_
         m = rs.normal(loc=thres_mean_mean, scale=thres_mean_std, size=shape)
         dd = rs.normal(loc=thres_diff_mean, scale=thres_diff_std, size=shape)
         pos, neg = m + (dd / 2), m - (dd / 2)
-    elif threshold_model == "spatial_independent":
+    elif threshold_model in ("spatial_independent", PER_FRAME_MODEL):
         pos = rs.normal(loc=thres_mean_mean, scale=thres_mean_std, size=shape)
         neg = rs.normal(loc=thres_mean_mean, scale=thres_mean_std, size=shape)
     else:
         raise NotImplementedError(
-            f"threshold_model {threshold_model!r}: only the time-invariant models are implemented "
-            "(the per-frame models redraw full-frame maps every frame; see DESIGN.md)")
+            f"threshold_model {threshold_model!r} is not implemented (spatial_independent_temporal_changing adds a random "
+            "walk to the maps every frame; no caller in the reference, see DESIGN.md)")
     return np.clip(pos, a_min=0.01, a_max=None), np.clip(neg, a_min=0.01, a_max=None)
 
 
@@ -106,8 +107,12 @@ def frames_to_voxel_v2e(frames: torch.Tensor, pos_thres, neg_thres, *, fps: floa
     if (N - 1) % group != 0:
         raise AssertionError(f"(N-1)={N - 1} must be a multiple of num_bins*frames_per_bin={group}")
     T = (N - 1) // group
-    pos_t = _as_dev(pos_thres, dev, torch.float64, (B, H, W), "pos_thres")
-    neg_t = _as_dev(neg_thres, dev, torch.float64, (B, H, W), "neg_thres")
+    per_interval = np.ndim(pos_thres) == 4          # [B,N-1,H,W]: maps re-drawn on every frame (spatial_temporal_independent)
+    tshape = (B, N - 1, H, W) if per_interval else (B, H, W)
+    pos_t = _as_dev(pos_thres, dev, torch.float64, tshape, "pos_thres")
+    neg_t = _as_dev(neg_thres, dev, torch.float64, tshape, "neg_thres")
+    if per_interval and noise == "philox":
+        raise NotImplementedError("per-frame threshold maps come with host-drawn fields (noise 'none' or 'explicit')")
     nr_t = _as_dev(noise_rate, dev, torch.float32, (B, H, W), "noise_rate")
     lr_t = _as_dev(leak_randn, dev, torch.float64, (B, N - 1, H, W), "leak_randn")
     ps_t = _as_dev(pos_shot, dev, torch.int32, (B, N - 1, H, W), "pos_shot")
@@ -126,6 +131,7 @@ def frames_to_voxel_v2e(frames: torch.Tensor, pos_thres, neg_thres, *, fps: floa
     d.shot_noise_rate_hz, d.leak_jitter_fraction = float(shot_noise_rate_hz), float(leak_jitter_fraction)
     d.frames, d.lut = _ptr(frames), _ptr(lut_t)
     d.pos_thres, d.neg_thres, d.noise_rate = _ptr(pos_t), _ptr(neg_t), _ptr(nr_t)
+    d.thres_per_interval = int(per_interval)
     d.leak_randn, d.pos_shot, d.neg_shot = _ptr(lr_t), _ptr(ps_t), _ptr(ns_t)
     d.pos_thres_nominal, d.neg_thres_nominal = float(pos_thres_nominal), float(neg_thres_nominal)
     d.seed, d.clip_index_base = int(seed) & 0xFFFFFFFFFFFFFFFF, int(clip_index_base)
@@ -177,6 +183,12 @@ def video_to_voxel(video, FPS, threshold_model, thres_mean_mean, thres_mean_std,
     N, H, W = vid8.shape
     if seed is not None:                                                        # :312-314
         np.random.seed(seed)
+    per_frame = threshold_model == PER_FRAME_MODEL
+    if per_frame:
+        if rng != "numpy":
+            raise NotImplementedError("threshold_model 'spatial_temporal_independent' redraws two full-frame maps from the "
+                                      "NumPy stream before every frame: rng='numpy' only")
+        threshold_maps(threshold_model, thres_mean_mean, thres_mean_std, 0, 0, (H, W))     # :417-421 on frame 0 (then _init draws again)
     pos, neg = threshold_maps(threshold_model, thres_mean_mean, thres_mean_std, thres_diff_mean, thres_diff_std,
                               (H, W))
     nrate = noise_rate_map(noise_rate_cov_decades, (H, W))
@@ -185,17 +197,23 @@ def video_to_voxel(video, FPS, threshold_model, thres_mean_mean, thres_mean_std,
     kw = dict(noise="none")
     if rng == "numpy":
         leak_r = pos_s = neg_s = None
-        if leak_rate_hz > 0 or shot_noise_rate_hz > 0:
+        pos_f = np.empty((N - 1, H, W)) if per_frame else None
+        neg_f = np.empty((N - 1, H, W)) if per_frame else None
+        if leak_rate_hz > 0 or shot_noise_rate_hz > 0 or per_frame:
             leak_r = np.zeros((N - 1, H, W)) if leak_rate_hz > 0 else None
             if shot_noise_rate_hz > 0:
                 pos_s = np.zeros((N - 1, H, W), dtype=np.int32)
                 neg_s = np.zeros((N - 1, H, W), dtype=np.int32)
                 pos_pp, neg_pp = np.divide(pos_nom, pos), np.divide(neg_nom, neg)
             t_prev = 0.0
-            for k in range(1, N):                       # per-frame draw order: leak randn, poisson x2
+            for k in range(1, N):                       # per-frame draw order: (threshold maps,) leak randn, poisson x2
                 t_k = k / FPS
                 dt = t_k - t_prev
                 t_prev = t_k
+                if per_frame:                                                   # :417-421
+                    pos_f[k - 1], neg_f[k - 1] = threshold_maps(threshold_model, thres_mean_mean, thres_mean_std, 0, 0, (H, W))
+                    if shot_noise_rate_hz > 0:
+                        pos_pp, neg_pp = np.divide(pos_nom, pos_f[k - 1]), np.divide(neg_nom, neg_f[k - 1])
                 if leak_rate_hz > 0:
                     leak_r[k - 1] = np.random.randn(H, W)                       # :201
                 if shot_noise_rate_hz > 0:                                      # :90-103
@@ -219,6 +237,8 @@ def video_to_voxel(video, FPS, threshold_model, thres_mean_mean, thres_mean_std,
     if N < 2:
         return np.zeros((0, H, W))
     frames = torch.from_numpy(np.ascontiguousarray(vid8)).to(device)
+    if per_frame:
+        pos, neg = pos_f, neg_f
     out = frames_to_voxel_v2e(frames, pos[None], neg[None], fps=FPS, cutoff_hz=cutoff_hz, leak_rate_hz=leak_rate_hz,
                               shot_noise_rate_hz=shot_noise_rate_hz, leak_jitter_fraction=leak_jitter_fraction,
                               noise_rate=nrate[None], pos_thres_nominal=pos_nom, neg_thres_nominal=neg_nom,
