@@ -66,6 +66,7 @@ enum v2v_threshold_mode {
 #define V2V_ESIM_FLAG_GENERIC 1      /* always the generic kernel (esim.cu); tests compare the two paths bit for bit   */
 #define V2V_ESIM_FLAG_SMALL_FAST 2   /* launches below 148*2048 pixels: throughput kernel                             */
 #define V2V_ESIM_FLAG_SMALL_P1 4     /* launches below 148*2048 pixels: one pixel per thread                          */
+#define V2V_ESIM_FLAG_STAGED 16      /* noise-free throughput kernel: frames through a cp.async.bulk ring in shared memory (A/B)  */
 #define V2V_ESIM_FLAG_GEOM(g) (((g) & 0xf) << 8) /* CTA geometry index of the throughput kernel (tuning sweeps)       */
 
 typedef struct v2v_esim_desc {

@@ -443,6 +443,27 @@ def test_train_batch_shape_bit_exact_vs_c_oracle(cuda_device):
         assert st[0] == int(np.maximum(ref, 0).sum()) and st[1] == int(np.maximum(-ref, 0).sum())
 
 
+def test_staged_frame_ring_variant_is_bit_identical(cuda_device):
+    """The noise-free throughput kernel with its frames staged through shared memory by bulk async copies
+    (cp.async.bulk + mbarrier ring, V2V_ESIM_FLAG_STAGED) equals the per-lane LDG form bit for bit: full tiles, a ragged
+    last tile, statistics and ground-truth frames, interval counts that are not multiples of the ring depth."""
+    import v2v_b200 as v2v
+    lut = orc.esim_log_lut()
+    for (B, n, h, w) in ((3, 21, 480, 640), (2, 11, 72, 112), (1, 6, 480, 644)):
+        vids = np.stack([synth_video("walk", n, h, w, 500 + b) for b in range(B)])
+        fr = torch.from_numpy(vids).to(cuda_device)
+        u0 = torch.rand((B, h, w), dtype=torch.float64, device=cuda_device)
+        kw = dict(num_bins=5, u0=u0, lut=lut, with_stats=True, return_potential=True, frame_out="frames",
+                  kernel_flags=_lib.ESIM_FLAG_SMALL_FAST)
+        a = v2v.frames_to_voxel(fr, [0.21] * B, [0.17] * B, **kw)
+        kw["kernel_flags"] |= _lib.ESIM_FLAG_STAGED
+        b_ = v2v.frames_to_voxel(fr, [0.21] * B, [0.17] * B, **kw)
+        assert torch.equal(a.voxel, b_.voxel) and torch.equal(a.potential, b_.potential)
+        assert torch.equal(a.stats, b_.stats) and torch.equal(a.frames, b_.frames)
+        ref = orc.esim_video_to_voxel(vids[0], 0.21, 0.17, 0.0, u0[0].cpu().numpy(), np.zeros((h, w)), np.zeros((n - 1, h, w)), False, lut)
+        assert np.array_equal(b_.voxel[0].cpu().numpy().reshape(n - 1, h, w).astype(np.float64), ref)
+
+
 def test_noise_field_distribution_and_independence(cuda_device):
     """Statistical audit of the in-kernel generator (Philox-seeded 64-bit LCG streams + table Box-Muller) on the dumped
     base-noise field: moments, Kolmogorov distance to the normal law, tails, and the correlations the construction could

@@ -42,5 +42,5 @@ torch.cuda.synchronize()
 if a.time:
     ms = [x.elapsed_time(y) for x, y in evs]
     gb = a.clips * bench.ALGO_BYTES_PER_CLIP / 1e9
-    print(f"noise={a.noise} stats={int(a.stats)} clips={a.clips} geom={os.environ.get('V2V_ESIM_GEOM','default')} "
+    print(f"noise={a.noise} stats={int(a.stats)} clips={a.clips} geom={os.environ.get('V2V_ESIM_GEOM','default')} staged={os.environ.get('V2V_ESIM_STAGED','0')} "
           f"ms={np.min(ms[1:] or ms):.3f} GB/s={gb / (np.min(ms[1:] or ms) * 1e-3):.0f}")

@@ -46,7 +46,7 @@ class EsimDesc(C.Structure):
     ]
 
 
-ESIM_FLAG_GENERIC, ESIM_FLAG_SMALL_FAST, ESIM_FLAG_SMALL_P1 = 1, 2, 4
+ESIM_FLAG_GENERIC, ESIM_FLAG_SMALL_FAST, ESIM_FLAG_SMALL_P1, ESIM_FLAG_STAGED = 1, 2, 4, 16
 V2E_FLAG_GENERIC, V2E_FLAG_FAST, V2E_FLAG_DIVERGENT_DIV = 1, 2, 4
 
 

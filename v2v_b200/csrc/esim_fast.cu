@@ -79,6 +79,26 @@ __device__ __forceinline__ void single_cross_sel(double& x, float& ov, uint32_t&
   ov = dn ? -1.0f : ov;
 }
 
+// ---- bulk-copy frame ring (STAGED variants): cp.async.bulk + mbarrier, SASS UBLKCP / SYNCS ----------------------------
+constexpr int kRingDepth = 8;   // frame tiles in flight per CTA
+constexpr int kRingLag = 4;     // a slot is refilled kRingLag intervals after it was read (no warp waits for the slowest one)
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, int count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count)); }
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, int bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory"); }
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n .reg .pred p;\n WAIT_%=: mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n @p bra DONE_%=;\n bra WAIT_%=;\n DONE_%=:\n}" ::"r"(bar),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, int bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
+
 template <int NOISE, bool FRAMES, bool GATHER, int THREADS>
 struct FastSmem {
   static constexpr bool kPh = NOISE == V2V_NOISE_PHILOX;
@@ -88,10 +108,12 @@ struct FastSmem {
   static constexpr int f255 = hot + (kPh ? THREADS * 16 : 0);
   static constexpr int rcp = f255 + (FRAMES ? 256 * 4 : 0);
   static constexpr int fnum = rcp + 16;
-  static size_t bytes(int N) { return fnum + (GATHER ? static_cast<size_t>(N) * 4 : 0); }
+  static __host__ __device__ size_t bytes(int N) { return fnum + (GATHER ? static_cast<size_t>(N) * 4 : 0); }
+  static __host__ __device__ size_t ring(int N) { return (bytes(N) + 127) / 128 * 128; }                       // offset of the staged frame ring
+  static size_t bytes_staged(int N) { return ring(N) + static_cast<size_t>(kRingDepth) * THREADS * 4 + 16 * kRingDepth; }
 };
 
-template <int NOISE, bool FRAMES, bool STATS, bool GATHER, int THREADS, int CTAS>
+template <int NOISE, bool FRAMES, bool STATS, bool GATHER, int THREADS, int CTAS, bool STAGED = false>
 __global__ void __launch_bounds__(THREADS, CTAS) esim_fast_kernel(const EsimArgs a) {
   using L = FastSmem<NOISE, FRAMES, GATHER, THREADS>;
   constexpr bool kPh = NOISE == V2V_NOISE_PHILOX;
@@ -112,6 +134,17 @@ __global__ void __launch_bounds__(THREADS, CTAS) esim_fast_kernel(const EsimArgs
     for (int n = threadIdx.x; n < d.N; n += THREADS) fnum_s[n] = static_cast<uint32_t>(min(max(fidx[n], 0), a.Mraw - 1));
   }
   if (threadIdx.x < 2) cta_rcp[threadIdx.x] = __drcp_rn(threadIdx.x ? d.neg_thres[blockIdx.y] : d.pos_thres[blockIdx.y]);
+  const uint32_t ring_a = smem_base + static_cast<uint32_t>(L::ring(d.N));                 // STAGED: frame ring, then full / empty barriers
+  const uint32_t full_a = ring_a + kRingDepth * THREADS * 4, empty_a = full_a + 8 * kRingDepth;
+  if (STAGED && threadIdx.x == 0) {
+    const int64_t left = (a.HW - static_cast<int64_t>(blockIdx.x) * THREADS * 4 + 3) / 4;          // lanes of this tile that own pixels
+    const int warps = static_cast<int>((min(left, static_cast<int64_t>(THREADS)) + 31) / 32);
+    for (int q = 0; q < kRingDepth; ++q) {
+      mbar_init(full_a + 8 * q, 1);
+      mbar_init(empty_a + 8 * q, warps);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
   {
     const uint8_t* vmap = d.value_map ? d.value_map + static_cast<int64_t>(blockIdx.y) * 256 : nullptr;   // degrade folded into the LUTs
     for (int j = threadIdx.x; j < 256 * 4; j += THREADS) {     // a quarter row (8 copies) per task, two copies per 128-bit store
@@ -355,8 +388,41 @@ __global__ void __launch_bounds__(THREADS, CTAS) esim_fast_kernel(const EsimArgs
     }
   };
 
-  // ---- main loop: kPF frames per trip, the next trip's words already in flight ----
   const int M = N - 1;                       // intervals
+  if (STAGED) {
+    // ---- main loop, frames staged through shared memory: thread 0 keeps kRingDepth tiles of THREADS*4 bytes in flight
+    // with bulk async copies that complete on the slot's "full" mbarrier; a warp waits for the slot, reads its words with
+    // one LDS.32 per lane and releases the slot on its "empty" mbarrier; thread 0 refills a slot kRingLag intervals after
+    // it was read, when every warp of the tile has released it.  No frame word is held in registers across intervals and
+    // no lane computes a global address.
+    const int64_t tile0 = static_cast<int64_t>(blockIdx.x) * THREADS * 4;
+    const uint8_t* tile_src = d.frames + (static_cast<int64_t>(b) * a.Mraw) * HW + tile0;
+    const int tile_bytes = static_cast<int>(min(static_cast<int64_t>(THREADS) * 4, HW - tile0));
+    if (threadIdx.x == 0) {
+      for (int q = 0; q < kRingDepth && q < M; ++q) {
+        mbar_expect_tx(full_a + 8 * q, tile_bytes);
+        bulk_g2s(ring_a + q * THREADS * 4, tile_src + static_cast<int64_t>(1 + q) * HW, tile_bytes, full_a + 8 * q);
+      }
+    }
+#pragma unroll 4
+    for (int i = 0; i < M; ++i) {
+      const int q = i % kRingDepth;
+      mbar_wait(full_a + 8 * q, (i / kRingDepth) & 1);
+      uint32_t w;
+      asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w) : "r"(ring_a + q * THREADS * 4 + threadIdx.x * 4));
+      step(w);
+      if (STATS && (i & 31) == 31) flush_stats();
+      __syncwarp(full);
+      if ((threadIdx.x & 31) == 0) mbar_arrive(empty_a + 8 * q);
+      if (threadIdx.x == 0 && i >= kRingLag && i - kRingLag + kRingDepth < M) {
+        const int j = i - kRingLag, qj = j % kRingDepth;
+        mbar_wait(empty_a + 8 * qj, (j / kRingDepth) & 1);
+        mbar_expect_tx(full_a + 8 * qj, tile_bytes);
+        bulk_g2s(ring_a + qj * THREADS * 4, tile_src + static_cast<int64_t>(1 + j + kRingDepth) * HW, tile_bytes, full_a + 8 * qj);
+      }
+    }
+  } else {
+  // ---- main loop: kPF frames per trip, the next trip's words already in flight ----
   const int trips = M / kPF;
   uint32_t cur[kPF], nxt[kPF];
   if (trips > 0) {
@@ -377,6 +443,7 @@ __global__ void __launch_bounds__(THREADS, CTAS) esim_fast_kernel(const EsimArgs
     if (STATS && (t & (kFlushTrips - 1)) == kFlushTrips - 1) flush_stats();
   }
   for (; i < N; ++i) step(ld_stream_u32(frame_ptr(i)));               // ragged tail (< kPF intervals)
+  }
 
   if (d.potential_out) {
 #pragma unroll
@@ -395,22 +462,22 @@ __global__ void __launch_bounds__(THREADS, CTAS) esim_fast_kernel(const EsimArgs
 
 // cudaFuncAttributeMaxDynamicSharedMemorySize is a per-device attribute of each instantiation: set it on the first
 // launch on a device, not on every launch.
-template <int NOISE, bool FRAMES, bool STATS, bool GATHER, int THREADS, int CTAS>
+template <int NOISE, bool FRAMES, bool STATS, bool GATHER, int THREADS, int CTAS, bool STAGED = false>
 int launch_variant(const EsimArgs& a, cudaStream_t s) {
   using L = FastSmem<NOISE, FRAMES, GATHER, THREADS>;
   static std::atomic<uint64_t> configured{0};
   int dev = 0;
   V2V_CUDA(cudaGetDevice(&dev));
   const uint64_t bit = 1ull << (dev & 63);
-  const size_t smem = L::bytes(a.d.N);
+  const size_t smem = STAGED ? L::bytes_staged(a.d.N) : L::bytes(a.d.N);
   if (!(configured.load(std::memory_order_acquire) & bit)) {
-    V2V_CUDA(cudaFuncSetAttribute(esim_fast_kernel<NOISE, FRAMES, STATS, GATHER, THREADS, CTAS>,
+    V2V_CUDA(cudaFuncSetAttribute(esim_fast_kernel<NOISE, FRAMES, STATS, GATHER, THREADS, CTAS, STAGED>,
                                   cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     configured.fetch_or(bit, std::memory_order_release);
   }
   const int64_t groups = a.HW / 4;
   dim3 grid(static_cast<unsigned int>((groups + THREADS - 1) / THREADS), static_cast<unsigned int>(a.d.B));
-  esim_fast_kernel<NOISE, FRAMES, STATS, GATHER, THREADS, CTAS><<<grid, THREADS, smem, s>>>(a);
+  esim_fast_kernel<NOISE, FRAMES, STATS, GATHER, THREADS, CTAS, STAGED><<<grid, THREADS, smem, s>>>(a);
   count_launch();
   V2V_CUDA(cudaGetLastError());
   return V2V_OK;
@@ -453,6 +520,13 @@ int launch_esim_fast(const EsimArgs& a, cudaStream_t s) {
       case 3: return launch_geom<V2V_NOISE_PHILOX, 768, 1>(a, s);
       default: return launch_geom<V2V_NOISE_PHILOX, 384, 2>(a, s);
     }
+  }
+  // frames through a bulk-copy ring in shared memory (cp.async.bulk + mbarrier) instead of per-lane LDG: A/B in
+  // profiles/r02_esim_experiments.md; needs 16-byte aligned tiles
+  if ((a.d.kernel_flags & V2V_ESIM_FLAG_STAGED) && geom == 0 && !a.d.frame_index && a.HW % 16 == 0 && aligned(a.d.frames, 16)) {
+    const bool fr = a.d.frame_out_mode != 0, st = a.d.stats != nullptr;
+    if (fr) return st ? launch_variant<V2V_NOISE_NONE, true, true, false, 512, 2, true>(a, s) : launch_variant<V2V_NOISE_NONE, true, false, false, 512, 2, true>(a, s);
+    return st ? launch_variant<V2V_NOISE_NONE, false, true, false, 512, 2, true>(a, s) : launch_variant<V2V_NOISE_NONE, false, false, false, 512, 2, true>(a, s);
   }
   switch (geom) {
     case 1: return launch_geom<V2V_NOISE_NONE, 320, 3>(a, s);

@@ -246,6 +246,8 @@ def _env_kernel_flags() -> int:
         f |= _lib.esim_flag_geom(int(g))
     if os.environ.get("V2V_ESIM_GENERIC") == "1":
         f |= _lib.ESIM_FLAG_GENERIC
+    if os.environ.get("V2V_ESIM_STAGED") == "1":
+        f |= _lib.ESIM_FLAG_STAGED
     return f
 
 
