@@ -142,6 +142,9 @@ int v2v_rng_words(const uint32_t counter[4], const uint32_t key[2], uint32_t* ph
 #define V2V_V2E_FLAG_GENERIC 1       /* always the generic kernel (v2e.cu)                                          */
 #define V2V_V2E_FLAG_FAST 2          /* throughput kernel also below 148*2048 pixels per launch                     */
 #define V2V_V2E_FLAG_DIVERGENT_DIV 4 /* throughput kernel: single-crossing fast path + divergent exact division     */
+#define V2V_V2E_FLAG_U8_INTENSITY 8 /* NOT a tuning flag: the caller's video was a uint8 array, so rescale_intensity_frame
+                                       (data/v2v_core_v2e.py:190) computed new_frame+20 in uint8 and wrapped for values >= 236:
+                                       inten01 = ((v+20) & 255)/275.  Without it (float video) inten01 = (v+20)/275.     */
 
 typedef struct v2v_v2e_desc {
   int32_t B, N, H, W;
@@ -167,7 +170,7 @@ typedef struct v2v_v2e_desc {
   /* optional fused frame-side packing, as in v2v_esim_desc (pause gather + HDR/LDR degrade of the dataset) */
   const int32_t* frame_index;    /* [B,N] raw frame used as frame n (clamped to the clip), or NULL = identity            */
   int32_t raw_frames_per_clip;   /* frames per clip in `frames` when frame_index is given; 0 = N                         */
-  int32_t kernel_flags;          /* 0 = library's choice; V2V_V2E_FLAG_* (tests and tuning: kernel selection never changes results) */
+  int32_t kernel_flags;          /* 0 = library's choice; V2V_V2E_FLAG_* (kernel selection never changes results; U8_INTENSITY selects the reference's uint8 arithmetic) */
   const uint8_t* value_map;      /* [B,256] uint8 -> uint8 applied to every pixel before any use of its value, or NULL   */
   int32_t thres_per_interval;    /* 1: pos_thres / neg_thres are [B,N-1,H,W], the maps in force at frame i = interval i-1
                                   * (threshold_model "spatial_temporal_independent", data/v2v_core_v2e.py:417-421; noise_mode
@@ -246,6 +249,12 @@ typedef struct v2v_scatter_desc {
 #define V2V_SCATTER_FLAG_RANGES 1        /* interpolated mode: contiguous-range kernel even when the workspace allows the one-visit path */
 #define V2V_SCATTER_FLAG_GENERIC_SCAN 2  /* never take the 16-bit coordinate scan                                                       */
 #define V2V_SCATTER_FLAG_NO_PACKED16 4   /* discrete mode: 32-bit instead of packed 16-bit counters                                      */
+
+/* Accumulation is integer and order independent.  Discrete h5 mode: exact for any count (packed 16-bit counters while a bin
+ * holds <= 32767 events, 32-bit counters otherwise).  Interpolated h5 mode: weights are rounded to 2^-30 once
+ * (|error| <= n * 2^-31 per cell, n = events on that cell, bin and window; 2^-24 per event for work items of <= 255 events);
+ * items that could put more than 65535 events on one cell switch to one 64-bit word per cell, so there is no count at which
+ * a cell overflows.  Torch modes: float32 atomics (the reference is a sequential float32 sum). */
 
 /* Bytes of `workspace` that enable every path for this descriptor (sizes and mode are read; pointers are not). */
 int64_t v2v_scatter_workspace_bytes(const v2v_scatter_desc* desc);

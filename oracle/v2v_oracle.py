@@ -194,8 +194,9 @@ def v2e_video_to_voxel(video, fps, params, rs=np.random, lut=None, record=None, 
 
     Restates video_to_voxel / EventEmulator.generate_events
     (data/v2v_core_v2e.py:401-581).  ``video`` is [N,H,W] with integer values
-    0..255 held in float64 (uint8 input wraps in ``(x+20)/275``, SURVEY §4, so
-    callers convert first).  ``params`` keys: threshold_model, thres_mean_mean,
+    0..255; a uint8 array takes the reference's uint8 arithmetic in
+    ``rescale_intensity_frame`` (:190: ``new_frame+20`` wraps for values >= 236), any other dtype is
+    converted to float64 first (no wrap).  ``params`` keys: threshold_model, thres_mean_mean,
     thres_mean_std, thres_diff_mean, thres_diff_std, cutoff_hz, leak_rate_hz,
     shot_noise_rate_hz, leak_jitter_fraction, noise_rate_cov_decades
     (refractory_period_s must be 0: the reference's branch raises TypeError).
@@ -242,7 +243,7 @@ def v2e_video_to_voxel(video, fps, params, rs=np.random, lut=None, record=None, 
         log_new = lut[vid_idx[k]]                                     # float32, :447
         inten01 = None
         if cutoff > 0 or shot_hz > 0:
-            inten01 = (frame + 20) / 275.                             # :455,190
+            inten01 = (((vid_idx[k] + 20) & 255) if video.dtype == np.uint8 else (frame + 20)) / 275.   # :455,190
         if base is None:
             lp = log_new                                              # :463-465
         if cutoff > 0:                                                # :157-173

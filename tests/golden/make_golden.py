@@ -187,11 +187,18 @@ def gen_v2e(v2e, out):
     lut = orc.v2e_log_lut()
     k = 0
     for preset, params in V2E_PRESETS.items():
-        for kind, n, h, w in (("walk", 11, 12, 16), ("iid", 6, 9, 7)):
-            seed = 40 + k
-            k += 1
-            video8 = hdr_degrade(synth_video(kind, n, h, w, 300 + seed), 2.1)
+        kinds = [("walk", 11, 12, 16), ("iid", 6, 9, 7)]
+        if preset in ("noisy", "cutoff_only", "shot_only"):
+            kinds.append(("u8", 9, 10, 12))
+        for kind, n, h, w in kinds:
+            seed = 40 + k if kind != "u8" else 140 + k
+            k += kind != "u8"
+            video8 = hdr_degrade(synth_video("walk" if kind == "u8" else kind, n, h, w, 300 + seed), 2.1)
             video = video8.astype(np.float64)
+            if kind == "u8":
+                # uint8 handed to the reference as is: rescale_intensity_frame (:190) wraps for values >= 236
+                video = video8
+                assert (video8 >= 236).mean() > 0.02
             ref = v2e.video_to_voxel(video, 24, refractory_period_s=0, seed=seed, **params)
             rec = {}
             np.random.seed(seed)
@@ -202,7 +209,7 @@ def gen_v2e(v2e, out):
                 assert same(ref, again)
             # lin_log LUT identity
             assert same(v2e.lin_log(video[0]), lut[video8[0]])
-            d = dict(video=video8, fps=24, seed=seed, lut=lut, ref=ref,
+            d = dict(video=video8, fps=24, seed=seed, lut=lut, ref=ref, u8_input=int(kind == "u8"),
                      thr_a=rec["thr_a"], thr_b=rec["thr_b"], noise_randn=rec["noise_randn"],
                      pos_thres=rec["pos_thres"], neg_thres=rec["neg_thres"], noise_rate=rec["noise_rate"],
                      threshold_model=np.array(params["threshold_model"]))

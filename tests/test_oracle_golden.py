@@ -69,14 +69,15 @@ def test_v2e(name):
     c = golden("v2e").case(name)
     p = v2e_params(c)
     np.random.seed(int(c["seed"]))
-    out = orc.v2e_video_to_voxel(c["video"].astype(np.float64), int(c["fps"]), p, np.random, lut=c["lut"])
+    video = c["video"] if int(c.get("u8_input", 0)) else c["video"].astype(np.float64)   # uint8 input: wrapping inten01
+    out = orc.v2e_video_to_voxel(video, int(c["fps"]), p, np.random, lut=c["lut"])
     assert same(out, c["ref"])
     if p["threshold_model"] == "spatial_temporal_independent":      # (the replay helper covers the time-invariant models)
         return
     fields = {k: c[k] for k in ("thr_a", "thr_b", "noise_randn")}
     for k in ("leak_randn", "pos_shot", "neg_shot"):
         fields[k] = list(c[k]) if k in c else []
-    assert same(orc.v2e_replay(c["video"].astype(np.float64), int(c["fps"]), p, fields, lut=c["lut"]), c["ref"])
+    assert same(orc.v2e_replay(video, int(c["fps"]), p, fields, lut=c["lut"]), c["ref"])
 
 
 @pytest.mark.parametrize("name", golden("scatter").names("scat_mv_"))

@@ -295,6 +295,32 @@ def test_interp_paths_agree_and_take_any_event_order(cuda_device):
         assert np.allclose(u[k].cpu().numpy(), orc.make_voxel(tsu[s], xsu[s], ysu[s], psu[s], 5, h, w, True), **TOL)
 
 
+def test_interp_hot_pixel_beyond_the_two_word_range(cuda_device):
+    """300 k same-sign events on ONE pixel of one window, 3 bins: the middle bin's cell sums ~150 k unit weights, more than
+    the two 32-bit fixed-point words of a cell hold (65535).  Both interpolated kernels must switch that item to the
+    64-bit accumulator and stay within n * 2^-31 of the reference (data/testh5.py:74-80)."""
+    import v2v_b200 as v2v
+    from v2v_b200 import _lib
+    h, w, ne = 40, 64, 320_000
+    g = np.random.Generator(np.random.PCG64(21))
+    xs = g.integers(0, w, ne).astype(np.uint16)
+    ys = g.integers(0, h, ne).astype(np.uint16)
+    hot = g.random(ne) < 0.94
+    xs[hot], ys[hot] = 11, 17
+    ts = np.sort(g.random(ne)) * 0.5 + 3.0
+    ps = (g.random(ne) < 0.5).astype(np.uint8)
+    ps[hot] = 0                                           # negative hot pixel: the sign path of the wide form
+    off = np.array([0, ne], dtype=np.int64)
+    ref = orc.make_voxel(ts, xs, ys, ps, 3, h, w, True)
+    assert np.abs(ref).max() > 100_000
+    for flags in (0, _lib.SCATTER_FLAG_RANGES):
+        got = v2v.voxelize_windows(xs, ys, ts, ps, off, 3, h, w, mode="h5_interp", out_dtype=torch.float64,
+                                   kernel_flags=flags)[0].cpu().numpy()
+        assert np.abs(got - ref).max() < 2e-4, (flags, np.abs(got - ref).max())
+    got32 = v2v.make_voxel([ts, xs, ys, ps], 3, h, w, True)
+    assert np.allclose(got32, ref, rtol=1e-6, atol=1e-3)
+
+
 def test_unsorted_windows_raise_in_contiguous_range_modes(cuda_device):
     """The discrete and torch modes assign bins as contiguous ranges: unsorted timestamps must not silently mis-bin.
     The device-side check (default on) raises; a decrease exactly at a window boundary is legitimate."""

@@ -32,7 +32,8 @@ def test_v2e_golden_replay(cuda_device, name):
         neg_thres_nominal=p["thres_mean_mean"] - p["thres_diff_mean"] / 2, noise="explicit",
         leak_randn=c["leak_randn"][None] if "leak_randn" in c else None,
         pos_shot=c["pos_shot"][None] if "pos_shot" in c else None,
-        neg_shot=c["neg_shot"][None] if "neg_shot" in c else None, lut=c["lut"], with_stats=True)
+        neg_shot=c["neg_shot"][None] if "neg_shot" in c else None, lut=c["lut"], with_stats=True,
+        u8_intensity=bool(int(c.get("u8_input", 0))))
     got = out["voxel"][0, :, 0].cpu().numpy().astype(np.float64)
     assert np.array_equal(got, c["ref"])
 
@@ -43,7 +44,8 @@ def test_v2e_reference_signature_same_seed(cuda_device, name):
     from v2v_b200.v2e import video_to_voxel
     c = golden("v2e").case(name)
     p = params_of(c)
-    got = video_to_voxel(c["video"].astype(np.float64), int(c["fps"]), refractory_period_s=0, seed=int(c["seed"]),
+    video = c["video"] if int(c.get("u8_input", 0)) else c["video"].astype(np.float64)
+    got = video_to_voxel(video, int(c["fps"]), refractory_period_s=0, seed=int(c["seed"]),
                          rng="numpy", lut=c["lut"], **p)
     assert got.dtype == np.float64 and np.array_equal(got, c["ref"])
 

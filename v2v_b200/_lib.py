@@ -47,7 +47,7 @@ class EsimDesc(C.Structure):
 
 
 ESIM_FLAG_GENERIC, ESIM_FLAG_SMALL_FAST, ESIM_FLAG_SMALL_P1, ESIM_FLAG_STAGED = 1, 2, 4, 16
-V2E_FLAG_GENERIC, V2E_FLAG_FAST, V2E_FLAG_DIVERGENT_DIV = 1, 2, 4
+V2E_FLAG_GENERIC, V2E_FLAG_FAST, V2E_FLAG_DIVERGENT_DIV, V2E_FLAG_U8_INTENSITY = 1, 2, 4, 8
 
 
 def esim_flag_geom(g: int) -> int:

@@ -174,6 +174,9 @@ __global__ void __launch_bounds__(kScatterThreads, 2) scatter_kernel(const Scatt
     // h5 discrete: packed 16-bit counters (two cells per word, biased by 0x8000) are exact whenever the bin holds
     // at most 32767 events; otherwise the strip is done as two half-height passes with 32-bit counters
     const bool packed = MODE == V2V_SCATTER_H5_DISCRETE && a.packed16 && (hi - lo) <= 32767;
+    // h5 interpolated: the two 32-bit words of a cell hold up to 65535 same-sign unit weights; a range that could exceed
+    // that (a hot pixel in a multi-million-event window) accumulates in ONE 64-bit word per cell instead (same footprint)
+    const bool wide = MODE == V2V_SCATTER_H5_INTERP && (hi - lo) > 65535;
     const int passes = (MODE == V2V_SCATTER_H5_DISCRETE && a.packed16 && !packed) ? 2 : 1;
     const int strip_r0 = r0, strip_rows = rows;
     for (int pass = 0; pass < passes; ++pass) {
@@ -372,7 +375,9 @@ __global__ void __launch_bounds__(kScatterThreads, 2) scatter_kernel(const Scatt
           if (MODE == V2V_SCATTER_H5_INTERP) {
             const double wgt = fmax(0.0, __dsub_rn(1.0, fabs(__dsub_rn(tnd, static_cast<double>(bin)))));   // testh5.py:79
             const long long fx = __double2ll_rn(__dmul_rn(wgt * static_cast<double>(pw), 1073741824.0));
-            if (fx != 0) {
+            if (wide) {
+              if (fx != 0) atomicAdd(reinterpret_cast<unsigned long long*>(acc_i) + cell, static_cast<unsigned long long>(fx));
+            } else if (fx != 0) {
               const int hiw = static_cast<int>(fx >> kLoBits);
               const unsigned int low = static_cast<unsigned int>(fx & ((1 << kLoBits) - 1));
               if (hiw) atomicAdd(&acc_i[cell], hiw);
@@ -397,8 +402,9 @@ __global__ void __launch_bounds__(kScatterThreads, 2) scatter_kernel(const Scatt
       const int64_t out_base = ((static_cast<int64_t>(vwin) * B + bin) * H + r0) * W;
       auto value = [&](int i) -> double {          // float64 outputs (drop-in make_voxel)
         if (kInterp) {
-          const long long tot = static_cast<long long>(acc_i[i]) * (1 << kLoBits) +
-                                static_cast<long long>(reinterpret_cast<unsigned int*>(acc_lo)[i]);
+          const long long tot = wide ? reinterpret_cast<const long long*>(acc_i)[i]
+                                     : static_cast<long long>(acc_i[i]) * (1 << kLoBits) +
+                                       static_cast<long long>(reinterpret_cast<unsigned int*>(acc_lo)[i]);
           return static_cast<double>(tot) * (1.0 / 1073741824.0);
         }
         if (packed) return static_cast<double>(static_cast<int>((static_cast<unsigned int>(acc_i[i >> 1]) >> ((i & 1) * 16)) & 0xffffu) - 32768);
@@ -406,6 +412,7 @@ __global__ void __launch_bounds__(kScatterThreads, 2) scatter_kernel(const Scatt
       };
       auto valuef = [&](int i) -> float {          // float32 outputs: stay off the conversion unit where possible
         if (kInterp) {
+          if (wide) return static_cast<float>(static_cast<double>(reinterpret_cast<const long long*>(acc_i)[i]) * (1.0 / 1073741824.0));
           const int h = acc_i[i];
           const unsigned int l = reinterpret_cast<unsigned int*>(acc_lo)[i];
           if ((static_cast<unsigned int>(h) | l) == 0u) return 0.f;                   // most cells of a strip hold no event

@@ -322,6 +322,10 @@ __global__ void __launch_bounds__(kItemThreads, 8) scatter_sorted_kernel(const S
     // 2^23 < 2^31; error <= n_cell * 2^-24 per cell): two shared atomics per event instead of four and half the tile to
     // zero and read.  Larger items (hot rows, long windows) keep the exact two-word form.
     const bool one_word = s1 - s0 <= 255u;
+    // ... and an item with more than 65535 records could overflow the two-word form (65536 same-sign unit weights on one
+    // cell): it accumulates in ONE 64-bit word per cell instead, same footprint, exact for any count
+    const bool wide = s1 - s0 > 65535u;
+    unsigned long long* acc64 = reinterpret_cast<unsigned long long*>(smem_raw);
     {
       int4* z = reinterpret_cast<int4*>(smem_raw);
       const int n4 = ((one_word ? 1 : 2) * B * plane + 3) / 4;
@@ -340,6 +344,11 @@ __global__ void __launch_bounds__(kItemThreads, 8) scatter_sorted_kernel(const S
         continue;
       }
       const long long f1 = static_cast<long long>(rec.y), f0 = 1073741824ll - f1;   // 2^-30 units
+      if (wide) {
+        if (b0 >= 0 && f0 != 0) atomicAdd(&acc64[b0 * plane + cell], static_cast<unsigned long long>(negp ? -f0 : f0));
+        if (b0 + 1 < B && f1 != 0) atomicAdd(&acc64[(b0 + 1) * plane + cell], static_cast<unsigned long long>(negp ? -f1 : f1));
+        continue;
+      }
       if (b0 >= 0 && f0 != 0) {
         const long long fx = negp ? -f0 : f0;
         const int hiw = static_cast<int>(fx >> kLoBits);
@@ -361,6 +370,7 @@ __global__ void __launch_bounds__(kItemThreads, 8) scatter_sorted_kernel(const S
       const int* h = acc_hi + b * plane;
       const unsigned int* l = acc_lo + b * plane;
       auto valuef = [&](int i) -> float {
+        if (wide) return static_cast<float>(static_cast<double>(static_cast<long long>(acc64[b * plane + i])) * (1.0 / 1073741824.0));
         const int hv = h[i];
         if (one_word) return hv == 0 ? 0.f : __fmul_rn(static_cast<float>(hv), 1.0f / 8388608.0f);
         const unsigned int lv = l[i];
@@ -371,7 +381,9 @@ __global__ void __launch_bounds__(kItemThreads, 8) scatter_sorted_kernel(const S
       if (d.out_dtype == V2V_F64) {
         double* o = static_cast<double*>(d.voxel) + ob;
         for (int i = threadIdx.x; i < cells; i += kItemThreads) {
-          if (one_word) {
+          if (wide) {
+            o[i] = static_cast<double>(static_cast<long long>(acc64[b * plane + i])) * (1.0 / 1073741824.0);
+          } else if (one_word) {
             o[i] = static_cast<double>(h[i]) * (1.0 / 8388608.0);
           } else {
             const long long tot = static_cast<long long>(h[i]) * (1 << kLoBits) + static_cast<long long>(l[i]);

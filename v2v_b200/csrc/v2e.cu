@@ -39,7 +39,7 @@ __global__ void __launch_bounds__(kV2eThreads) v2e_kernel(const V2eArgs a) {
   for (int i = threadIdx.x; i < 256; i += kV2eThreads) {
     const int mv = v2e_mapped(a, blockIdx.y, i);                  // the degrade is a function of the pixel value: folded into the LUTs
     L.logv[i] = d.lut[mv];
-    const double it = __ddiv_rn(__dadd_rn(static_cast<double>(mv), 20.0), 275.0);
+    const double it = v2e_inten01(a, mv);
     L.inten[i] = it;
     L.facf[i] = static_cast<float>(__dsub_rn(1.0, __dmul_rn(0.75, it)));
   }
@@ -237,7 +237,7 @@ __global__ void __launch_bounds__(256) v2e_shot_accum_kernel(const V2eArgs a, lo
   __shared__ unsigned long long sacc[8][2][kShotChunk];      // one row per warp: lane 0 adds without atomics
   const v2v_v2e_desc& d = a.d;
   const int b = blockIdx.y;
-  for (int i = threadIdx.x; i < 256; i += 256) fac_s[i] = 1.0 - 0.75 * ((static_cast<double>(v2e_mapped(a, b, i)) + 20.0) / 275.0);
+  for (int i = threadIdx.x; i < 256; i += 256) fac_s[i] = __dsub_rn(1.0, __dmul_rn(0.75, v2e_inten01(a, v2e_mapped(a, b, i))));
   const bool vec = (a.HW % 4 == 0) && aligned_dev(d.frames, 4);
   const int M = d.N - 1;
   for (int c0 = 0; c0 < M; c0 += kShotChunk) {
@@ -369,7 +369,7 @@ __global__ void v2e_philox_fields_kernel(const V2eArgs a, double* leak_randn, in
     if (leak_randn) leak_randn[o] = static_cast<double>(lz[j]);
     if (shot && pos_shot && neg_shot) {
       const uint32_t v = v2e_mapped(a, b, d.frames[(static_cast<int64_t>(b) * a.Mraw + v2e_frame_number(a, b, i)) * a.HW + pix]);
-      const double it = __ddiv_rn(__dadd_rn(static_cast<double>(v), 20.0), 275.0);
+      const double it = v2e_inten01(a, static_cast<int>(v));
       const float fac = static_cast<float>(__dsub_rn(1.0, __dmul_rn(0.75, it)));
       const int64_t si = static_cast<int64_t>(b) * (d.N - 1) + (i - 1);
       pos_shot[o] = poisson_small(v2e_shot_lambda(fac, ppf, v2e_scale_f32(d.shot_pos_scale[si])), up[j]);

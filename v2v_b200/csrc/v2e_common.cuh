@@ -23,6 +23,12 @@ __device__ __forceinline__ int v2e_frame_number(const V2eArgs& a, int b, int n) 
 __device__ __forceinline__ int v2e_mapped(const V2eArgs& a, int b, int v) {
   return a.d.value_map ? a.d.value_map[static_cast<int64_t>(b) * 256 + v] : v;
 }
+// rescale_intensity_frame (:190) of the mapped pixel value: (v+20)/275 in float64, or in the caller's uint8 arithmetic
+// (v+20 wraps for v >= 236) when the video handed to the reference was a uint8 array
+__device__ __forceinline__ double v2e_inten01(const V2eArgs& a, int mv) {
+  const int w = (a.d.kernel_flags & V2V_V2E_FLAG_U8_INTENSITY) ? ((mv + 20) & 255) : (mv + 20);
+  return __ddiv_rn(static_cast<double>(w), 275.0);
+}
 
 // np.floor_divide(max(diff,0), thr) for a >= thr > 0 (the caller filters a < thr); the reciprocal is only
 // needed on the multi-threshold path

@@ -90,7 +90,7 @@ __global__ void __launch_bounds__(kThreads, 4) v2e_fast_kernel(const V2eArgs a) 
   if (LEAK && PHILOX) fill_trig_table(trig_s);
   for (int i = threadIdx.x; i < 256; i += kThreads) {
     const int mv = v2e_mapped(a, b, i);                                                // degrade folded into the LUTs
-    const double it = __ddiv_rn(__dadd_rn(static_cast<double>(mv), 20.0), 275.0);      // :190
+    const double it = v2e_inten01(a, mv);                                              // :190
     lut2[i] = make_double2(static_cast<double>(d.lut[mv]), it);
     facf_s[i] = static_cast<float>(__dsub_rn(1.0, __dmul_rn(0.75, it)));              // :90
     logf_s[i] = d.lut[mv];

@@ -131,6 +131,8 @@ def voxelize_windows(xs, ys, ts, ps, window_offsets, num_bins: int, height: int,
     work = torch.empty((int(_lib.load().v2v_scatter_workspace_bytes(C.byref(d))) + 15) // 16 * 2, dtype=torch.int64, device=dev)
     d.workspace, d.workspace_bytes = _ptr(work), work.numel() * 8
     s = stream if stream is not None else torch.cuda.current_stream(dev)
+    if stream is not None:       # conversions, counters and H2D copies above were enqueued on the current stream
+        stream.wait_stream(torch.cuda.current_stream(dev))
     with torch.cuda.device(dev):
         _lib.check(_lib.load().v2v_events_to_voxel(C.byref(d), C.c_void_p(s.cuda_stream)))
     for t in (xs_t, ys_t, ts_t, ps_t, off_t, work, counters):

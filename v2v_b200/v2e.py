@@ -75,8 +75,11 @@ def frames_to_voxel_v2e(frames: torch.Tensor, pos_thres, neg_thres, *, fps: floa
                         pos_thres_nominal: float = 0.2, neg_thres_nominal: float = 0.2, noise: str = "none",
                         leak_randn=None, pos_shot=None, neg_shot=None, seed: int = 0, clip_index_base: int = 0,
                         with_stats: bool = False, lut: Optional[np.ndarray] = None,
-                        return_fields: bool = False, frame_index=None, value_map=None) -> dict:
+                        return_fields: bool = False, frame_index=None, value_map=None,
+                        u8_intensity: bool = False) -> dict:
     """CUDA uint8 ``[B,N,H,W]`` + per-pixel threshold maps ``[B,H,W]`` -> float32 ``[B,T,bins,H,W]``.
+    ``u8_intensity``: the reference was handed a uint8 video, so its ``rescale_intensity_frame``
+    (data/v2v_core_v2e.py:190) wrapped ``new_frame+20`` for values >= 236 (affects the low-pass and shot noise only).
     ``frame_index`` int32 ``[B,N]`` / ``value_map`` uint8 ``[B,256]``: the dataset's pause gather and HDR/LDR degrade fused
     into the pass, as in ``frames_to_voxel`` (``frames`` is then the raw stack ``[B,M,H,W]``)."""
     if frames.dim() == 3:
@@ -137,7 +140,7 @@ def frames_to_voxel_v2e(frames: torch.Tensor, pos_thres, neg_thres, *, fps: floa
     d.seed, d.clip_index_base = int(seed) & 0xFFFFFFFFFFFFFFFF, int(clip_index_base)
     d.voxel, d.stats = _ptr(vox), _ptr(stats_t)
     d.frame_index, d.raw_frames_per_clip, d.value_map = _ptr(fidx_t), (M if fidx_t is not None else 0), _ptr(vmap_t)
-    d.kernel_flags = _env_kernel_flags()
+    d.kernel_flags = _env_kernel_flags() | (_lib.V2E_FLAG_U8_INTENSITY if u8_intensity else 0)
     s = torch.cuda.current_stream(dev)
     lib = _lib.load()
     scales = None
@@ -162,7 +165,9 @@ def video_to_voxel(video, FPS, threshold_model, thres_mean_mean, thres_mean_std,
                    cutoff_hz, leak_rate_hz, refractory_period_s, shot_noise_rate_hz, leak_jitter_fraction,
                    noise_rate_cov_decades, seed, *, rng: str = "numpy", device="cuda", lut=None):
     """Same contract as the reference's ``video_to_voxel`` (data/v2v_core_v2e.py:556-581):
-    ``video`` ``[N,H,W]`` with integer values 0..255 -> float64 ``[N-1,H,W]``.
+    ``video`` ``[N,H,W]`` with integer values 0..255 -> float64 ``[N-1,H,W]``.  Like the reference, a uint8 array takes
+    uint8 arithmetic in ``rescale_intensity_frame`` (:190: ``new_frame+20`` wraps for values >= 236, which changes the
+    low-pass constant and the shot-noise rate of bright pixels); any other dtype does not wrap.
 
     rng="numpy": every random field is drawn from the global legacy NumPy stream
     in the reference's order (seeded by ``seed`` exactly like the reference's
@@ -174,7 +179,8 @@ def video_to_voxel(video, FPS, threshold_model, thres_mean_mean, thres_mean_std,
         raise TypeError("refractory_period_s > 0: the reference's branch calls np.clip(x, a_max=...) "
                         "and raises TypeError (SURVEY §4); not implemented")
     vid = np.asarray(video)
-    if vid.dtype != np.uint8:
+    u8 = vid.dtype == np.uint8
+    if not u8:
         if not np.array_equal(vid, np.clip(np.rint(vid), 0, 255)):
             raise ValueError("video must hold integer values in 0..255")
         vid8 = vid.astype(np.uint8)
@@ -217,7 +223,7 @@ def video_to_voxel(video, FPS, threshold_model, thres_mean_mean, thres_mean_std,
                 if leak_rate_hz > 0:
                     leak_r[k - 1] = np.random.randn(H, W)                       # :201
                 if shot_noise_rate_hz > 0:                                      # :90-103
-                    inten01 = (vid8[k].astype(np.float64) + 20) / 275.
+                    inten01 = ((vid8[k] + np.uint8(20)) if u8 else (vid8[k].astype(np.float64) + 20)) / 275.
                     fac = 1 - (1 - 0.25) * inten01
                     pf = fac * pos_pp
                     pf = pf / np.mean(pf)
@@ -242,5 +248,5 @@ def video_to_voxel(video, FPS, threshold_model, thres_mean_mean, thres_mean_std,
     out = frames_to_voxel_v2e(frames, pos[None], neg[None], fps=FPS, cutoff_hz=cutoff_hz, leak_rate_hz=leak_rate_hz,
                               shot_noise_rate_hz=shot_noise_rate_hz, leak_jitter_fraction=leak_jitter_fraction,
                               noise_rate=nrate[None], pos_thres_nominal=pos_nom, neg_thres_nominal=neg_nom,
-                              lut=lut, **kw)
+                              lut=lut, u8_intensity=u8, **kw)
     return out["voxel"][0, :, 0].to(torch.float64).cpu().numpy()
