@@ -24,11 +24,15 @@
 // event, against 4 bytes per voxel cell written once.
 #include "scatter_common.cuh"
 
+#include <type_traits>
+
 namespace v2v {
 namespace {
 
-constexpr int kChunk = 2048;          // events per CTA in the count / fill passes
-constexpr int kSortThreads = 256;
+constexpr int kSortThreads = 512;
+constexpr int kPer = 8;                        // events per thread of the sort pass (all loads issued before any arithmetic)
+constexpr int kChunk = kSortThreads * kPer;    // events per CTA of the sort pass
+constexpr int kMaxCounters = 2048;             // (window, strip) counters of one pass over a chunk (8 KB of shared memory)
 constexpr int kItemThreads = 256;
 constexpr int kTileBudget = 28 * 1024;    // eight CTAs per SM: an item is short (~200 records), its latency is hidden across CTAs
 
@@ -38,11 +42,21 @@ struct SortedArgs {
   uint32_t r_magic;       // y / R == (y * r_magic) >> 32 for y < 65536
   int64_t items;          // Wn * S
   WinConst* wcs;          // [Wn]
-  uint32_t* counts;       // [items]
-  uint32_t* cursor;       // [items + 1]: exclusive prefix (segment starts), advanced by the fill pass
-  uint32_t* starts;       // [items + 1]: exclusive prefix, kept
-  uint2* records;         // [Ne]
+  int32_t* chunk_w0;      // [chunks + 1]: window of the chunk's first event (written per window, no search); [chunks] = Wn - 1
+  int32_t* win_w0f;       // [Wn]: chunk_w0 of the chunk that holds the window's first event
+  int64_t chunks;
+  uint16_t* tab;          // per chunk c, at (c + w0[c]) * S + c: exclusive offsets of its (window - w0, strip) runs, then the total
+  uint2* records;         // [Ne]: chunk c's records, sorted by (window, strip), at [c * kChunk, c * kChunk + total)
 };
+
+__device__ __forceinline__ int first_window_of(const v2v_scatter_desc& d, int64_t e) {     // last window with start <= e
+  int lo = 0, hi = d.num_windows;
+  while (hi - lo > 1) {
+    const int mid = (lo + hi) >> 1;
+    if (d.window_offsets[mid] <= e) lo = mid; else hi = mid;
+  }
+  return lo;
+}
 
 __global__ void window_constants_kernel(const SortedArgs a) {
   const int w = blockIdx.x * blockDim.x + threadIdx.x;
@@ -54,128 +68,123 @@ __global__ void window_constants_kernel(const SortedArgs a) {
   c.t_first = c.t_span = c.t_tpb = 0.f;
   if (e1 > e0) {
     c = window_constants<V2V_SCATTER_H5_INTERP>(a.d, e0, e1);
-    c.h5_den = __ddiv_rn(static_cast<double>(a.d.num_bins - 1), c.h5_den);       // the fill pass multiplies
+    c.h5_den = __ddiv_rn(static_cast<double>(a.d.num_bins - 1), c.h5_den);       // the sort pass multiplies
     if (a.d.ts_dtype == V2V_F64) c.h5_tpb = static_cast<const double*>(a.d.ts)[e0];   // first timestamp of the window
     else c.t_first = static_cast<const float*>(a.d.ts)[e0];
   }
   a.wcs[w] = c;
+  // the chunks whose FIRST event lies in this window get their first window from here (no search in the sort pass);
+  // window 0 also takes the chunks before the first offset, the last window everything after the last one
+  const int64_t lo = w == 0 ? 0 : (e0 + kChunk - 1) / kChunk;
+  const int64_t hi = w == a.d.num_windows - 1 ? a.chunks + 1 : min(a.chunks + 1, (e1 + kChunk - 1) / kChunk);
+  for (int64_t ch = lo; ch < hi; ++ch) a.chunk_w0[ch] = w;
+  a.win_w0f[w] = first_window_of(a.d, e0 / kChunk * kChunk);
 }
 
-// Both passes walk the stream in chunks of kChunk consecutive events per CTA.  A chunk rarely spans more than a couple
-// of windows, so the (window, strip) counters of the chunk live in shared memory: one shared atomic per event, and
-// one global atomic per touched (window, strip) per CTA (a chunk that spans more than kMaxWin windows falls back to one
-// global atomic per event).
-constexpr int kMaxWin = 4;
-
-__device__ __forceinline__ int first_window_of(const v2v_scatter_desc& d, int64_t e) {     // last window with start <= e
-  int lo = 0, hi = d.num_windows;
-  while (hi - lo > 1) {
-    const int mid = (lo + hi) >> 1;
-    if (d.window_offsets[mid] <= e) lo = mid; else hi = mid;
-  }
-  return lo;
+__device__ __forceinline__ int64_t table_base(const SortedArgs& a, int64_t chunk, int w0) {
+  // chunk c owns (w1 - w0 + 1) * S + 1 entries; consecutive chunks share at most one window, so these bases never overlap
+  return (chunk + w0) * a.S + chunk;
 }
 
-// Count pass: only the row coordinate is read (2 bytes per event).  It over-counts (events that the fill pass drops for
-// their column, bin or zero weight keep their slot): segments are sized by it, the fill pass records how much of each
-// segment is used.
-__global__ void __launch_bounds__(kSortThreads) count_events_kernel(const SortedArgs a) {
-  const v2v_scatter_desc& d = a.d;
-  extern __shared__ uint32_t h_s[];                 // [kMaxWin * S]
-  __shared__ int s_w0, s_w1;
-  const int64_t c0 = static_cast<int64_t>(blockIdx.x) * kChunk;
-  const int64_t c1 = min(d.num_events, c0 + kChunk);
-  if (threadIdx.x == 0) {
-    s_w0 = first_window_of(d, c0);
-    s_w1 = first_window_of(d, c1 - 1);
+// In-place exclusive prefix sum of h[0..n) by the whole CTA (n <= kMaxCounters); returns the total.
+__device__ __forceinline__ uint32_t cta_exclusive_scan(uint32_t* h, int n, uint32_t* warp_tot) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int per = (n + kSortThreads - 1) / kSortThreads;
+  const int i0 = threadIdx.x * per;
+  uint32_t tsum = 0u;
+  for (int k = 0; k < per; ++k)
+    if (i0 + k < n) tsum += h[i0 + k];
+  uint32_t inc = tsum;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc += t;
   }
-  for (int i = threadIdx.x; i < kMaxWin * a.S; i += kSortThreads) h_s[i] = 0u;
+  if (lane == 31) warp_tot[warp] = inc;
   __syncthreads();
-  const int w0 = s_w0;
-  const bool local = s_w1 - w0 < kMaxWin;
-  const bool c16 = d.ys_dtype == V2V_U16 || d.ys_dtype == V2V_I16;
-  const int64_t first = d.window_offsets[0], last = d.window_offsets[d.num_windows];
-  int w = w0;
-  for (int64_t e = c0 + threadIdx.x; e < c1; e += kSortThreads) {
-    if (e < first || e >= last) continue;
-    while (e >= d.window_offsets[w + 1]) ++w;
-    long long y;
-    if (c16) {
-      y = static_cast<const uint16_t*>(d.ys)[e];
-    } else {
-      bool ok = true;
-      y = load_int(d.ys, d.ys_dtype, e, &ok);
-      if (!ok) y = -1;
+  if (warp == 0) {
+    const uint32_t t = lane < kSortThreads / 32 ? warp_tot[lane] : 0u;
+    uint32_t sc = t;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t u = __shfl_up_sync(0xffffffffu, sc, o);
+      if (lane >= o) sc += u;
     }
-    if (y < 0 || y >= d.H) continue;
-    const uint32_t strip = static_cast<uint32_t>((static_cast<uint64_t>(y) * a.r_magic) >> 32);
-    if (local) atomicAdd(&h_s[(w - w0) * a.S + strip], 1u);
-    else atomicAdd(a.counts + static_cast<int64_t>(w) * a.S + strip, 1u);
+    warp_tot[lane] = sc - t;                       // exclusive prefix of the warp totals
+    if (lane == 31) warp_tot[32] = sc;             // the total
   }
   __syncthreads();
-  if (local) {
-    const int n = min(kMaxWin, d.num_windows - w0) * a.S;
-    for (int i = threadIdx.x; i < n; i += kSortThreads)
-      if (h_s[i]) atomicAdd(a.counts + static_cast<int64_t>(w0) * a.S + i, h_s[i]);
-  }
+  uint32_t excl = warp_tot[warp] + inc - tsum;
+  for (int k = 0; k < per; ++k)
+    if (i0 + k < n) {
+      const uint32_t v = h[i0 + k];
+      h[i0 + k] = excl;
+      excl += v;
+    }
+  const uint32_t total = warp_tot[32];
+  __syncthreads();
+  return total;
 }
 
-// Fill pass: every thread keeps the records of its kChunk / kSortThreads events in registers, takes a chunk-local slot per
-// event from the shared counters, the CTA reserves one range per touched (window, strip) in the global cursors, and the
-// records go to their slots.
-__global__ void __launch_bounds__(kSortThreads) fill_events_kernel(const SortedArgs a) {
+// Sort pass: ONE read of the events.  A CTA takes kChunk consecutive events, builds the 8-byte record of every event it
+// keeps, counts them per (window, strip) in shared memory (the slot of a record is the value its shared atomic returns),
+// turns the counters into offsets, stages the records in (window, strip) order in shared memory and writes them back over
+// the chunk's own slice of the record array with coalesced stores, next to a small table of the run offsets.  No global
+// counters, no second traversal: what used to be count + scan + fill.  A chunk whose windows x strips exceed the shared
+// counters (thousands of tiny or empty windows) is done in several rounds over groups of windows.
+__global__ void __launch_bounds__(kSortThreads, 2) sort_chunks_kernel(const SortedArgs a) {
   const v2v_scatter_desc& d = a.d;
-  extern __shared__ uint32_t h_s[];                 // [kMaxWin * S] counters, then [kMaxWin * S] reserved bases
-  uint32_t* base_s = h_s + kMaxWin * a.S;
-  __shared__ int s_w0, s_w1;
+  __shared__ uint32_t h_s[kMaxCounters];
+  __shared__ uint2 stage[kChunk];
+  __shared__ uint32_t warp_tot[33];
   const int64_t c0 = static_cast<int64_t>(blockIdx.x) * kChunk;
   const int64_t c1 = min(d.num_events, c0 + kChunk);
-  if (threadIdx.x == 0) {
-    s_w0 = first_window_of(d, c0);
-    s_w1 = first_window_of(d, c1 - 1);
-  }
-  for (int i = threadIdx.x; i < kMaxWin * a.S; i += kSortThreads) h_s[i] = 0u;
-  __syncthreads();
-  const int w0 = s_w0;
-  const bool local = s_w1 - w0 < kMaxWin;
-  const int B = d.num_bins, H = d.H, W = d.W;
+  // the chunk's windows: from the window of its first event to the window of the next chunk's first event (which may hold
+  // none of this chunk's events: its runs are then empty; the table layout counts on exactly this span)
+  const int w0 = a.chunk_w0[blockIdx.x], w1 = a.chunk_w0[blockIdx.x + 1];
+  const int B = d.num_bins, H = d.H, W = d.W, S = a.S;
   const bool c16 = (d.xs_dtype == V2V_U16 || d.xs_dtype == V2V_I16) && (d.ys_dtype == V2V_U16 || d.ys_dtype == V2V_I16);
   const int64_t first = d.window_offsets[0], last = d.window_offsets[d.num_windows];
-  constexpr int kPer = kChunk / kSortThreads;
   uint2 rec[kPer];
-  int where[kPer];                                  // index of the event's (window, strip) counter, or -1
-  uint32_t slot[kPer];
+  int where[kPer];                                  // (window - w0) * S + strip of a kept event, or -1
   long long ndrop = 0;
-  // phase 1: every load of the thread's events is issued before any dependent arithmetic
+  // phase 1: every load of the thread's events is issued before anything depends on one (the window search comes after)
   int wv[kPer];
   long long yv[kPer], xv[kPer];
   float pv[kPer];
   double tv[kPer];
+#pragma unroll
+  for (int u = 0; u < kPer; ++u) {
+    const int64_t e = c0 + u * kSortThreads + threadIdx.x;
+    yv[u] = xv[u] = -1;
+    pv[u] = 0.f;
+    tv[u] = 0.0;
+    if (e >= c1) continue;
+    if (c16) {
+      yv[u] = static_cast<const uint16_t*>(d.ys)[e];                      // negative int16 read as >= 32768: out of the sensor
+      xv[u] = static_cast<const uint16_t*>(d.xs)[e];
+    } else {
+      bool ok = true;
+      yv[u] = load_int(d.ys, d.ys_dtype, e, &ok);
+      xv[u] = load_int(d.xs, d.xs_dtype, e, &ok);
+      if (!ok) yv[u] = -1;
+    }
+    pv[u] = d.ps_dtype == V2V_U8 ? static_cast<float>(static_cast<const uint8_t*>(d.ps)[e]) : load_f32(d.ps, d.ps_dtype, e);
+    tv[u] = d.ts_dtype == V2V_F64 ? static_cast<const double*>(d.ts)[e] : static_cast<double>(static_cast<const float*>(d.ts)[e]);
+  }
   {
     int w = w0;
 #pragma unroll
     for (int u = 0; u < kPer; ++u) {
       const int64_t e = c0 + u * kSortThreads + threadIdx.x;
       wv[u] = -1;
-      yv[u] = xv[u] = -1;
-      pv[u] = 0.f;
-      tv[u] = 0.0;
       if (e >= c1 || e < first || e >= last) continue;
-      while (e >= d.window_offsets[w + 1]) ++w;
+      if (w0 != w1)                                   // (most chunks lie inside one window)
+        while (e >= d.window_offsets[w + 1]) ++w;
       wv[u] = w;
-      if (c16) {
-        yv[u] = static_cast<const uint16_t*>(d.ys)[e];                      // negative int16 read as >= 32768: out of the sensor
-        xv[u] = static_cast<const uint16_t*>(d.xs)[e];
-      } else {
-        bool ok = true;
-        yv[u] = load_int(d.ys, d.ys_dtype, e, &ok);
-        xv[u] = load_int(d.xs, d.xs_dtype, e, &ok);
-        if (!ok) yv[u] = -1;
-      }
-      pv[u] = d.ps_dtype == V2V_U8 ? static_cast<float>(static_cast<const uint8_t*>(d.ps)[e]) : load_f32(d.ps, d.ps_dtype, e);
-      tv[u] = d.ts_dtype == V2V_F64 ? static_cast<const double*>(d.ts)[e] : static_cast<double>(static_cast<const float*>(d.ts)[e]);
     }
   }
+  const WinConst wc0 = a.wcs[w0];
 #pragma unroll
   for (int u = 0; u < kPer; ++u) {
     where[u] = -1;
@@ -189,7 +198,8 @@ __global__ void __launch_bounds__(kSortThreads) fill_events_kernel(const SortedA
       else if (d.polarity_mode == V2V_POL_NEG_ONLY) pw = p <= 0.f ? 1.f : 0.f;
       else pw = 2.f * p - 1.f;                                              // testh5.py:67
     }
-    const WinConst wc = a.wcs[w];
+    WinConst wc = wc0;
+    if (w != w0) wc = a.wcs[w];
     // t_norm = tau / (tau_last + 1e-4) * (bins - 1) (:68,77) with the two constant factors folded into one per window
     // (h5_den holds (bins-1)/(tau_last+1e-4) here, t_first/h5_tpb the window's first timestamp): at most 2 ulp from the
     // reference's two roundings, far below the 2^-30 the weights are rounded to.  tau = trunc((ts - ts0)*1e6) stays in
@@ -210,203 +220,238 @@ __global__ void __launch_bounds__(kSortThreads) fill_events_kernel(const SortedA
     const uint32_t cell = static_cast<uint32_t>((y - static_cast<long long>(strip) * a.R) * W + x);
     const uint32_t frac = static_cast<uint32_t>(__double2int_rn(__dmul_rn(__dsub_rn(tn, fl), 1073741824.0)));   // in [0, 2^30]
     rec[u] = make_uint2(cell | (static_cast<uint32_t>(static_cast<int>(fl) + 1) << 16) | (pw < 0.f ? 0x80000000u : 0u), frac);
-    if (local) {
-      where[u] = (w - w0) * a.S + static_cast<int>(strip);
-      slot[u] = atomicAdd(&h_s[where[u]], 1u);
-    } else {
-      a.records[atomicAdd(a.cursor + static_cast<int64_t>(w) * a.S + strip, 1u)] = rec[u];
-    }
+    where[u] = (w - w0) * S + static_cast<int>(strip);
   }
-  __syncthreads();
-  if (local) {
-    const int n = min(kMaxWin, d.num_windows - w0) * a.S;
-    for (int i = threadIdx.x; i < n; i += kSortThreads)
-      base_s[i] = h_s[i] ? atomicAdd(a.cursor + static_cast<int64_t>(w0) * a.S + i, h_s[i]) : 0u;
+  // phase 2: rounds over groups of windows whose counters fit (one round for every realistic stream)
+  const int G = max(1, kMaxCounters / S);
+  const int64_t tb = table_base(a, blockIdx.x, w0);
+  uint32_t running = 0u;
+  for (int wg = w0; wg <= w1; wg += G) {
+    const int n = min(G, w1 - wg + 1) * S;
+    const int lo = (wg - w0) * S;
+    for (int i = threadIdx.x; i < n; i += kSortThreads) h_s[i] = 0u;
     __syncthreads();
+    uint32_t slot[kPer];
 #pragma unroll
     for (int u = 0; u < kPer; ++u)
-      if (where[u] >= 0) a.records[base_s[where[u]] + slot[u]] = rec[u];
+      if (where[u] >= lo && where[u] < lo + n) slot[u] = atomicAdd(&h_s[where[u] - lo], 1u);
+    __syncthreads();
+    const uint32_t total = cta_exclusive_scan(h_s, n, warp_tot);
+    for (int i = threadIdx.x; i < n; i += kSortThreads) a.tab[tb + lo + i] = static_cast<uint16_t>(running + h_s[i]);
+#pragma unroll
+    for (int u = 0; u < kPer; ++u)
+      if (where[u] >= lo && where[u] < lo + n) stage[running + h_s[where[u] - lo] + slot[u]] = rec[u];
+    running += total;
+    __syncthreads();
   }
+  if (threadIdx.x == 0) a.tab[tb + static_cast<int64_t>(w1 - w0 + 1) * S] = static_cast<uint16_t>(running);
+  for (uint32_t i = threadIdx.x; i < running; i += kSortThreads) a.records[c0 + i] = stage[i];
   if (d.dropped && ndrop) atomicAdd(reinterpret_cast<unsigned long long*>(d.dropped), static_cast<unsigned long long>(ndrop));
 }
 
-// exclusive prefix sum of counts[0..items) into cursor and starts (one CTA of 1024 threads, 8 consecutive items per thread)
-__global__ void __launch_bounds__(1024) scan_counts_kernel(const SortedArgs a) {
-  __shared__ uint32_t warp_tot[32];
-  __shared__ uint32_t carry_s;
-  if (threadIdx.x == 0) carry_s = 0u;
-  __syncthreads();
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  constexpr int kV = 8;
-  for (int64_t base = 0; base < a.items; base += 1024 * kV) {
-    const int64_t i0 = base + static_cast<int64_t>(threadIdx.x) * kV;
-    uint32_t v[kV], tsum = 0u;
-    if (i0 + kV <= a.items) {               // two 128-bit loads per thread: the warp reads 1 KB contiguously
-      const uint4 q0 = reinterpret_cast<const uint4*>(a.counts + i0)[0], q1 = reinterpret_cast<const uint4*>(a.counts + i0)[1];
-      v[0] = q0.x, v[1] = q0.y, v[2] = q0.z, v[3] = q0.w, v[4] = q1.x, v[5] = q1.y, v[6] = q1.z, v[7] = q1.w;
-    } else {
-#pragma unroll
-      for (int k = 0; k < kV; ++k) v[k] = i0 + k < a.items ? a.counts[i0 + k] : 0u;
-    }
-#pragma unroll
-    for (int k = 0; k < kV; ++k) tsum += v[k];
-    uint32_t inc = tsum;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
-      if (lane >= o) inc += t;
-    }
-    if (lane == 31) warp_tot[warp] = inc;
-    __syncthreads();
-    if (warp == 0) {
-      uint32_t t = warp_tot[lane], s = t;
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        const uint32_t u = __shfl_up_sync(0xffffffffu, s, o);
-        if (lane >= o) s += u;
-      }
-      warp_tot[lane] = s - t;              // exclusive prefix of the warp totals
-    }
-    __syncthreads();
-    uint32_t excl = carry_s + warp_tot[warp] + inc - tsum;
-    uint32_t ex[kV];
-#pragma unroll
-    for (int k = 0; k < kV; ++k) {
-      ex[k] = excl;
-      excl += v[k];
-    }
-    if (i0 + kV <= a.items) {
-      const uint4 q0 = make_uint4(ex[0], ex[1], ex[2], ex[3]), q1 = make_uint4(ex[4], ex[5], ex[6], ex[7]);
-      reinterpret_cast<uint4*>(a.cursor + i0)[0] = q0, reinterpret_cast<uint4*>(a.cursor + i0)[1] = q1;
-      reinterpret_cast<uint4*>(a.starts + i0)[0] = q0, reinterpret_cast<uint4*>(a.starts + i0)[1] = q1;
-    } else {
-#pragma unroll
-      for (int k = 0; k < kV; ++k)
-        if (i0 + k < a.items) a.cursor[i0 + k] = a.starts[i0 + k] = ex[k];
-    }
-    __syncthreads();
-    if (threadIdx.x == 1023) carry_s = excl;
-    __syncthreads();
-  }
-  if (threadIdx.x == 0) a.starts[a.items] = carry_s;
-}
+// Scatter pass.  A task is (window, group of kGroup consecutive strips); an item is one strip of it: all bins of rows
+// [r0, r0+rows) as fixed-point words in shared memory.  The window's run offsets for the whole group are fetched once per
+// task (lane j of EVERY warp holds chunk j's kGroup+1 table entries: no shared staging, no barrier, and run lookups of an
+// item are register shuffles), so an item costs one global round trip (its records), three barriers and its stores.
+constexpr int kGroup = 8;
 
-// work item = (window, strip): all bins of rows [r0, r0+rows) as fixed-point pairs in shared memory
 __global__ void __launch_bounds__(kItemThreads, 8) scatter_sorted_kernel(const SortedArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const v2v_scatter_desc& d = a.d;
-  const int W = d.W, H = d.H, B = d.num_bins, R = a.R;
+  const int W = d.W, H = d.H, B = d.num_bins, R = a.R, S = a.S;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   int* acc_hi = reinterpret_cast<int*>(smem_raw);
-  for (int64_t item = blockIdx.x; item < a.items; item += gridDim.x) {
-    const int win = static_cast<int>(item / a.S), strip = static_cast<int>(item - static_cast<int64_t>(win) * a.S);
-    const int r0 = strip * R, rows = min(R, H - r0);
-    const int cells = rows * W;                       // per bin
-    const int plane = R * W;                          // tile layout: [bin][R*W] high words, then the same for low words
-    unsigned int* acc_lo = reinterpret_cast<unsigned int*>(acc_hi + B * plane);
-    const uint32_t s0 = a.starts[item], s1 = a.cursor[item];            // the used part of the segment (the count pass over-counts)
-    const int64_t out_base = (static_cast<int64_t>(win) * B * H + r0) * W;      // + bin * H * W
-    if (s1 == s0) {                                   // no event in these rows: zeros straight to HBM
-      for (int b = 0; b < B; ++b) {
-        const int64_t ob = out_base + static_cast<int64_t>(b) * H * W;
-        if (d.out_dtype == V2V_F64) {
-          double* o = static_cast<double*>(d.voxel) + ob;
-          for (int i = threadIdx.x; i < cells; i += kItemThreads) o[i] = 0.0;
-        } else {
-          float* o = static_cast<float*>(d.voxel) + ob;
-          for (int i = threadIdx.x; i < cells; i += kItemThreads) st_stream_f32(o + i, 0.f);
-        }
-      }
-      continue;
+  unsigned long long* acc64 = reinterpret_cast<unsigned long long*>(smem_raw);
+  const int plane = R * W;                            // tile layout: [bin][R*W] high words, then the same for low words
+  unsigned int* acc_lo = reinterpret_cast<unsigned int*>(acc_hi + B * plane);
+  const int groups = (S + kGroup - 1) / kGroup;
+  const int64_t tasks = static_cast<int64_t>(d.num_windows) * groups;
+  for (int64_t task = blockIdx.x; task < tasks; task += gridDim.x) {
+    const int win = static_cast<int>(task / groups), s0 = static_cast<int>(task - static_cast<int64_t>(win) * groups) * kGroup;
+    const int ns = min(kGroup, S - s0);
+    const int64_t e0 = d.window_offsets[win], e1 = d.window_offsets[win + 1];
+    const int64_t cf = e0 / kChunk;
+    const int nch = e1 > e0 ? static_cast<int>((e1 - 1) / kChunk - cf + 1) : 0;   // chunks that overlap the window
+    const int w0f = nch ? a.win_w0f[win] : 0;
+    // table row of the item group in chunk cf + j (every later chunk than the first starts inside this window)
+    auto row_of = [&](int j) -> const uint16_t* {
+      const int64_t c = cf + j;
+      const int w0c = j == 0 ? w0f : win;
+      return a.tab + table_base(a, c, w0c) + static_cast<int64_t>(win - w0c) * S + s0;
+    };
+    uint32_t t[kGroup + 1];                           // lane j: run offsets of chunk cf + j for strips s0 .. s0 + ns
+#pragma unroll
+    for (int k = 0; k <= kGroup; ++k) t[k] = 0u;
+    if (lane < nch) {
+      const uint16_t* row = row_of(lane);
+#pragma unroll
+      for (int k = 0; k <= kGroup; ++k) t[k] = row[min(k, ns)];
     }
-    // An item with at most 255 records cannot overflow ONE 32-bit word per cell at 2^-23 per unit weight (|sum| < 255 *
-    // 2^23 < 2^31; error <= n_cell * 2^-24 per cell): two shared atomics per event instead of four and half the tile to
-    // zero and read.  Larger items (hot rows, long windows) keep the exact two-word form.
-    const bool one_word = s1 - s0 <= 255u;
-    // ... and an item with more than 65535 records could overflow the two-word form (65536 same-sign unit weights on one
-    // cell): it accumulates in ONE 64-bit word per cell instead, same footprint, exact for any count
-    const bool wide = s1 - s0 > 65535u;
-    unsigned long long* acc64 = reinterpret_cast<unsigned long long*>(smem_raw);
-    {
-      int4* z = reinterpret_cast<int4*>(smem_raw);
-      const int n4 = ((one_word ? 1 : 2) * B * plane + 3) / 4;
-      for (int i = threadIdx.x; i < n4; i += kItemThreads) z[i] = make_int4(0, 0, 0, 0);
-    }
-    __syncthreads();
-    for (uint32_t r = s0 + threadIdx.x; r < s1; r += kItemThreads) {
-      const uint2 rec = a.records[r];
-      const int cell = static_cast<int>(rec.x & 0xffffu);
-      const int b0 = static_cast<int>((rec.x >> 16) & 0xffu) - 1;          // floor(t_norm)
-      const bool negp = (rec.x >> 31) != 0u;
-      if (one_word) {
-        const int f1 = static_cast<int>((rec.y + 64u) >> 7), f0 = 8388608 - f1;    // weights of bins b0+1 and b0 (:79), 2^-23 units
-        if (b0 >= 0 && f0 != 0) atomicAdd(&acc_hi[b0 * plane + cell], negp ? -f0 : f0);
-        if (b0 + 1 < B && f1 != 0) atomicAdd(&acc_hi[(b0 + 1) * plane + cell], negp ? -f1 : f1);
-        continue;
+    const int64_t my_chunk0 = (cf + lane) * kChunk;
+#pragma unroll 1
+    for (int k = 0; k < ns; ++k) {
+      const int strip = s0 + k;
+      const int r0 = strip * R, rows = min(R, H - r0);
+      const int cells = rows * W;                     // per bin
+      const int64_t out_base = (static_cast<int64_t>(win) * B * H + r0) * W;      // + bin * H * W
+      const uint32_t my_beg = t[k], my_len = t[k + 1] - t[k];
+      uint32_t tot = my_len;
+      for (int j = 32 + lane; j < nch; j += 32) {     // (windows of more than 32 chunks)
+        const uint16_t* row = row_of(j);
+        tot += static_cast<uint32_t>(row[k + 1]) - row[k];
       }
-      const long long f1 = static_cast<long long>(rec.y), f0 = 1073741824ll - f1;   // 2^-30 units
-      if (wide) {
-        if (b0 >= 0 && f0 != 0) atomicAdd(&acc64[b0 * plane + cell], static_cast<unsigned long long>(negp ? -f0 : f0));
-        if (b0 + 1 < B && f1 != 0) atomicAdd(&acc64[(b0 + 1) * plane + cell], static_cast<unsigned long long>(negp ? -f1 : f1));
-        continue;
-      }
-      if (b0 >= 0 && f0 != 0) {
-        const long long fx = negp ? -f0 : f0;
-        const int hiw = static_cast<int>(fx >> kLoBits);
-        const unsigned int low = static_cast<unsigned int>(fx & ((1 << kLoBits) - 1));
-        if (hiw) atomicAdd(&acc_hi[b0 * plane + cell], hiw);
-        if (low) atomicAdd(&acc_lo[b0 * plane + cell], low);
-      }
-      if (b0 + 1 < B && f1 != 0) {
-        const long long fx = negp ? -f1 : f1;
-        const int hiw = static_cast<int>(fx >> kLoBits);
-        const unsigned int low = static_cast<unsigned int>(fx & ((1 << kLoBits) - 1));
-        if (hiw) atomicAdd(&acc_hi[(b0 + 1) * plane + cell], hiw);
-        if (low) atomicAdd(&acc_lo[(b0 + 1) * plane + cell], low);
-      }
-    }
-    __syncthreads();
-    for (int b = 0; b < B; ++b) {
-      const int64_t ob = out_base + static_cast<int64_t>(b) * H * W;
-      const int* h = acc_hi + b * plane;
-      const unsigned int* l = acc_lo + b * plane;
-      auto valuef = [&](int i) -> float {
-        if (wide) return static_cast<float>(static_cast<double>(static_cast<long long>(acc64[b * plane + i])) * (1.0 / 1073741824.0));
-        const int hv = h[i];
-        if (one_word) return hv == 0 ? 0.f : __fmul_rn(static_cast<float>(hv), 1.0f / 8388608.0f);
-        const unsigned int lv = l[i];
-        if ((static_cast<unsigned int>(hv) | lv) == 0u) return 0.f;         // most cells hold no event
-        // hv*2^-15 + lv*2^-30 is exact in float64 (46 significant bits at most): one rounding, to float32
-        return static_cast<float>(__fma_rn(static_cast<double>(hv), 1.0 / 32768.0, __dmul_rn(static_cast<double>(lv), 1.0 / 1073741824.0)));
-      };
-      if (d.out_dtype == V2V_F64) {
-        double* o = static_cast<double*>(d.voxel) + ob;
-        for (int i = threadIdx.x; i < cells; i += kItemThreads) {
-          if (wide) {
-            o[i] = static_cast<double>(static_cast<long long>(acc64[b * plane + i])) * (1.0 / 1073741824.0);
-          } else if (one_word) {
-            o[i] = static_cast<double>(h[i]) * (1.0 / 8388608.0);
+      const uint32_t nrec = __reduce_add_sync(0xffffffffu, tot);
+      if (nrec == 0u) {                               // no event in these rows: zeros straight to HBM
+        for (int b = 0; b < B; ++b) {
+          const int64_t ob = out_base + static_cast<int64_t>(b) * H * W;
+          if (d.out_dtype == V2V_F64) {
+            double* o = static_cast<double*>(d.voxel) + ob;
+            for (int i = threadIdx.x; i < cells; i += kItemThreads) o[i] = 0.0;
           } else {
-            const long long tot = static_cast<long long>(h[i]) * (1 << kLoBits) + static_cast<long long>(l[i]);
-            o[i] = static_cast<double>(tot) * (1.0 / 1073741824.0);
+            float* o = static_cast<float*>(d.voxel) + ob;
+            for (int i = threadIdx.x; i < cells; i += kItemThreads) st_stream_f32(o + i, 0.f);
           }
         }
-      } else {
-        float* o = static_cast<float*>(d.voxel) + ob;
-        const int head = min(static_cast<int>((4 - (ob & 3)) & 3), cells);
-        for (int i = threadIdx.x; i < head; i += kItemThreads) st_stream_f32(o + i, valuef(i));
-        const int n4 = (cells - head) / 4;
-        for (int q = threadIdx.x; q < n4; q += kItemThreads) {
-          const int i = head + 4 * q;
-          st_stream_f32x4(o + i, valuef(i), valuef(i + 1), valuef(i + 2), valuef(i + 3));
-        }
-        for (int i = head + 4 * n4 + threadIdx.x; i < cells; i += kItemThreads) st_stream_f32(o + i, valuef(i));
+        continue;
       }
+      // An item with at most 255 records cannot overflow ONE 32-bit word per cell at 2^-23 per unit weight (|sum| < 255 *
+      // 2^23 < 2^31; error <= n_cell * 2^-24 per cell): two shared atomics per event instead of four and half the tile to
+      // zero and read.  Larger items (hot rows, long windows) keep the exact two-word form, and an item with more than 65535
+      // records, which could overflow that (65536 same-sign unit weights on one cell), takes ONE 64-bit word per cell: same
+      // footprint, exact for any count.
+      const bool one_word = nrec <= 255u;
+      const bool wide = nrec > 65535u;
+      {
+        int4* z = reinterpret_cast<int4*>(smem_raw);
+        const int n4 = ((one_word ? 1 : 2) * B * plane + 3) / 4;
+        for (int i = threadIdx.x; i < n4; i += kItemThreads) z[i] = make_int4(0, 0, 0, 0);
+      }
+      __syncthreads();
+      auto add_record = [&](const uint2 rec) {
+        const int cell = static_cast<int>(rec.x & 0xffffu);
+        const int b0 = static_cast<int>((rec.x >> 16) & 0xffu) - 1;          // floor(t_norm)
+        const bool negp = (rec.x >> 31) != 0u;
+        if (one_word) {
+          const int f1 = static_cast<int>((rec.y + 64u) >> 7), f0 = 8388608 - f1;    // weights of bins b0+1 and b0 (:79), 2^-23 units
+          if (b0 >= 0 && f0 != 0) atomicAdd(&acc_hi[b0 * plane + cell], negp ? -f0 : f0);
+          if (b0 + 1 < B && f1 != 0) atomicAdd(&acc_hi[(b0 + 1) * plane + cell], negp ? -f1 : f1);
+          return;
+        }
+        const long long f1 = static_cast<long long>(rec.y), f0 = 1073741824ll - f1;   // 2^-30 units
+        if (wide) {
+          if (b0 >= 0 && f0 != 0) atomicAdd(&acc64[b0 * plane + cell], static_cast<unsigned long long>(negp ? -f0 : f0));
+          if (b0 + 1 < B && f1 != 0) atomicAdd(&acc64[(b0 + 1) * plane + cell], static_cast<unsigned long long>(negp ? -f1 : f1));
+          return;
+        }
+        if (b0 >= 0 && f0 != 0) {
+          const long long fx = negp ? -f0 : f0;
+          const int hiw = static_cast<int>(fx >> kLoBits);
+          const unsigned int low = static_cast<unsigned int>(fx & ((1 << kLoBits) - 1));
+          if (hiw) atomicAdd(&acc_hi[b0 * plane + cell], hiw);
+          if (low) atomicAdd(&acc_lo[b0 * plane + cell], low);
+        }
+        if (b0 + 1 < B && f1 != 0) {
+          const long long fx = negp ? -f1 : f1;
+          const int hiw = static_cast<int>(fx >> kLoBits);
+          const unsigned int low = static_cast<unsigned int>(fx & ((1 << kLoBits) - 1));
+          if (hiw) atomicAdd(&acc_hi[(b0 + 1) * plane + cell], hiw);
+          if (low) atomicAdd(&acc_lo[(b0 + 1) * plane + cell], low);
+        }
+      };
+      // one warp per run (the item's records of one chunk): coalesced 8-byte loads; the run comes from lane j's registers
+      for (int j = warp; j < min(nch, 32); j += kItemThreads / 32) {
+        const int64_t beg = __shfl_sync(0xffffffffu, my_chunk0 + my_beg, j);
+        const uint32_t len = __shfl_sync(0xffffffffu, my_len, j);
+        for (uint32_t r = lane; r < len; r += 32) add_record(a.records[beg + r]);
+      }
+      for (int j = 32 + warp; j < nch; j += kItemThreads / 32) {           // (windows of more than 32 chunks)
+        const uint16_t* row = row_of(j);
+        const int64_t beg = (cf + j) * kChunk + row[k];
+        const uint32_t len = static_cast<uint32_t>(row[k + 1]) - row[k];
+        for (uint32_t r = lane; r < len; r += 32) add_record(a.records[beg + r]);
+      }
+      __syncthreads();
+      // one specialised, branch-free write-out per accumulator form (a per-cell "is it zero" test compiles to a divergent
+      // branch per cell and was 60 % of this kernel's instructions)
+      const bool flat = d.out_dtype != V2V_F64 && ((static_cast<int64_t>(H) * W) & 3) == 0 && 8 * B <= kItemThreads;
+      auto write_out = [&](auto form_tag) {
+        constexpr int FORM = decltype(form_tag)::value;                        // 0 one word, 1 two words, 2 one 64-bit word
+        for (int b = 0; b < B; ++b) {
+          const int64_t ob = out_base + static_cast<int64_t>(b) * H * W;
+          const int* h = acc_hi + b * plane;
+          const unsigned int* l = acc_lo + b * plane;
+          const unsigned long long* q64 = acc64 + b * plane;
+          auto total = [&](int i) -> long long {                              // the cell's sum in 2^-30 units (FORM 1, 2)
+            if (FORM == 2) return static_cast<long long>(q64[i]);
+            return static_cast<long long>(h[i]) * (1 << kLoBits) + static_cast<long long>(l[i]);
+          };
+          auto valuef = [&](int i) -> float {
+            if (FORM == 0) return __fmul_rn(static_cast<float>(h[i]), 1.0f / 8388608.0f);
+            // integer -> float32 is ONE correctly rounded conversion, the power-of-two scale is exact
+            return __fmul_rn(__ll2float_rn(total(i)), 1.0f / 1073741824.0f);
+          };
+          if (d.out_dtype == V2V_F64) {
+            double* o = static_cast<double*>(d.voxel) + ob;
+            for (int i = threadIdx.x; i < cells; i += kItemThreads)
+              o[i] = FORM == 0 ? static_cast<double>(h[i]) * (1.0 / 8388608.0) : static_cast<double>(total(i)) * (1.0 / 1073741824.0);
+          } else {
+            if (flat) continue;                                               // done below, all bins in one loop
+            float* o = static_cast<float*>(d.voxel) + ob;
+            const int head = min(static_cast<int>((4 - (ob & 3)) & 3), cells);
+            const int n4 = (cells - head) / 4;
+            for (int q = threadIdx.x; q < n4; q += kItemThreads) {
+              const int i = head + 4 * q;
+              st_stream_f32x4(o + i, valuef(i), valuef(i + 1), valuef(i + 2), valuef(i + 3));
+            }
+            // (up to three cells before and after the aligned part)
+            if (threadIdx.x < head) st_stream_f32(o + threadIdx.x, valuef(threadIdx.x));
+            const int tail0 = head + 4 * n4;
+            if (static_cast<int>(threadIdx.x) < cells - tail0) st_stream_f32(o + tail0 + threadIdx.x, valuef(tail0 + threadIdx.x));
+          }
+        }
+        if (flat) {
+          // float32 planes whose size is a multiple of 4 cells: every bin's slice of the strip has the same 16-byte phase,
+          // so the B slices are written by ONE loop over (bin, group of 4 cells) - no per-bin loop overhead (it was 5 x ~50
+          // instructions per warp and item around a single store).  (bin, q) advance incrementally: no division.
+          float* o0 = static_cast<float*>(d.voxel) + out_base;
+          const int head = min(static_cast<int>((4 - (out_base & 3)) & 3), cells);
+          const int n4 = (cells - head) / 4;
+          const int64_t HW = static_cast<int64_t>(H) * W;
+          auto cellf = [&](int b, int i) -> float {
+            if (FORM == 0) return __fmul_rn(static_cast<float>(acc_hi[b * plane + i]), 1.0f / 8388608.0f);
+            const long long tot = FORM == 2 ? static_cast<long long>(acc64[b * plane + i])
+                                            : static_cast<long long>(acc_hi[b * plane + i]) * (1 << kLoBits) + static_cast<long long>(acc_lo[b * plane + i]);
+            return __fmul_rn(__ll2float_rn(tot), 1.0f / 1073741824.0f);
+          };
+          if (n4 > 0) {
+            int b = 0, q = threadIdx.x;
+            while (q >= n4 && b < B) q -= n4, ++b;
+            while (b < B) {
+              const int i = head + 4 * q;
+              st_stream_f32x4(o0 + b * HW + i, cellf(b, i), cellf(b, i + 1), cellf(b, i + 2), cellf(b, i + 3));
+              q += kItemThreads;
+              while (q >= n4 && b < B) q -= n4, ++b;
+            }
+          }
+          const int tail0 = head + 4 * n4;
+          if (static_cast<int>(threadIdx.x) < 8 * B) {                       // up to three cells before and after the aligned part
+            const int b = threadIdx.x >> 3, j = threadIdx.x & 7;
+            const int i = j < 4 ? j : tail0 + j - 4;
+            if (j < 4 ? j < head : i < cells) st_stream_f32(o0 + b * HW + i, cellf(b, i));
+          }
+        }
+      };
+      if (wide) write_out(std::integral_constant<int, 2>{});
+      else if (one_word) write_out(std::integral_constant<int, 0>{});
+      else write_out(std::integral_constant<int, 1>{});
+      __syncthreads();
     }
-    __syncthreads();
   }
 }
 
 }  // namespace
+
+static size_t align16(size_t n) { return (n + 15) / 16 * 16; }
 
 size_t scatter_sorted_workspace_bytes(const v2v_scatter_desc& d, int* rows_per_strip, int* strips) {
   if (d.H <= 0 || d.W <= 0) return 0;
@@ -422,8 +467,9 @@ size_t scatter_sorted_workspace_bytes(const v2v_scatter_desc& d, int* rows_per_s
   if (S > 1024) return 0;                                         // the chunk-local counters of the sort live in shared memory
   *rows_per_strip = R;
   *strips = S;
-  const int64_t items = static_cast<int64_t>(d.num_windows) * S;
-  return (static_cast<size_t>(d.num_events) * 8 + 15) / 16 * 16 + 3 * ((static_cast<size_t>(items + 1) * 4 + 15) / 16 * 16) +
+  const size_t chunks = static_cast<size_t>((d.num_events + kChunk - 1) / kChunk);
+  return align16(static_cast<size_t>(d.num_events) * 8) + align16((chunks + 1) * 4) + align16(static_cast<size_t>(d.num_windows) * 4) +
+         align16(((chunks + static_cast<size_t>(d.num_windows)) * S + chunks + 1) * 2) +
          static_cast<size_t>(d.num_windows) * sizeof(WinConst) + 64;
 }
 
@@ -431,7 +477,10 @@ bool scatter_sorted_eligible(const v2v_scatter_desc& d) {
   int R, S;
   if (d.mode != V2V_SCATTER_H5_INTERP || d.polarity_mode == V2V_POL_SPLIT || d.num_bins > 254 || d.H > 65535 || d.num_events >= (1ll << 32)) return false;
   const size_t need = scatter_sorted_workspace_bytes(d, &R, &S);
-  return need != 0 && d.workspace && static_cast<size_t>(d.workspace_bytes) >= need && aligned(d.workspace, 16);
+  if (need == 0 || !d.workspace || static_cast<size_t>(d.workspace_bytes) < need || !aligned(d.workspace, 16)) return false;
+  // a work item is one CTA's job: a few huge windows (the offline cache builder) are better served by the contiguous-range
+  // kernel, which slices a window over many CTAs
+  return d.num_events <= static_cast<int64_t>(d.num_windows) * S * 32768;
 }
 
 int launch_scatter_sorted(const v2v_scatter_desc& d, cudaStream_t s) {
@@ -440,25 +489,20 @@ int launch_scatter_sorted(const v2v_scatter_desc& d, cudaStream_t s) {
   scatter_sorted_workspace_bytes(d, &a.R, &a.S);
   a.r_magic = static_cast<uint32_t>(((1ull << 32) + a.R - 1) / a.R);          // exact for y < 65536 (y * (R-1) < 2^32)
   a.items = static_cast<int64_t>(d.num_windows) * a.S;
+  const size_t chunks = static_cast<size_t>((d.num_events + kChunk - 1) / kChunk);
   char* p = static_cast<char*>(d.workspace);
   a.records = reinterpret_cast<uint2*>(p);
-  p += (static_cast<size_t>(d.num_events) * 8 + 15) / 16 * 16;
-  const size_t arr = (static_cast<size_t>(a.items + 1) * 4 + 15) / 16 * 16;     // 16-byte aligned arrays (128-bit loads in the scan)
-  a.counts = reinterpret_cast<uint32_t*>(p);
-  p += arr;
-  a.cursor = reinterpret_cast<uint32_t*>(p);
-  p += arr;
-  a.starts = reinterpret_cast<uint32_t*>(p);
-  p += arr;
-  p = reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(p) + 15) & ~static_cast<uintptr_t>(15));
+  p += align16(static_cast<size_t>(d.num_events) * 8);
+  a.chunk_w0 = reinterpret_cast<int32_t*>(p);
+  p += align16((chunks + 1) * 4);
+  a.win_w0f = reinterpret_cast<int32_t*>(p);
+  p += align16(static_cast<size_t>(d.num_windows) * 4);
+  a.chunks = static_cast<int64_t>(chunks);
+  a.tab = reinterpret_cast<uint16_t*>(p);
+  p += align16(((chunks + static_cast<size_t>(d.num_windows)) * a.S + chunks + 1) * 2);
   a.wcs = reinterpret_cast<WinConst*>(p);
-  V2V_CUDA(cudaMemsetAsync(a.counts, 0, static_cast<size_t>(a.items + 1) * 4, s));
   window_constants_kernel<<<(d.num_windows + 127) / 128, 128, 0, s>>>(a);
-  const int chunks = static_cast<int>((d.num_events + kChunk - 1) / kChunk);
-  const size_t hsm = static_cast<size_t>(kMaxWin) * a.S * sizeof(uint32_t);
-  if (chunks > 0) count_events_kernel<<<chunks, kSortThreads, hsm, s>>>(a);
-  scan_counts_kernel<<<1, 1024, 0, s>>>(a);
-  if (chunks > 0) fill_events_kernel<<<chunks, kSortThreads, 2 * hsm, s>>>(a);
+  if (chunks > 0) sort_chunks_kernel<<<static_cast<unsigned int>(chunks), kSortThreads, 0, s>>>(a);
   const size_t smem = static_cast<size_t>(2) * d.num_bins * a.R * d.W * 4 + 16;
   static std::atomic<uint64_t> configured{0};
   int dev = 0, sms = 148;
@@ -469,9 +513,10 @@ int launch_scatter_sorted(const v2v_scatter_desc& d, cudaStream_t s) {
     configured.fetch_or(bit, std::memory_order_release);
   }
   V2V_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-  const int grid = static_cast<int>(a.items < 32ll * sms ? a.items : 32ll * sms);
+  const int64_t tasks = static_cast<int64_t>(d.num_windows) * ((a.S + kGroup - 1) / kGroup);
+  const int grid = static_cast<int>(tasks < 32ll * sms ? tasks : 32ll * sms);
   scatter_sorted_kernel<<<grid, kItemThreads, smem, s>>>(a);
-  count_launch(5);
+  count_launch(3);
   V2V_CUDA(cudaGetLastError());
   return V2V_OK;
 }
