@@ -250,9 +250,16 @@ __global__ void __launch_bounds__(kSortThreads, 2) sort_chunks_kernel(const Sort
 }
 
 // Scatter pass.  A task is (window, group of kGroup consecutive strips); an item is one strip of it: all bins of rows
-// [r0, r0+rows) as fixed-point words in shared memory.  The window's run offsets for the whole group are fetched once per
-// task (lane j of EVERY warp holds chunk j's kGroup+1 table entries: no shared staging, no barrier, and run lookups of an
-// item are register shuffles), so an item costs one global round trip (its records), three barriers and its stores.
+// [r0, r0+rows) as fixed-point words in shared memory.
+//  * The window's run offsets for the whole group are fetched once per task: lane j of EVERY warp holds chunk j's kGroup+1
+//    table entries in registers (shifted down by one per item, so the current item is always entries 0 and 1): no shared
+//    staging, no barrier, and the run lookups of an item are register shuffles.
+//  * ONE barrier per item.  Items of at most 255 records (the common case) need one 32-bit word per cell, so the tile holds
+//    two accumulators used alternately; the write-out of an item clears each cell as it reads it.  A thread that has
+//    written its share of item k goes straight on to add the records of item k+1 into the other accumulator; the only
+//    barrier sits between the adds and the write-out of the same item, and it also orders "clear of item k-1" before
+//    "adds of item k+1" on the same accumulator.  Items that need the whole tile (two words or one 64-bit word per cell)
+//    put a barrier on either side.
 constexpr int kGroup = 8;
 
 __global__ void __launch_bounds__(kItemThreads, 8) scatter_sorted_kernel(const SortedArgs a) {
@@ -260,10 +267,17 @@ __global__ void __launch_bounds__(kItemThreads, 8) scatter_sorted_kernel(const S
   const v2v_scatter_desc& d = a.d;
   const int W = d.W, H = d.H, B = d.num_bins, R = a.R, S = a.S;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  int* acc_hi = reinterpret_cast<int*>(smem_raw);
-  unsigned long long* acc64 = reinterpret_cast<unsigned long long*>(smem_raw);
-  const int plane = R * W;                            // tile layout: [bin][R*W] high words, then the same for low words
-  unsigned int* acc_lo = reinterpret_cast<unsigned int*>(acc_hi + B * plane);
+  const int plane = (R * W + 3) / 4 * 4 + 4;          // words of one bin of the tile: the strip's cells + room for the phase shift
+  const int half = B * plane;                         // words of one accumulator: tile = [2][bin][plane] 32-bit words
+  int* tile = reinterpret_cast<int*>(smem_raw);
+  const int64_t HW = static_cast<int64_t>(H) * W;
+  const bool flat = d.out_dtype != V2V_F64 && (HW & 3) == 0 && 8 * B <= kItemThreads;
+  {
+    int4* z = reinterpret_cast<int4*>(smem_raw);
+    for (int i = threadIdx.x; i < (2 * half + 3) / 4; i += kItemThreads) z[i] = make_int4(0, 0, 0, 0);
+  }
+  __syncthreads();
+  int pp = 0;                                         // accumulator of the next one-word item
   const int groups = (S + kGroup - 1) / kGroup;
   const int64_t tasks = static_cast<int64_t>(d.num_windows) * groups;
   for (int64_t task = blockIdx.x; task < tasks; task += gridDim.x) {
@@ -294,7 +308,12 @@ __global__ void __launch_bounds__(kItemThreads, 8) scatter_sorted_kernel(const S
       const int r0 = strip * R, rows = min(R, H - r0);
       const int cells = rows * W;                     // per bin
       const int64_t out_base = (static_cast<int64_t>(win) * B * H + r0) * W;      // + bin * H * W
-      const uint32_t my_beg = t[k], my_len = t[k + 1] - t[k];
+      // float32 planes are written with 16-byte stores: the strip sits in the tile at the phase of its global address, so the
+      // same four cells are one aligned 128-bit word on both sides
+      const int shift = flat ? static_cast<int>(out_base & 3) : 0;
+      const uint32_t my_beg = t[0], my_len = t[1] - t[0];
+#pragma unroll
+      for (int q = 0; q < kGroup; ++q) t[q] = t[q + 1];                         // the next item's entries move to 0 and 1
       uint32_t tot = my_len;
       for (int j = 32 + lane; j < nch; j += 32) {     // (windows of more than 32 chunks)
         const uint16_t* row = row_of(j);
@@ -303,7 +322,7 @@ __global__ void __launch_bounds__(kItemThreads, 8) scatter_sorted_kernel(const S
       const uint32_t nrec = __reduce_add_sync(0xffffffffu, tot);
       if (nrec == 0u) {                               // no event in these rows: zeros straight to HBM
         for (int b = 0; b < B; ++b) {
-          const int64_t ob = out_base + static_cast<int64_t>(b) * H * W;
+          const int64_t ob = out_base + static_cast<int64_t>(b) * HW;
           if (d.out_dtype == V2V_F64) {
             double* o = static_cast<double*>(d.voxel) + ob;
             for (int i = threadIdx.x; i < cells; i += kItemThreads) o[i] = 0.0;
@@ -315,30 +334,26 @@ __global__ void __launch_bounds__(kItemThreads, 8) scatter_sorted_kernel(const S
         continue;
       }
       // An item with at most 255 records cannot overflow ONE 32-bit word per cell at 2^-23 per unit weight (|sum| < 255 *
-      // 2^23 < 2^31; error <= n_cell * 2^-24 per cell): two shared atomics per event instead of four and half the tile to
-      // zero and read.  Larger items (hot rows, long windows) keep the exact two-word form, and an item with more than 65535
-      // records, which could overflow that (65536 same-sign unit weights on one cell), takes ONE 64-bit word per cell: same
-      // footprint, exact for any count.
-      const bool one_word = nrec <= 255u;
-      const bool wide = nrec > 65535u;
-      {
-        int4* z = reinterpret_cast<int4*>(smem_raw);
-        const int n4 = ((one_word ? 1 : 2) * B * plane + 3) / 4;
-        for (int i = threadIdx.x; i < n4; i += kItemThreads) z[i] = make_int4(0, 0, 0, 0);
-      }
-      __syncthreads();
+      // 2^23 < 2^31; error <= n_cell * 2^-24 per cell).  Larger items (hot rows, long windows) take the exact two-word form
+      // (2^-30 units split 15 + 15 bits), and an item with more than 65535 records, which could overflow that (65536
+      // same-sign unit weights on one cell), ONE 64-bit word per cell: same footprint, exact for any count.
+      const int form = nrec <= 255u ? 0 : (nrec <= 65535u ? 1 : 2);
+      int* acc_hi = tile + (form == 0 ? pp * half : 0);
+      unsigned int* acc_lo = reinterpret_cast<unsigned int*>(tile + half);
+      unsigned long long* acc64 = reinterpret_cast<unsigned long long*>(smem_raw);
+      if (form != 0) __syncthreads();                 // the whole tile: every earlier write-out (and its clearing) is done
       auto add_record = [&](const uint2 rec) {
-        const int cell = static_cast<int>(rec.x & 0xffffu);
+        const int cell = static_cast<int>(rec.x & 0xffffu) + shift;
         const int b0 = static_cast<int>((rec.x >> 16) & 0xffu) - 1;          // floor(t_norm)
         const bool negp = (rec.x >> 31) != 0u;
-        if (one_word) {
+        if (form == 0) {
           const int f1 = static_cast<int>((rec.y + 64u) >> 7), f0 = 8388608 - f1;    // weights of bins b0+1 and b0 (:79), 2^-23 units
           if (b0 >= 0 && f0 != 0) atomicAdd(&acc_hi[b0 * plane + cell], negp ? -f0 : f0);
           if (b0 + 1 < B && f1 != 0) atomicAdd(&acc_hi[(b0 + 1) * plane + cell], negp ? -f1 : f1);
           return;
         }
         const long long f1 = static_cast<long long>(rec.y), f0 = 1073741824ll - f1;   // 2^-30 units
-        if (wide) {
+        if (form == 2) {
           if (b0 >= 0 && f0 != 0) atomicAdd(&acc64[b0 * plane + cell], static_cast<unsigned long long>(negp ? -f0 : f0));
           if (b0 + 1 < B && f1 != 0) atomicAdd(&acc64[(b0 + 1) * plane + cell], static_cast<unsigned long long>(negp ? -f1 : f1));
           return;
@@ -371,64 +386,64 @@ __global__ void __launch_bounds__(kItemThreads, 8) scatter_sorted_kernel(const S
         for (uint32_t r = lane; r < len; r += 32) add_record(a.records[beg + r]);
       }
       __syncthreads();
-      // one specialised, branch-free write-out per accumulator form (a per-cell "is it zero" test compiles to a divergent
-      // branch per cell and was 60 % of this kernel's instructions)
-      const bool flat = d.out_dtype != V2V_F64 && ((static_cast<int64_t>(H) * W) & 3) == 0 && 8 * B <= kItemThreads;
+      // Write-out: one specialised, branch-free loop per accumulator form (a per-cell "is it zero" test compiles to a
+      // divergent branch per cell and was 60 % of this kernel's instructions); every cell is cleared as it is read.
       auto write_out = [&](auto form_tag) {
         constexpr int FORM = decltype(form_tag)::value;                        // 0 one word, 1 two words, 2 one 64-bit word
-        for (int b = 0; b < B; ++b) {
-          const int64_t ob = out_base + static_cast<int64_t>(b) * H * W;
-          const int* h = acc_hi + b * plane;
-          const unsigned int* l = acc_lo + b * plane;
-          const unsigned long long* q64 = acc64 + b * plane;
-          auto total = [&](int i) -> long long {                              // the cell's sum in 2^-30 units (FORM 1, 2)
-            if (FORM == 2) return static_cast<long long>(q64[i]);
-            return static_cast<long long>(h[i]) * (1 << kLoBits) + static_cast<long long>(l[i]);
-          };
-          auto valuef = [&](int i) -> float {
-            if (FORM == 0) return __fmul_rn(static_cast<float>(h[i]), 1.0f / 8388608.0f);
-            // integer -> float32 is ONE correctly rounded conversion, the power-of-two scale is exact
-            return __fmul_rn(__ll2float_rn(total(i)), 1.0f / 1073741824.0f);
-          };
-          if (d.out_dtype == V2V_F64) {
-            double* o = static_cast<double*>(d.voxel) + ob;
-            for (int i = threadIdx.x; i < cells; i += kItemThreads)
-              o[i] = FORM == 0 ? static_cast<double>(h[i]) * (1.0 / 8388608.0) : static_cast<double>(total(i)) * (1.0 / 1073741824.0);
-          } else {
-            if (flat) continue;                                               // done below, all bins in one loop
-            float* o = static_cast<float*>(d.voxel) + ob;
-            const int head = min(static_cast<int>((4 - (ob & 3)) & 3), cells);
-            const int n4 = (cells - head) / 4;
-            for (int q = threadIdx.x; q < n4; q += kItemThreads) {
-              const int i = head + 4 * q;
-              st_stream_f32x4(o + i, valuef(i), valuef(i + 1), valuef(i + 2), valuef(i + 3));
-            }
-            // (up to three cells before and after the aligned part)
-            if (threadIdx.x < head) st_stream_f32(o + threadIdx.x, valuef(threadIdx.x));
-            const int tail0 = head + 4 * n4;
-            if (static_cast<int>(threadIdx.x) < cells - tail0) st_stream_f32(o + tail0 + threadIdx.x, valuef(tail0 + threadIdx.x));
+        auto take = [&](int idx) -> long long {                               // cell idx = bin * plane + i: its sum, cleared
+          if (FORM == 0) {
+            const int v = acc_hi[idx];
+            acc_hi[idx] = 0;
+            return v;
           }
-        }
+          if (FORM == 2) {
+            const long long v = static_cast<long long>(acc64[idx]);
+            acc64[idx] = 0ull;
+            return v;
+          }
+          const long long v = static_cast<long long>(acc_hi[idx]) * (1 << kLoBits) + static_cast<long long>(acc_lo[idx]);
+          acc_hi[idx] = 0;
+          acc_lo[idx] = 0u;
+          return v;
+        };
+        // integer -> float32 is ONE correctly rounded conversion, the power-of-two scale is exact
+        auto takef = [&](int idx) -> float {
+          if (FORM == 0) return __fmul_rn(static_cast<float>(static_cast<int>(take(idx))), 1.0f / 8388608.0f);
+          return __fmul_rn(__ll2float_rn(take(idx)), 1.0f / 1073741824.0f);
+        };
         if (flat) {
           // float32 planes whose size is a multiple of 4 cells: every bin's slice of the strip has the same 16-byte phase,
-          // so the B slices are written by ONE loop over (bin, group of 4 cells) - no per-bin loop overhead (it was 5 x ~50
-          // instructions per warp and item around a single store).  (bin, q) advance incrementally: no division.
+          // so the B slices are written by ONE loop over (bin, group of 4 cells); (bin, q) advance incrementally
           float* o0 = static_cast<float*>(d.voxel) + out_base;
           const int head = min(static_cast<int>((4 - (out_base & 3)) & 3), cells);
           const int n4 = (cells - head) / 4;
-          const int64_t HW = static_cast<int64_t>(H) * W;
-          auto cellf = [&](int b, int i) -> float {
-            if (FORM == 0) return __fmul_rn(static_cast<float>(acc_hi[b * plane + i]), 1.0f / 8388608.0f);
-            const long long tot = FORM == 2 ? static_cast<long long>(acc64[b * plane + i])
-                                            : static_cast<long long>(acc_hi[b * plane + i]) * (1 << kLoBits) + static_cast<long long>(acc_lo[b * plane + i]);
-            return __fmul_rn(__ll2float_rn(tot), 1.0f / 1073741824.0f);
-          };
           if (n4 > 0) {
             int b = 0, q = threadIdx.x;
             while (q >= n4 && b < B) q -= n4, ++b;
             while (b < B) {
-              const int i = head + 4 * q;
-              st_stream_f32x4(o0 + b * HW + i, cellf(b, i), cellf(b, i + 1), cellf(b, i + 2), cellf(b, i + 3));
+              const int i = head + 4 * q, idx = b * plane + shift + i;         // idx is a multiple of 4
+              float v0, v1, v2, v3;
+              if (FORM == 0) {
+                int4* c = reinterpret_cast<int4*>(acc_hi + idx);
+                const int4 h = *c;
+                *c = make_int4(0, 0, 0, 0);
+                constexpr float sc = 1.0f / 8388608.0f;
+                v0 = __fmul_rn(static_cast<float>(h.x), sc), v1 = __fmul_rn(static_cast<float>(h.y), sc);
+                v2 = __fmul_rn(static_cast<float>(h.z), sc), v3 = __fmul_rn(static_cast<float>(h.w), sc);
+              } else if (FORM == 1) {
+                int4* ch = reinterpret_cast<int4*>(acc_hi + idx);
+                uint4* cl = reinterpret_cast<uint4*>(acc_lo + idx);
+                const int4 h = *ch;
+                const uint4 l = *cl;
+                *ch = make_int4(0, 0, 0, 0);
+                *cl = make_uint4(0u, 0u, 0u, 0u);
+                constexpr float sc = 1.0f / 1073741824.0f;
+                auto f = [&](int hv, unsigned int lv) { return __fmul_rn(__ll2float_rn(static_cast<long long>(hv) * (1 << kLoBits) + static_cast<long long>(lv)), sc); };
+                v0 = f(h.x, l.x), v1 = f(h.y, l.y), v2 = f(h.z, l.z), v3 = f(h.w, l.w);
+              } else {
+                v0 = takef(idx), v1 = takef(idx + 1), v2 = takef(idx + 2), v3 = takef(idx + 3);
+              }
+              st_stream_f32x4(o0 + b * HW + i, v0, v1, v2, v3);
               q += kItemThreads;
               while (q >= n4 && b < B) q -= n4, ++b;
             }
@@ -437,14 +452,27 @@ __global__ void __launch_bounds__(kItemThreads, 8) scatter_sorted_kernel(const S
           if (static_cast<int>(threadIdx.x) < 8 * B) {                       // up to three cells before and after the aligned part
             const int b = threadIdx.x >> 3, j = threadIdx.x & 7;
             const int i = j < 4 ? j : tail0 + j - 4;
-            if (j < 4 ? j < head : i < cells) st_stream_f32(o0 + b * HW + i, cellf(b, i));
+            if (j < 4 ? j < head : i < cells) st_stream_f32(o0 + b * HW + i, takef(b * plane + shift + i));
+          }
+          return;
+        }
+        for (int b = 0; b < B; ++b) {
+          const int64_t ob = out_base + static_cast<int64_t>(b) * HW;
+          if (d.out_dtype == V2V_F64) {
+            double* o = static_cast<double*>(d.voxel) + ob;
+            for (int i = threadIdx.x; i < cells; i += kItemThreads)
+              o[i] = static_cast<double>(take(b * plane + i)) * (FORM == 0 ? 1.0 / 8388608.0 : 1.0 / 1073741824.0);
+          } else {
+            float* o = static_cast<float*>(d.voxel) + ob;
+            for (int i = threadIdx.x; i < cells; i += kItemThreads) st_stream_f32(o + i, takef(b * plane + i));
           }
         }
       };
-      if (wide) write_out(std::integral_constant<int, 2>{});
-      else if (one_word) write_out(std::integral_constant<int, 0>{});
+      if (form == 2) write_out(std::integral_constant<int, 2>{});
+      else if (form == 0) write_out(std::integral_constant<int, 0>{});
       else write_out(std::integral_constant<int, 1>{});
-      __syncthreads();
+      if (form != 0) __syncthreads();                 // (the next item may add into either half)
+      else pp ^= 1;
     }
   }
 }
@@ -456,7 +484,7 @@ static size_t align16(size_t n) { return (n + 15) / 16 * 16; }
 size_t scatter_sorted_workspace_bytes(const v2v_scatter_desc& d, int* rows_per_strip, int* strips) {
   if (d.H <= 0 || d.W <= 0) return 0;
   const int64_t per_row = static_cast<int64_t>(d.num_bins) * d.W * 8;
-  int R = static_cast<int>(kTileBudget / per_row);
+  int R = static_cast<int>((kTileBudget - static_cast<int64_t>(d.num_bins) * 7 * 8) / per_row);   // (+ up to 7 padding words per bin)
   if (R < 1) return 0;                                            // one row of all bins does not fit: not eligible
   if (static_cast<int64_t>(R) * d.W > 65535) R = 65535 / d.W;     // 16-bit cell index in the record
   if (R > d.H) R = d.H;
@@ -503,7 +531,7 @@ int launch_scatter_sorted(const v2v_scatter_desc& d, cudaStream_t s) {
   a.wcs = reinterpret_cast<WinConst*>(p);
   window_constants_kernel<<<(d.num_windows + 127) / 128, 128, 0, s>>>(a);
   if (chunks > 0) sort_chunks_kernel<<<static_cast<unsigned int>(chunks), kSortThreads, 0, s>>>(a);
-  const size_t smem = static_cast<size_t>(2) * d.num_bins * a.R * d.W * 4 + 16;
+  const size_t smem = static_cast<size_t>(2) * d.num_bins * ((a.R * d.W + 3) / 4 * 4 + 4) * 4 + 16;
   static std::atomic<uint64_t> configured{0};
   int dev = 0, sms = 148;
   V2V_CUDA(cudaGetDevice(&dev));
