@@ -35,11 +35,12 @@ constexpr int kChunk = kSortThreads * kPer;    // events per CTA of the sort pas
 constexpr int kMaxCounters = 2048;             // (window, strip) counters of one pass over a chunk (8 KB of shared memory)
 constexpr int kItemThreads = 256;
 constexpr int kTileBudget = 28 * 1024;    // eight CTAs per SM: an item is short (~200 records), its latency is hidden across CTAs
+constexpr int kTileBudgetLarge = 56 * 1024;   // many bins (one row of 15 x 346 cells is 41 KB): four CTAs per SM
 
 struct SortedArgs {
   v2v_scatter_desc d;
   int R, S;               // rows per strip, strips per window
-  uint32_t r_magic;       // y / R == (y * r_magic) >> 32 for y < 65536
+  uint64_t r_magic;       // y / R == (y * r_magic) >> 32 for y < 65536 (2^32 for R = 1: 33 bits)
   int64_t items;          // Wn * S
   WinConst* wcs;          // [Wn]
   int32_t* chunk_w0;      // [chunks + 1]: window of the chunk's first event (written per window, no search); [chunks] = Wn - 1
@@ -216,7 +217,7 @@ __global__ void __launch_bounds__(kSortThreads, 2) sort_chunks_kernel(const Sort
       continue;
     }
     if (pw == 0.f) continue;                                               // one-polarity modes: weight 0 contributes nothing
-    const uint32_t strip = static_cast<uint32_t>((static_cast<uint64_t>(y) * a.r_magic) >> 32);
+    const uint32_t strip = static_cast<uint32_t>((static_cast<uint64_t>(y) * a.r_magic) >> 32);     // y / R
     const uint32_t cell = static_cast<uint32_t>((y - static_cast<long long>(strip) * a.R) * W + x);
     const uint32_t frac = static_cast<uint32_t>(__double2int_rn(__dmul_rn(__dsub_rn(tn, fl), 1073741824.0)));   // in [0, 2^30]
     rec[u] = make_uint2(cell | (static_cast<uint32_t>(static_cast<int>(fl) + 1) << 16) | (pw < 0.f ? 0x80000000u : 0u), frac);
@@ -484,7 +485,9 @@ static size_t align16(size_t n) { return (n + 15) / 16 * 16; }
 size_t scatter_sorted_workspace_bytes(const v2v_scatter_desc& d, int* rows_per_strip, int* strips) {
   if (d.H <= 0 || d.W <= 0) return 0;
   const int64_t per_row = static_cast<int64_t>(d.num_bins) * d.W * 8;
-  int R = static_cast<int>((kTileBudget - static_cast<int64_t>(d.num_bins) * 7 * 8) / per_row);   // (+ up to 7 padding words per bin)
+  const int64_t pad = static_cast<int64_t>(d.num_bins) * 7 * 8;                                 // (+ up to 7 padding words per bin)
+  int R = static_cast<int>((kTileBudget - pad) / per_row);
+  if (R < 1) R = static_cast<int>((kTileBudgetLarge - pad) / per_row);
   if (R < 1) return 0;                                            // one row of all bins does not fit: not eligible
   if (static_cast<int64_t>(R) * d.W > 65535) R = 65535 / d.W;     // 16-bit cell index in the record
   if (R > d.H) R = d.H;
@@ -515,7 +518,7 @@ int launch_scatter_sorted(const v2v_scatter_desc& d, cudaStream_t s) {
   SortedArgs a;
   a.d = d;
   scatter_sorted_workspace_bytes(d, &a.R, &a.S);
-  a.r_magic = static_cast<uint32_t>(((1ull << 32) + a.R - 1) / a.R);          // exact for y < 65536 (y * (R-1) < 2^32)
+  a.r_magic = ((1ull << 32) + a.R - 1) / a.R;                                 // exact for y < 65536 (y * (R-1) < 2^32)
   a.items = static_cast<int64_t>(d.num_windows) * a.S;
   const size_t chunks = static_cast<size_t>((d.num_events + kChunk - 1) / kChunk);
   char* p = static_cast<char*>(d.workspace);
@@ -537,7 +540,7 @@ int launch_scatter_sorted(const v2v_scatter_desc& d, cudaStream_t s) {
   V2V_CUDA(cudaGetDevice(&dev));
   const uint64_t bit = 1ull << (dev & 63);
   if (!(configured.load(std::memory_order_acquire) & bit)) {
-    V2V_CUDA(cudaFuncSetAttribute(scatter_sorted_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 30 * 1024));
+    V2V_CUDA(cudaFuncSetAttribute(scatter_sorted_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTileBudgetLarge + 1024));
     configured.fetch_or(bit, std::memory_order_release);
   }
   V2V_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
