@@ -89,7 +89,8 @@ def voxelize_windows(xs, ys, ts, ps, window_offsets, num_bins: int, height: int,
     non-decreasing inside every window (true for every h5 file the reference's converters write); the library counts
     violations on the device in the same call.  ``validate`` (default: on, unless ``return_dropped`` hands the counters
     back for the caller to check without a sync here) reads that counter and raises ``ValueError`` for unsorted input
-    instead of returning mis-binned voxels.  With ``return_dropped`` the result is ``(out, dropped, unsorted)``.
+    instead of returning mis-binned voxels.  With ``return_dropped`` the result is ``(out, dropped, unsorted)``;
+    ``validate=False`` without ``return_dropped`` skips the check pass (one read of the timestamps) altogether.
     """
     dev = torch.device(device)
     modes = {"h5_discrete": _lib.SCATTER_H5_DISCRETE, "h5_interp": _lib.SCATTER_H5_INTERP,
@@ -126,7 +127,7 @@ def voxelize_windows(xs, ys, ts, ps, window_offsets, num_bins: int, height: int,
     d.out_dtype = {torch.float32: _lib.F32, torch.float64: _lib.F64}[out.dtype]
     d.xs, d.ys, d.ts, d.ps = _ptr(xs_t), _ptr(ys_t), _ptr(ts_t), _ptr(ps_t)
     d.window_offsets, d.voxel, d.dropped = _ptr(off_t), _ptr(out), _ptr(dropped)
-    d.unsorted = _ptr(unsorted)
+    d.unsorted = _ptr(unsorted) if (validate or return_dropped) else None     # validate=False without the counters: no check pass
     d.kernel_flags, d.tuning_splits, d.tuning_smem_kb = int(kernel_flags) | _env_flags(), _env_int("V2V_SCATTER_SPLITS"), _env_int("V2V_SCATTER_SMEM_KB")
     work = torch.empty((int(_lib.load().v2v_scatter_workspace_bytes(C.byref(d))) + 15) // 16 * 2, dtype=torch.int64, device=dev)
     d.workspace, d.workspace_bytes = _ptr(work), work.numel() * 8
