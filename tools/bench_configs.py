@@ -39,6 +39,33 @@ def timeit(fn, iters=10, warm=3):
     return float(np.median(ms)), float(np.min(ms))
 
 
+def timeit_graph(fn, n=20, reps=5):
+    """The same call captured n times in one CUDA graph and replayed: what a training loop that captures its data path
+    sees (no per-call Python / ctypes / allocator time between the launches).  Returns ms per call (min over replays)."""
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        fn()
+        fn()
+    torch.cuda.current_stream().wait_stream(side)
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        for _ in range(n):
+            fn()
+    g.replay()
+    torch.cuda.synchronize()
+    ms = []
+    for _ in range(reps):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        g.replay()
+        b.record()
+        torch.cuda.synchronize()
+        ms.append(a.elapsed_time(b) / n)
+    return float(np.min(ms))
+
+
 def walk(B, N, H, W, seed, dev):
     g = torch.Generator(device=dev)
     g.manual_seed(seed)
@@ -72,9 +99,10 @@ def secondary_configs(dev, cpu_arm=True):
     u0 = torch.rand((1, 256, 256), dtype=torch.float64, device=dev)
     out1 = torch.empty((1, 39, 1, 256, 256), dtype=torch.float32, device=dev)
     pos = torch.full((1,), 0.2, dtype=torch.float64, device=dev)
-    med, mn = timeit(lambda: v2v.frames_to_voxel(fr, pos, pos, num_bins=1, u0=u0, out=out1), 20)
+    f1 = lambda: v2v.frames_to_voxel(fr, pos, pos, num_bins=1, u0=u0, out=out1)
+    med, mn = timeit(f1, 20)
     by = 40 * 65536 + 39 * 65536 * 4
-    res["config1_one_clip_40x256x256"] = {"ms": med, "ms_min": mn, "clips_per_s": 1e3 / med, "Mpix_frames_per_s": 39 * 65536 / med / 1e3,
+    res["config1_one_clip_40x256x256"] = {"ms": med, "ms_min": mn, "ms_graph_replay": timeit_graph(f1), "clips_per_s": 1e3 / med, "Mpix_frames_per_s": 39 * 65536 / med / 1e3,
                                           "GBps": by / med / 1e6, "frac": by / med / 1e6 / PEAK, "note": "single small clip: launch/latency bound (SURVEY §7)"}
     # ... and as the drop-in call a user of the reference makes: EventEmulator(...).video_to_voxel, NumPy in -> NumPy out
     vid1 = fr[0].cpu().numpy()
@@ -103,12 +131,19 @@ def secondary_configs(dev, cpu_arm=True):
     frt = walk(12, 201, 128, 128, 3, dev)
     outt = torch.empty((12, 40, 5, 128, 128), dtype=torch.float32, device=dev)
     c = lambda v, n: torch.full((n,), v, dtype=torch.float64, device=dev)
-    med, mn = timeit(lambda: v2v.frames_to_voxel(frt, c(0.3, 12), c(0.4, 12), num_bins=5, noise="philox", base_noise_std=c(0.05, 12),
-                                                 hot_pixel_fraction=c(0.0005, 12), hot_pixel_std=c(5.0, 12), out=outt), 20)
+    tp, tn_, tstd, tfrac, thstd = c(0.3, 12), c(0.4, 12), c(0.05, 12), c(0.0005, 12), c(5.0, 12)
+    ft = lambda: v2v.frames_to_voxel(frt, tp, tn_, num_bins=5, noise="philox", base_noise_std=tstd, hot_pixel_fraction=tfrac,
+                                     hot_pixel_std=thstd, seed=7, out=outt)
+    med, mn = timeit(ft, 20)
+    mg = timeit_graph(ft)
     by = 12 * 128 * 128 * (201 + 200 * 4)
-    res["train_batch_12x201x128x128_philox"] = {"ms": med, "clips_per_s": 12e3 / med, "Mpix_frames_per_s": 12 * 200 * 16384 / med / 1e3,
+    res["train_batch_12x201x128x128_philox"] = {"ms": med, "ms_graph_replay": mg, "clips_per_s": 12e3 / med,
+                                                "Mpix_frames_per_s": 12 * 200 * 16384 / med / 1e3,
                                                 "GBps": by / med / 1e6, "frac": by / med / 1e6 / PEAK,
-                                                "note": "the real training batch; 196k pixels of parallelism only"}
+                                                "frac_graph_replay": by / mg / 1e6 / PEAK,
+                                                "note": "the real training batch; 196k pixels of parallelism only; ms = one call from "
+                                                        "Python (ctypes + tensor bookkeeping between launches), ms_graph_replay = the same "
+                                                        "call replayed from a CUDA graph"}
     if cpu_arm:
         vt = frt[0].cpu().numpy()
         rs = np.random.RandomState(0)
