@@ -444,6 +444,26 @@ __global__ void __launch_bounds__(kScatterThreads, 2) scatter_kernel(const Scatt
         const int head = static_cast<int>((4 - (out_base & 3)) & 3);
         for (int i = threadIdx.x; i < min(head, cells); i += kScatterThreads) st_stream_f32(o + i, valuef(i));
         const int n4 = (cells - min(head, cells)) / 4;
+        if (packed) {
+          // Packed 16-bit counters: four cells are two words (three when the strip starts on an odd cell).  One PRMT drops a
+          // counter c under the high half 0x4b3f: the float with those bits is 12517376 + c, exactly, and the count is
+          // c - 32768, so one FADD finishes it (was a variable shift, a mask, an integer add and an FADD per cell, behind
+          // one LDS per cell: 49 instructions per four cells, half of this kernel's instructions).
+          const unsigned int* wq = reinterpret_cast<const unsigned int*>(acc_i);
+          const bool odd = (head & 1) != 0;
+          auto cnt = [](unsigned int w, unsigned int sel) { return __fadd_rn(__uint_as_float(__byte_perm(w, 0x4b3fu, sel)), -12550144.0f); };
+          for (int q = threadIdx.x; q < n4; q += kScatterThreads) {
+            const int i = head + 4 * q, wi = i >> 1;
+            unsigned int a, b;
+            if (!odd) {
+              a = wq[wi], b = wq[wi + 1];
+            } else {
+              const unsigned int w0 = wq[wi], w1 = wq[wi + 1], w2 = wq[wi + 2];
+              a = __funnelshift_r(w0, w1, 16), b = __funnelshift_r(w1, w2, 16);
+            }
+            st_stream_f32x4(o + i, cnt(a, 0x5410u), cnt(a, 0x5432u), cnt(b, 0x5410u), cnt(b, 0x5432u));
+          }
+        } else
         for (int q = threadIdx.x; q < n4; q += kScatterThreads) {
           const int i = head + 4 * q;
           st_stream_f32x4(o + i, valuef(i), valuef(i + 1), valuef(i + 2),
