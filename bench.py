@@ -692,7 +692,7 @@ def main():
     ap.add_argument("--clips", type=int, default=32, help="clips per step per GPU")
     ap.add_argument("--seed", type=int, default=2026)
     ap.add_argument("--e2e-clips", type=int, default=16)
-    ap.add_argument("--e2e-chunk", type=int, default=2)
+    ap.add_argument("--e2e-chunk", type=int, default=1, help="clips per H2D / kernel / D2H chunk of the host pipeline (same-box sweep: 1: 368, 2: 363, 4: 353 clips/s)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-secondary", action="store_true", help="skip the secondary block (BASELINE configs 1, 3, 4, 5-shape, train batch)")

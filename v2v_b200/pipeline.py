@@ -16,7 +16,7 @@ from .esim import frames_to_voxel
 
 
 class HostPipeline:
-    def __init__(self, voxelizer, device="cuda", clips_per_chunk: int = 2, seed: int = 0, depth: int = 3):
+    def __init__(self, voxelizer, device="cuda", clips_per_chunk: int = 1, seed: int = 0, depth: int = 3):
         self.vz = voxelizer
         self.dev = torch.device(device)
         self.chunk = int(clips_per_chunk)
