@@ -365,11 +365,18 @@ __global__ void __launch_bounds__(THREADS, CTAS) esim_fast_kernel(const EsimArgs
           double q;
           const double an = multi_cross(fabs(xr), down ? neg : pos, cta_rcp[down ? 1 : 0], &q);
           pot[k] = down ? -an : an;
+          // What the common path counted for this pixel.  Asking x0 >= pos again makes the compiler carry the common path's
+          // predicates into here as a bit mask (8 ALU-pipe LOP3 per interval); reading it back from the output word (+1.0f
+          // up, -1.0f down) trades them for register moves on the FMA pipe.  Same-box A/B: the noise-free variants, short of
+          // ALU slots, gain 7 % from the read-back; the noise variants, whose FMA pipe carries the generator, lose 10 %.
+          const int counted = __float_as_int(o[k]);
+          const int cu = kPh ? (x0[k] >= pos ? 1 : 0) : (counted > 0 ? 1 : 0);
+          const int cd = kPh ? (x0[k] <= mneg ? 1 : 0) : (counted < 0 ? 1 : 0);
           o[k] = static_cast<float>(down ? -q : q);
           if (STATS) {          // replace what the common path counted for this pixel (from x without the hot noise)
             const int qi = static_cast<int>(q);
-            xpos += static_cast<unsigned int>((down ? 0 : qi) - (x0[k] >= pos ? 1 : 0));
-            xneg += static_cast<unsigned int>((down ? qi : 0) - (x0[k] <= mneg ? 1 : 0));
+            xpos += static_cast<unsigned int>((down ? 0 : qi) - cu);
+            xneg += static_cast<unsigned int>((down ? qi : 0) - cd);
           }
         }
       }
