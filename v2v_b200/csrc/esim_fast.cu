@@ -107,8 +107,8 @@ struct FastSmem {
   static constexpr int hot = dir + (kPh ? kDirEntries * 16 : 0);
   static constexpr int f255 = hot + (kPh ? THREADS * 16 : 0);
   static constexpr int rcp = f255 + (FRAMES ? 256 * 4 : 0);
-  static constexpr int xst = rcp + 16;                        // statistics parked in shared memory: uint2 per thread + uint2 per warp
-  static constexpr int fnum = xst + THREADS * 8 + (THREADS / 32) * 8;
+  static constexpr int xst = rcp + 16;                        // the warps' running event totals (variants that park them): uint2 per warp
+  static constexpr int fnum = xst + (THREADS / 32) * 8;
   static __host__ __device__ size_t bytes(int N) { return fnum + (GATHER ? static_cast<size_t>(N) * 4 : 0); }
   static __host__ __device__ size_t ring(int N) { return (bytes(N) + 127) / 128 * 128; }                       // offset of the staged frame ring
   static size_t bytes_staged(int N) { return ring(N) + static_cast<size_t>(kRingDepth) * THREADS * 4 + 16 * kRingDepth; }
@@ -235,26 +235,30 @@ __global__ void __launch_bounds__(THREADS, CTAS) esim_fast_kernel(const EsimArgs
   // back exactly while #up < 4096 and #down < 512 per lane — they are unpacked every 32 intervals (<= 128 each).  A
   // multi-threshold crossing has already contributed one event here; the exact path adds the other q-1.
   uint32_t su = 0u, sv = 0u;
-  // The surplus of the multi-threshold crossings (own slot per thread) and the warp's running totals (one slot per warp,
-  // written by its first working lane) live in shared memory: four registers less in a loop that is short of them
-  // (with statistics the kernel was 15 % slower than without, 4 % of it the adds themselves).
-  uint2* xst_s = reinterpret_cast<uint2*>(dyn_smem + L::xst);
-  uint2* wst_s = xst_s + THREADS;
-  if (STATS) {
-    xst_s[threadIdx.x] = make_uint2(0u, 0u);
+  unsigned int xpos = 0u, xneg = 0u;      // extra events of the multi-threshold crossings since the last flush
+  // This warp's event totals.  The noise variants without frame output, which are short of registers in the loop, park them
+  // in shared memory (one slot per warp, written by its first working lane: same-box -3.5 % on config 2); with the frame
+  // output (config-5 shape, 25 intervals per clip) the parked form is 3.4 % slower, so those keep them in registers.
+  constexpr bool kPark = STATS && kPh && !FRAMES;
+  unsigned int wpos = 0u, wneg = 0u;
+  uint2* wst_s = reinterpret_cast<uint2*>(dyn_smem + L::xst);
+  if (kPark) {
     if ((threadIdx.x & 31) == 0) wst_s[threadIdx.x >> 5] = make_uint2(0u, 0u);
     __syncwarp();
   }
   auto flush_stats = [&]() {              // unpack, add across the warp with one REDUX each; registers only
     const uint32_t nu = ((su >> 20) * 3071u) & 4095u;                     // 1023 * 3071 = 1 (mod 4096)
     const uint32_t nd = ((((sv >> 23) - 127u * nu) & 511u) * 127u) & 511u;   // 383 * 127 = 1 (mod 512)
-    const uint2 x = xst_s[threadIdx.x];
-    xst_s[threadIdx.x] = make_uint2(0u, 0u);
-    const unsigned int rp = __reduce_add_sync(full, nu + x.x), rn = __reduce_add_sync(full, nd + x.y);
-    if ((threadIdx.x & 31) == (__ffs(full) - 1)) {
-      uint2 w = wst_s[threadIdx.x >> 5];
-      w.x += rp, w.y += rn;
-      wst_s[threadIdx.x >> 5] = w;
+    const unsigned int rp = __reduce_add_sync(full, nu + xpos), rn = __reduce_add_sync(full, nd + xneg);
+    xpos = xneg = 0u;
+    if (kPark) {
+      if ((threadIdx.x & 31) == (__ffs(full) - 1)) {
+        uint2 w = wst_s[threadIdx.x >> 5];
+        w.x += rp, w.y += rn;
+        wst_s[threadIdx.x >> 5] = w;
+      }
+    } else {
+      wpos += rp, wneg += rn;
     }
     su = sv = 0u;
   };
@@ -379,28 +383,29 @@ __global__ void __launch_bounds__(THREADS, CTAS) esim_fast_kernel(const EsimArgs
           double q;
           const double an = multi_cross(fabs(xr), down ? neg : pos, cta_rcp[down ? 1 : 0], &q);
           pot[k] = down ? -an : an;
-          // Replace what the common path counted for this pixel (from x without the hot noise).  Two forms, chosen by a
-          // same-box A/B per variant; neither repeats a compare of x0 in here, which would make the compiler carry the common
-          // path's predicates across the branch as a bit mask (8 ALU-pipe LOP3 per interval: with statistics the noise
-          // kernel ran 15 % slower than without).  Noise variants: take the very words the common path added (hu[k], the
-          // bits of o[k]) back out of the packed sums (-3.1 %).  Noise-free variants: read the count back from the sign of
-          // the output word (-6 %; the subtract form costs them 2 %).
+          // Replace what the common path counted for this pixel (from x without the hot noise).  Three forms, chosen per
+          // variant by same-box A/Bs (profiles/r02_esim_experiments.md section 7).  Asking x0 >= pos again in here makes the
+          // compiler carry the common path's predicates across the branch as a bit mask (8 ALU-pipe LOP3 per interval: with
+          // statistics the noise kernel ran 15 % slower than without).  Noise variants: take the very words the common
+          // path added (hu[k], the bits of o[k]) back out of the packed sums (-5.7 %).  Noise-free variants: read the count
+          // back from the sign of the output word (-6 %; the subtract form costs them 2 %).
           const uint32_t counted_v = __float_as_uint(o[k]);
           o[k] = static_cast<float>(down ? -q : q);
           if (STATS) {
             const int qi = static_cast<int>(q);
-            uint2 x = xst_s[threadIdx.x];
-            if (kPh) {
+            if (kPh && !FRAMES) {
               su -= hu[k];
               sv -= counted_v;
-              x.x += static_cast<unsigned int>(down ? 0 : qi);
-              x.y += static_cast<unsigned int>(down ? qi : 0);
+              xpos += static_cast<unsigned int>(down ? 0 : qi);
+              xneg += static_cast<unsigned int>(down ? qi : 0);
+            } else if (kPh) {       // (with the frame output in the loop the plain compare form is 4 % faster: config-5 shape)
+              xpos += static_cast<unsigned int>((down ? 0 : qi) - (x0[k] >= pos ? 1 : 0));
+              xneg += static_cast<unsigned int>((down ? qi : 0) - (x0[k] <= mneg ? 1 : 0));
             } else {
               const int counted = static_cast<int>(counted_v);
-              x.x += static_cast<unsigned int>((down ? 0 : qi) - (counted > 0 ? 1 : 0));
-              x.y += static_cast<unsigned int>((down ? qi : 0) - (counted < 0 ? 1 : 0));
+              xpos += static_cast<unsigned int>((down ? 0 : qi) - (counted > 0 ? 1 : 0));
+              xneg += static_cast<unsigned int>((down ? qi : 0) - (counted < 0 ? 1 : 0));
             }
-            xst_s[threadIdx.x] = x;
           }
         }
       }
@@ -484,7 +489,7 @@ __global__ void __launch_bounds__(THREADS, CTAS) esim_fast_kernel(const EsimArgs
     // One pair of global reductions per warp, no CTA barrier and no shared-memory stage: a warp that is done leaves.
     flush_stats();
     if ((threadIdx.x & 31) == (__ffs(full) - 1)) {
-      const unsigned int wpos = wst_s[threadIdx.x >> 5].x, wneg = wst_s[threadIdx.x >> 5].y;
+      if (kPark) wpos = wst_s[threadIdx.x >> 5].x, wneg = wst_s[threadIdx.x >> 5].y;
       if (wpos) atomicAdd(reinterpret_cast<unsigned long long*>(d.stats + 2 * blockIdx.y), static_cast<unsigned long long>(wpos));
       if (wneg) atomicAdd(reinterpret_cast<unsigned long long*>(d.stats + 2 * blockIdx.y) + 1, static_cast<unsigned long long>(wneg));
     }
