@@ -330,6 +330,20 @@ int v2v_voxel_value_hist(const float* voxel, int32_t clips, int64_t elems_per_cl
 /* In place: voxel[c, e] = voxel > 0 ? voxel / pos_max[c] : voxel / neg_max[c]  (float32 division, :165). */
 int v2v_voxel_normalize(float* voxel, int32_t clips, int64_t elems_per_clip, const float* pos_max, const float* neg_max, void* stream);
 
+/* ======================================================================= *
+ * 8. Learned-representation scatter (NER-Net quantization layer)
+ *    replaces  vox.put_(idx, values, accumulate=True) called once per temporal bin
+ *                                              model/nernet/representation_modules.py:143-168, 228-248
+ *    out[min(idx[e] + b*bin_stride, out_numel-1)] += values[b*n + e]   for b in [0, num_bins), e in [0, n)
+ *    (the reference clamps the index from above, :166/:246; a negative index is counted in `bad` and skipped, where
+ *    put_ would raise).  All bins in ONE launch, float32 atomics like torch's CUDA put_.  `v2v_take_bins` is the
+ *    gather of the backward pass: grad_values[b*n + e] = grad_out[that index].
+ * ======================================================================= */
+int v2v_put_accumulate_bins(float* out, int64_t out_numel, const int64_t* idx, const float* values, int64_t n, int32_t num_bins,
+                            int64_t bin_stride, long long* bad, void* stream);
+int v2v_take_bins(const float* src, int64_t src_numel, const int64_t* idx, float* values_out, int64_t n, int32_t num_bins,
+                  int64_t bin_stride, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

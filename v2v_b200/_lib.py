@@ -120,6 +120,8 @@ SYMBOLS = {
     "v2v_voxel_add_noise": (C.c_int, [_p, C.c_int64, _p, _p, C.c_double, C.c_double, C.c_int, C.c_int, C.c_uint64, C.c_uint64, _p]),
     "v2v_voxel_add_map": (C.c_int, [_p, C.c_int64, C.c_int64, _p, _p]),
     "v2v_voxel_bin_abs_sums": (C.c_int, [_p, C.c_int64, C.c_int32, C.c_int64, _p, _p]),
+    "v2v_put_accumulate_bins": (C.c_int, [_p, C.c_int64, _p, _p, C.c_int64, C.c_int32, C.c_int64, _p, _p]),
+    "v2v_take_bins": (C.c_int, [_p, C.c_int64, _p, _p, C.c_int64, C.c_int32, C.c_int64, _p]),
     "v2v_voxel_value_hist": (C.c_int, [_p, C.c_int32, C.c_int64, _p, _p]),
     "v2v_voxel_normalize": (C.c_int, [_p, C.c_int32, C.c_int64, _p, _p, _p]),
     "v2v_bgr_to_gray": (C.c_int, [_p, C.c_int32, _p, C.c_int64, _p]),

@@ -89,3 +89,55 @@ def bin_abs_sums(voxel: torch.Tensor) -> torch.Tensor:
             _lib.check(_lib.load().v2v_voxel_bin_abs_sums(_p(voxel), groups, bins, plane, _p(sums),
                                                           C.c_void_p(torch.cuda.current_stream(voxel.device).cuda_stream)))
     return sums
+
+
+# ---- NER-Net's learned event representation (model/nernet/representation_modules.py:143-168, 228-248) ----------------
+class _PutAccumulateBins(torch.autograd.Function):
+    """vox.put_(idx + bin_stride*b, values[b], accumulate=True) for every bin b in one launch, differentiable in ``values``
+    (the quantization layer's MLP output) and in ``vox``."""
+
+    @staticmethod
+    def forward(ctx, vox, idx, values, bin_stride):
+        n, bins = idx.numel(), values.shape[0]
+        bad = torch.zeros(1, dtype=torch.int64, device=vox.device)
+        with torch.cuda.device(vox.device):
+            _lib.check(_lib.load().v2v_put_accumulate_bins(_p(vox), vox.numel(), _p(idx), _p(values), n, bins, int(bin_stride), _p(bad),
+                                                           C.c_void_p(torch.cuda.current_stream(vox.device).cuda_stream)))
+        ctx.save_for_backward(idx)
+        ctx.bin_stride, ctx.bins, ctx.bad = int(bin_stride), bins, bad
+        ctx.mark_dirty(vox)
+        return vox
+
+    @staticmethod
+    def backward(ctx, grad_vox):
+        (idx,) = ctx.saved_tensors
+        g = grad_vox.contiguous()
+        gv = torch.empty((ctx.bins, idx.numel()), dtype=torch.float32, device=g.device)
+        with torch.cuda.device(g.device):
+            _lib.check(_lib.load().v2v_take_bins(_p(g), g.numel(), _p(idx), _p(gv), idx.numel(), ctx.bins, ctx.bin_stride,
+                                                 C.c_void_p(torch.cuda.current_stream(g.device).cuda_stream)))
+        return grad_vox, None, gv, None
+
+
+def put_accumulate_bins(vox: torch.Tensor, idx_before_bins: torch.Tensor, values: torch.Tensor, bin_stride: int) -> torch.Tensor:
+    """The scatter of NER-Net's quantization layers: the reference loops over the C temporal bins and calls
+    ``vox.put_(clamp(idx_before_bins + W*H*i_bin, max=len(vox)-1), values_i, accumulate=True)`` once per bin
+    (model/nernet/representation_modules.py:143-168, 228-248).  Here all bins go in ONE launch and the index tensor is read
+    once: ``vox`` flat CUDA float32 (updated in place and returned), ``idx_before_bins`` int64 ``[n]``, ``values`` float32
+    ``[C, n]`` (row i = the layer's ``t * value_layer(t - i/(C-1))``), ``bin_stride`` = ``W*H``.  Differentiable in ``values``
+    and ``vox`` (the backward pass is the matching gather).  Indices are clamped from above like the reference's; a negative
+    index raises ``IndexError`` on the next ``check_put_indices`` (``put_`` would raise)."""
+    if not (vox.is_cuda and vox.dtype == torch.float32 and vox.is_contiguous() and vox.dim() == 1):
+        raise _lib.V2VError(-1, "vox must be a flat contiguous CUDA float32 tensor (no CPU fallback)")
+    idx = idx_before_bins.to(device=vox.device, dtype=torch.int64).contiguous().reshape(-1)
+    values = values.to(device=vox.device, dtype=torch.float32)
+    if values.dim() == 1:
+        values = values[None]
+    if values.shape[1] != idx.numel():
+        raise ValueError("values must be [C, n] for n indices")
+    return _PutAccumulateBins.apply(vox, idx, values.contiguous(), int(bin_stride))
+
+
+def put_accumulate(vox: torch.Tensor, idx: torch.Tensor, values: torch.Tensor) -> torch.Tensor:
+    """``vox.put_(idx, values, accumulate=True)`` for one bin (same kernel, C = 1)."""
+    return put_accumulate_bins(vox, idx, values.reshape(1, -1), 0)

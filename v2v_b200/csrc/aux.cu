@@ -355,3 +355,59 @@ extern "C" int v2v_voxel_normalize(float* voxel, int32_t clips, int64_t elems_pe
   V2V_CUDA(cudaGetLastError());
   return V2V_OK;
 }
+
+// ---- learned-representation scatter (NER-Net quantization layer, model/nernet/representation_modules.py:143-168) ----
+namespace v2v {
+namespace {
+template <bool PUT>
+__global__ void __launch_bounds__(256) put_take_bins_kernel(float* out, int64_t numel, const int64_t* idx, float* values, int64_t n, int bins,
+                                                            int64_t stride, long long* bad) {
+  long long nbad = 0;
+  for (int64_t e = static_cast<int64_t>(blockIdx.x) * 256 + threadIdx.x; e < n; e += static_cast<int64_t>(gridDim.x) * 256) {
+    const int64_t base = idx[e];                     // one index load serves every bin of the event
+    for (int b = 0; b < bins; ++b) {
+      int64_t i = base + stride * b;
+      if (i > numel - 1) i = numel - 1;              // torch.clamp(idx, max=numel-1), :166
+      if (i < 0) {
+        ++nbad;
+        if (!PUT) values[static_cast<int64_t>(b) * n + e] = 0.f;
+        continue;
+      }
+      if (PUT) atomicAdd(out + i, values[static_cast<int64_t>(b) * n + e]);
+      else values[static_cast<int64_t>(b) * n + e] = out[i];
+    }
+  }
+  if (PUT && bad && nbad) atomicAdd(reinterpret_cast<unsigned long long*>(bad), static_cast<unsigned long long>(nbad));
+}
+}  // namespace
+}  // namespace v2v
+
+extern "C" int v2v_put_accumulate_bins(float* out, int64_t out_numel, const int64_t* idx, const float* values, int64_t n, int32_t num_bins,
+                                       int64_t bin_stride, long long* bad, void* stream) {
+  using namespace v2v;
+  V2V_REQUIRE(out_numel >= 1 && n >= 0 && num_bins >= 1, V2V_ERR_INVALID_ARG, "bad sizes");
+  if (n == 0) return V2V_OK;
+  V2V_REQUIRE(out && idx && values, V2V_ERR_INVALID_ARG, "NULL pointer");
+  int64_t blocks = (n + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  put_take_bins_kernel<true><<<static_cast<unsigned int>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      out, out_numel, idx, const_cast<float*>(values), n, num_bins, bin_stride, bad);
+  count_launch();
+  V2V_CUDA(cudaGetLastError());
+  return V2V_OK;
+}
+
+extern "C" int v2v_take_bins(const float* src, int64_t src_numel, const int64_t* idx, float* values_out, int64_t n, int32_t num_bins,
+                             int64_t bin_stride, void* stream) {
+  using namespace v2v;
+  V2V_REQUIRE(src_numel >= 1 && n >= 0 && num_bins >= 1, V2V_ERR_INVALID_ARG, "bad sizes");
+  if (n == 0) return V2V_OK;
+  V2V_REQUIRE(src && idx && values_out, V2V_ERR_INVALID_ARG, "NULL pointer");
+  int64_t blocks = (n + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  put_take_bins_kernel<false><<<static_cast<unsigned int>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      const_cast<float*>(src), src_numel, idx, values_out, n, num_bins, bin_stride, nullptr);
+  count_launch();
+  V2V_CUDA(cudaGetLastError());
+  return V2V_OK;
+}
