@@ -1,0 +1,78 @@
+"""GPU twins of test_properties_cpu.py: the kernels against the oracle on RANDOM shapes, thresholds, bin layouts and event
+streams drawn by hypothesis (ragged planes, single rows / columns, 2-frame clips, empty windows ...), through the C ABI.
+Counts and discrete voxels bit-exact; interpolated voxels within the fixed-point bound."""
+import numpy as np
+import pytest
+import torch
+from hypothesis import HealthCheck, given, settings, strategies as st
+
+import v2v_oracle as orc
+
+pytestmark = pytest.mark.gpu
+SET = dict(max_examples=60, deadline=None, suppress_health_check=[HealthCheck.function_scoped_fixture])
+
+
+def _video(rs, n, h, w):
+    base = rs.randint(0, 256, (h, w)).astype(np.int64)
+    steps = rs.randint(-40, 41, (n, h, w))
+    steps[0] = 0
+    return np.clip(base[None] + np.cumsum(steps, 0), 0, 255).astype(np.uint8)
+
+
+@given(seed=st.integers(0, 2 ** 31 - 1), t=st.integers(1, 3), bins=st.sampled_from([1, 2, 5]), fpb=st.sampled_from([1, 2]),
+       h=st.integers(1, 12), w=st.integers(1, 16), pos=st.floats(0.05, 1.5), gap=st.floats(1.0, 1.5), std=st.floats(0.0, 0.3),
+       external=st.booleans(), flags=st.sampled_from([0, 1, 2, 4]))
+@settings(**SET)
+def test_esim_random_shapes_equal_oracle(cuda_device, seed, t, bins, fpb, h, w, pos, gap, std, external, flags):
+    """Explicit random fields, any plane shape and bin layout, every kernel choice (library's, generic, throughput kernel on
+    small launches, one pixel per thread): the crossing counts equal the oracle's bit for bit, the statistics equal their
+    sums, and with external noise the voxels are the float32 rounding of the oracle's float64 values."""
+    import v2v_b200 as v2v
+    rs = np.random.RandomState(seed)
+    n = t * bins * fpb + 1
+    neg = pos * gap
+    video = _video(rs, n, h, w)
+    u0, hot, g = orc.esim_draw_randomness(n, h, w, 0.2, 0.5, rs)
+    per_interval = orc.esim_video_to_voxel(video, pos, neg, std, u0, hot, g, external)
+    ref = orc.bin_accumulate(per_interval, bins, fpb)
+    o = v2v.frames_to_voxel(torch.from_numpy(video).to(cuda_device), pos, neg, num_bins=bins, frames_per_bin=fpb, noise="explicit",
+                            base_noise_std=std, put_noise_external=external, u0=u0[None], hot_noise=hot[None], base_gauss=g[None],
+                            with_stats=not external, kernel_flags=flags)
+    got = o.voxel[0].cpu().numpy()
+    assert got.shape == ref.shape
+    if external:
+        assert np.allclose(got, ref, rtol=1e-5, atol=1e-5)
+    else:
+        assert np.array_equal(got.astype(np.float64), ref)
+        s = o.stats[0].cpu().numpy()
+        # (event totals are counted per interval, before a bin nets opposite signs)
+        assert s[0] == int(np.maximum(per_interval, 0).sum()) and s[1] == int(np.maximum(-per_interval, 0).sum())
+
+
+@given(seed=st.integers(0, 2 ** 31 - 1), ne=st.integers(0, 3000), wn=st.integers(1, 6), h=st.integers(1, 40), w=st.integers(1, 50),
+       bins=st.sampled_from([1, 2, 5, 15]), interp=st.booleans(), f32=st.booleans(), ranges=st.booleans())
+@settings(**SET)
+def test_scatter_random_streams_equal_oracle(cuda_device, seed, ne, wn, h, w, bins, interp, f32, ranges):
+    """Random sorted streams cut into random windows (empty ones included): every window equals TestH5Dataset.make_voxel's
+    restatement (data/testh5.py:60-90) — discrete exact, interpolated within the fixed-point bound, on both interpolated paths."""
+    import v2v_b200 as v2v
+    from v2v_b200 import _lib
+    rs = np.random.RandomState(seed)
+    ts = np.sort(rs.rand(ne) * 0.2 + 7.0).astype(np.float32 if f32 else np.float64)
+    xs = rs.randint(0, w, ne).astype(np.uint16)
+    ys = rs.randint(0, h, ne).astype(np.uint16)
+    ps = rs.randint(0, 2, ne).astype(np.uint8)
+    off = np.sort(np.concatenate([[0, ne], rs.randint(0, ne + 1, wn - 1)])).astype(np.int64)
+    got = v2v.voxelize_windows(xs, ys, ts, ps, off, bins, h, w, mode="h5_interp" if interp else "h5_discrete", out_dtype=torch.float64,
+                               kernel_flags=_lib.SCATTER_FLAG_RANGES if ranges else 0).cpu().numpy()
+    assert got.shape == (wn, bins, h, w)
+    for k in range(wn):
+        s = slice(off[k], off[k + 1])
+        if off[k + 1] == off[k]:
+            assert not got[k].any()
+            continue
+        ref = orc.make_voxel(ts[s], xs[s], ys[s], ps[s], bins, h, w, interp)
+        if interp:
+            assert np.allclose(got[k], ref, rtol=0, atol=2e-6 * max(1.0, np.abs(ref).max()))
+        else:
+            assert np.array_equal(got[k], ref)
