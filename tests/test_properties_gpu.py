@@ -79,3 +79,31 @@ def test_scatter_random_streams_equal_oracle(cuda_device, seed, ne, wn, h, w, bi
             assert np.allclose(got[k], ref, rtol=0, atol=max(2e-6 * max(1.0, np.abs(ref).max()), min(nwin, 255) * 2.0 ** -24 + nwin * 2.0 ** -31))
         else:
             assert np.array_equal(got[k], ref)
+
+
+@given(seed=st.integers(0, 2 ** 31 - 1), t=st.integers(1, 4), bins=st.sampled_from([1, 5]), h=st.integers(1, 24), w4=st.integers(1, 16),
+       ragged=st.booleans(), pos=st.floats(0.05, 1.0), gap=st.floats(1.0, 1.5), std=st.floats(0.0, 0.1), frac=st.sampled_from([0.0, 0.001, 0.05]),
+       hstd=st.floats(0.0, 10.0), base=st.integers(0, 1 << 20), flags=st.sampled_from([0, 1, 2, 4, 16]))
+@settings(**SET)
+def test_esim_production_mode_random_shapes(cuda_device, seed, t, bins, h, w4, ragged, pos, gap, std, frac, hstd, base, flags):
+    """The production noise mode (in-kernel generator) on random shapes and parameters: whatever kernel is chosen (library's
+    choice, generic, throughput kernel on small launches, one pixel per thread, bulk-copy ring) the run equals the CPU oracle
+    fed with the fields the generator drew for that (seed, global clip index) — dumped through the audit hook — bit for bit,
+    including the residual potential and the event statistics."""
+    import v2v_b200 as v2v
+    rs = np.random.RandomState(seed)
+    w = 4 * w4 + (int(rs.randint(1, 4)) if ragged else 0)
+    n = t * bins + 1
+    neg = pos * gap
+    video = _video(rs, n, h, w)
+    o = v2v.frames_to_voxel(torch.from_numpy(video).to(cuda_device), pos, neg, num_bins=bins, noise="philox", base_noise_std=std,
+                            hot_pixel_fraction=frac, hot_pixel_std=hstd, seed=seed, clip_index_base=base, with_stats=True,
+                            return_potential=True, kernel_flags=flags)
+    u0, hot, bn = v2v.philox_fields(n, h, w, base_noise_std=std, hot_pixel_fraction=frac, hot_pixel_std=hstd, seed=seed, clip_index_base=base)
+    u0, hot, bn = u0[0].cpu().numpy(), hot[0].cpu().numpy(), bn[0].cpu().numpy()
+    assert np.isfinite(bn).all() and np.isfinite(hot).all() and 0.0 <= u0.min() and u0.max() < 1.0
+    per_interval, pot = orc.esim_video_to_voxel(video, pos, neg, 1.0, u0, hot, bn, False, return_state=True)
+    assert np.array_equal(o.voxel[0].cpu().numpy().astype(np.float64), orc.bin_accumulate(per_interval, bins, 1))
+    assert np.array_equal(o.potential[0].cpu().numpy(), pot)
+    s = o.stats[0].cpu().numpy()
+    assert s[0] == int(np.maximum(per_interval, 0).sum()) and s[1] == int(np.maximum(-per_interval, 0).sum())
