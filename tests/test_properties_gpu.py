@@ -107,3 +107,31 @@ def test_esim_production_mode_random_shapes(cuda_device, seed, t, bins, h, w4, r
     assert np.array_equal(o.potential[0].cpu().numpy(), pot)
     s = o.stats[0].cpu().numpy()
     assert s[0] == int(np.maximum(per_interval, 0).sum()) and s[1] == int(np.maximum(-per_interval, 0).sum())
+
+
+@given(seed=st.integers(0, 2 ** 31 - 1), ne=st.integers(2, 4000), h=st.integers(1, 30), w=st.integers(1, 40), bins=st.sampled_from([1, 3, 5, 9]),
+       bilinear=st.booleans())
+@settings(**SET)
+def test_torch_voxel_random_streams_equal_oracle(cuda_device, seed, ne, h, w, bins, bilinear):
+    """events_to_voxel_torch / events_to_neg_pos_voxel_torch (utils/event_utils.py:466-541) on random streams in the dtypes its
+    callers pass (float32 coordinates, timestamps relative to the first event, polarities +-1): discrete exact, bilinear
+    within float32 summation order; the one-launch neg / pos split equals the two reference calls."""
+    import v2v_b200 as v2v
+    rs = np.random.RandomState(seed)
+    ts = np.sort(rs.rand(ne) * 0.3).astype(np.float32)
+    ts -= ts[0]
+    if ts[-1] == 0:
+        ts[-1] = np.float32(0.01)
+    xs = rs.randint(0, w, ne).astype(np.float32)
+    ys = rs.randint(0, h, ne).astype(np.float32)
+    ps = (2.0 * rs.randint(0, 2, ne) - 1.0).astype(np.float32)
+    ref = orc.events_to_voxel_f32(xs, ys, ts, ps, bins, (h, w), bilinear)
+    rp, rn = orc.events_to_neg_pos_voxel_f32(xs, ys, ts, ps, bins, (h, w), bilinear)
+    args = [torch.from_numpy(a) for a in (xs, ys, ts, ps)]
+    got = v2v.events_to_voxel_torch(*args, bins, sensor_size=(h, w), temporal_bilinear=bilinear).cpu().numpy()
+    gp, gn = v2v.events_to_neg_pos_voxel_torch(*args, bins, sensor_size=(h, w), temporal_bilinear=bilinear)
+    tol = dict(rtol=1e-5, atol=1e-5 * max(1.0, float(np.abs(ref).max())))
+    if bilinear:
+        assert np.allclose(got, ref, **tol) and np.allclose(gp.cpu().numpy(), rp, **tol) and np.allclose(gn.cpu().numpy(), rn, **tol)
+    else:
+        assert np.array_equal(got, ref) and np.array_equal(gp.cpu().numpy(), rp) and np.array_equal(gn.cpu().numpy(), rn)
