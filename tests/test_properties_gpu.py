@@ -135,3 +135,29 @@ def test_torch_voxel_random_streams_equal_oracle(cuda_device, seed, ne, h, w, bi
         assert np.allclose(got, ref, **tol) and np.allclose(gp.cpu().numpy(), rp, **tol) and np.allclose(gn.cpu().numpy(), rn, **tol)
     else:
         assert np.array_equal(got, ref) and np.array_equal(gp.cpu().numpy(), rp) and np.array_equal(gn.cpu().numpy(), rn)
+
+
+@given(seed=st.integers(0, 2 ** 31 - 1), n=st.integers(2, 9), h=st.integers(1, 14), w=st.integers(1, 18), cutoff=st.sampled_from([0.0, 15.0, 200.0]),
+       leak=st.sampled_from([0.0, 0.1, 2.0]), shot=st.sampled_from([0.0, 5.0, 40.0]), jitter=st.sampled_from([0.0, 0.2]),
+       model=st.sampled_from(["pn_related", "spatial_independent"]), u8=st.booleans(), flags=st.sampled_from([0, 1, 2]))
+@settings(**SET)
+def test_v2e_random_presets_equal_oracle(cuda_device, seed, n, h, w, cutoff, leak, shot, jitter, model, u8, flags):
+    """v2e-style core (data/v2v_core_v2e.py:401-581) on random shapes and feature combinations (low-pass, leak + jitter, shot
+    noise, both time-invariant threshold models, uint8 or float video: the wrapping intensity rescale of :190): the kernels fed
+    with the fields the oracle drew equal it bit for bit, whichever kernel runs."""
+    from v2v_b200.v2e import frames_to_voxel_v2e
+    rs = np.random.RandomState(seed)
+    video = _video(rs, n, h, w)
+    video = np.clip((video.astype(np.float64) - 127.5) * 2.1 + 127.5, 0, 255).astype(np.uint8)        # HDR degrade: many values >= 236
+    p = dict(threshold_model=model, thres_mean_mean=0.2, thres_mean_std=0.04, thres_diff_mean=0.02, thres_diff_std=0.03, cutoff_hz=cutoff,
+             leak_rate_hz=leak, shot_noise_rate_hz=shot, leak_jitter_fraction=jitter, noise_rate_cov_decades=0.1)
+    rec = {}
+    ref = orc.v2e_video_to_voxel(video if u8 else video.astype(np.float64), 24, p, np.random.RandomState(seed + 1), record=rec)
+    out = frames_to_voxel_v2e(torch.from_numpy(video).to(cuda_device), rec["pos_thres"][None], rec["neg_thres"][None], fps=24, cutoff_hz=cutoff,
+                              leak_rate_hz=leak, shot_noise_rate_hz=shot, leak_jitter_fraction=jitter, noise_rate=rec["noise_rate"][None],
+                              pos_thres_nominal=0.2 + 0.01, neg_thres_nominal=0.2 - 0.01, noise="explicit",
+                              leak_randn=np.stack(rec["leak_randn"])[None] if rec["leak_randn"] else None,
+                              pos_shot=np.stack(rec["pos_shot"]).astype(np.int32)[None] if rec["pos_shot"] else None,
+                              neg_shot=np.stack(rec["neg_shot"]).astype(np.int32)[None] if rec["neg_shot"] else None,
+                              u8_intensity=u8, kernel_flags=flags)
+    assert np.array_equal(out["voxel"][0, :, 0].cpu().numpy().astype(np.float64), ref)

@@ -76,7 +76,7 @@ def frames_to_voxel_v2e(frames: torch.Tensor, pos_thres, neg_thres, *, fps: floa
                         leak_randn=None, pos_shot=None, neg_shot=None, seed: int = 0, clip_index_base: int = 0,
                         with_stats: bool = False, lut: Optional[np.ndarray] = None,
                         return_fields: bool = False, frame_index=None, value_map=None,
-                        u8_intensity: bool = False) -> dict:
+                        u8_intensity: bool = False, kernel_flags: int = 0) -> dict:
     """CUDA uint8 ``[B,N,H,W]`` + per-pixel threshold maps ``[B,H,W]`` -> float32 ``[B,T,bins,H,W]``.
     ``u8_intensity``: the reference was handed a uint8 video, so its ``rescale_intensity_frame``
     (data/v2v_core_v2e.py:190) wrapped ``new_frame+20`` for values >= 236 (affects the low-pass and shot noise only).
@@ -140,7 +140,7 @@ def frames_to_voxel_v2e(frames: torch.Tensor, pos_thres, neg_thres, *, fps: floa
     d.seed, d.clip_index_base = int(seed) & 0xFFFFFFFFFFFFFFFF, int(clip_index_base)
     d.voxel, d.stats = _ptr(vox), _ptr(stats_t)
     d.frame_index, d.raw_frames_per_clip, d.value_map = _ptr(fidx_t), (M if fidx_t is not None else 0), _ptr(vmap_t)
-    d.kernel_flags = _env_kernel_flags() | (_lib.V2E_FLAG_U8_INTENSITY if u8_intensity else 0)
+    d.kernel_flags = int(kernel_flags) | _env_kernel_flags() | (_lib.V2E_FLAG_U8_INTENSITY if u8_intensity else 0)
     s = torch.cuda.current_stream(dev)
     lib = _lib.load()
     scales = None
