@@ -237,7 +237,8 @@ def video_to_voxel(video, FPS, threshold_model, thres_mean_mean, thres_mean_std,
                   pos_shot=None if pos_s is None else pos_s[None],
                   neg_shot=None if neg_s is None else neg_s[None])
     elif rng == "philox":
-        kw = dict(noise="philox", seed=0 if seed is None else seed)
+        # (the reference seeds NumPy only when a seed is given, :312-314: without one every call draws fresh noise)
+        kw = dict(noise="philox", seed=int(np.random.randint(0, 2 ** 31 - 1)) if seed is None else seed)
     else:
         raise ValueError("rng must be 'numpy' or 'philox'")
     if N < 2:
