@@ -513,13 +513,34 @@ def run_ours(args):
                 torch.cuda.synchronize(dev)
                 best = max(best, (1 << 30) / (a.elapsed_time(b) * 1e-3) / 1e9)
             link[name + "_gbs"] = best
-        del hb, db
+        # ... and the D2H rate while H2D traffic in the pipeline's own proportion (1 byte in per 4 bytes out) runs beside it
+        hb2 = torch.empty(1 << 28, dtype=torch.uint8).pin_memory()
+        db2 = torch.empty(1 << 28, dtype=torch.uint8, device=dev)
+        s_h2d = torch.cuda.Stream(dev)
+        best = 0.0
+        for _ in range(3):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            barrier()
+            s_h2d.wait_stream(torch.cuda.current_stream(dev))
+            a.record()
+            with torch.cuda.stream(s_h2d):
+                db2.copy_(hb2, non_blocking=True)
+            hb.copy_(db, non_blocking=True)
+            b.record()
+            torch.cuda.synchronize(dev)
+            best = max(best, (1 << 30) / (a.elapsed_time(b) * 1e-3) / 1e9)
+        link["d2h_gbs_with_h2d_beside"] = best
+        del hb, db, hb2, db2
         per_clip_s = max(N_FRAMES * H * W / (link["h2d_gbs"] * 1e9), T * BINS * H * W * 4 / (link["d2h_gbs"] * 1e9))
+        link["ceiling_duplex_clips_per_s_per_gpu"] = link["d2h_gbs_with_h2d_beside"] * 1e9 / (T * BINS * H * W * 4)
         link["ceiling_clips_per_s_per_gpu"] = 1.0 / per_clip_s
         link["note"] = ("measured on this rank while all ranks copy at the same time; ceiling = 1 / max(frame bytes / h2d, voxel bytes / d2h) "
-                        "per clip (full duplex): the float32 voxels are 80 % of the bytes")
+                        "per clip from the one-directional rates (the float32 voxels are 80 % of the bytes); ceiling_duplex = the same "
+                        "with the D2H rate measured while H2D traffic in the pipeline's proportion runs beside it: what the link gives "
+                        "this byte mix")
         e2e["host_link"] = link
         e2e["frac_of_host_link_ceiling"] = e2e["clips_per_s"] / world / link["ceiling_clips_per_s_per_gpu"]
+        e2e["frac_of_duplex_ceiling"] = e2e["clips_per_s"] / world / link["ceiling_duplex_clips_per_s_per_gpu"]
 
     secondary = None
     if rank == 0 and world == 1 and not args.no_secondary:

@@ -354,6 +354,16 @@ def test_host_pipeline_and_batch_api(cuda_device):
     torch.cuda.synchronize()
     assert torch.equal(host_out, ref["events"].cpu())
     assert torch.equal(st.cpu(), ref["stats"].cpu())
+    # back-to-back calls overlap (the second call's copies and kernels run under the first call's draining D2H stream) and
+    # reuse the staging slots: both results must still be whole after synchronize()
+    host_b = torch.empty_like(host_out).pin_memory()
+    host_out.zero_()
+    ref_b = vz.batch_to_tensors(fr, params, seed=9, clip_index_base=900, with_stats=True)
+    pipe.run(host_in, params, host_out, clip_index_base=40)
+    st_b = pipe.run(host_in, params, host_b, clip_index_base=900)
+    pipe.synchronize()
+    assert torch.equal(host_out, ref["events"].cpu()) and torch.equal(host_b, ref_b["events"].cpu())
+    assert torch.equal(st_b.cpu(), ref_b["stats"].cpu())
     # sharding invariance: clips simulated one by one with their global index give the same noise streams
     one = vz.batch_to_tensors(fr[3:4], params[3:4], seed=9, clip_index_base=43)
     assert torch.equal(one["events"][0], ref["events"][3])

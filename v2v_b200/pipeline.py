@@ -41,7 +41,7 @@ class HostPipeline:
     def run(self, host_frames: torch.Tensor, params: Sequence[dict], host_out: torch.Tensor,
             clip_index_base: int = 0, stats: Optional[torch.Tensor] = None):
         """host_frames: pinned uint8 [B,N,H,W]; host_out: pinned float32 [B,T,bins,H,W] (filled on return
-        of ``torch.cuda.synchronize`` / ``self.s_out.synchronize()``), or None to keep the voxels on the
+        of ``torch.cuda.synchronize`` / ``self.synchronize()``), or None to keep the voxels on the
         device (read them from ``self.device_voxels`` chunk by chunk via ``on_chunk``).  Returns the
         per-clip stats tensor."""
         B, n, h, w = host_frames.shape
@@ -80,6 +80,12 @@ class HostPipeline:
                     host_out[b0:b1].copy_(slot["fout"][:nb], non_blocking=True)
                 slot["done"] = torch.cuda.Event()
                 slot["done"].record(self.s_out)
-        cur.wait_stream(self.s_out)
+        # The current stream waits for the kernels (the returned statistics, ``device_voxels``) but NOT for the D2H copies:
+        # host memory is only safe to read after ``synchronize()`` anyway, and without that wait the next call's H2D copies
+        # and kernels run under this call's draining D2H stream (back-to-back calls keep the link busy: the bottleneck).
         cur.wait_stream(self.s_k)
         return all_stats
+
+    def synchronize(self):
+        """Block until every voxel of the calls so far is in ``host_out``."""
+        self.s_out.synchronize()
