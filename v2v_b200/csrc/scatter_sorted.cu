@@ -149,14 +149,39 @@ __global__ void __launch_bounds__(kSortThreads, 2) sort_chunks_kernel(const Sort
   uint2 rec[kPer];
   int where[kPer];                                  // (window - w0) * S + strip of a kept event, or -1
   long long ndrop = 0;
-  // phase 1: every load of the thread's events is issued before anything depends on one (the window search comes after)
+  // phase 1: every load of the thread's events is issued before anything depends on one (the window search comes after).
+  // h5 streams (16-bit coordinates, uint8 polarity, float64 timestamps, 16-byte aligned, full chunk): a thread takes kPer
+  // CONSECUTIVE events with seven 128/64-bit loads (a warp request covers 512 B - 2 KB) instead of kPer strided ones with
+  // 32 small loads; the order of the records inside a run does not matter.
   int wv[kPer];
   long long yv[kPer], xv[kPer];
   float pv[kPer];
   double tv[kPer];
+  static_assert(kPer == 8, "the vector form below loads eight events per thread");
+  auto al = [](const void* q, uintptr_t n) { return (reinterpret_cast<uintptr_t>(q) & (n - 1)) == 0; };
+  const bool vec = c16 && d.ps_dtype == V2V_U8 && d.ts_dtype == V2V_F64 && c1 - c0 == kChunk && al(d.ys, 16) && al(d.xs, 16) &&
+                   al(d.ps, 8) && al(d.ts, 16);
+  auto event_of = [&](int u) -> int64_t { return vec ? c0 + static_cast<int64_t>(threadIdx.x) * kPer + u : c0 + u * kSortThreads + threadIdx.x; };
+  if (vec) {
+    const int64_t e = c0 + static_cast<int64_t>(threadIdx.x) * kPer;
+    const uint4 y8 = *reinterpret_cast<const uint4*>(static_cast<const uint16_t*>(d.ys) + e);
+    const uint4 x8 = *reinterpret_cast<const uint4*>(static_cast<const uint16_t*>(d.xs) + e);
+    const uint2 p8 = *reinterpret_cast<const uint2*>(static_cast<const uint8_t*>(d.ps) + e);
+    const double2* t2 = reinterpret_cast<const double2*>(static_cast<const double*>(d.ts) + e);
+    const double2 ta = t2[0], tb = t2[1], tc = t2[2], td = t2[3];
+    const uint32_t yw[4] = {y8.x, y8.y, y8.z, y8.w}, xw[4] = {x8.x, x8.y, x8.z, x8.w}, pw2[2] = {p8.x, p8.y};
+    const double tt[8] = {ta.x, ta.y, tb.x, tb.y, tc.x, tc.y, td.x, td.y};
+#pragma unroll
+    for (int u = 0; u < kPer; ++u) {
+      yv[u] = (yw[u >> 1] >> ((u & 1) * 16)) & 0xffffu;
+      xv[u] = (xw[u >> 1] >> ((u & 1) * 16)) & 0xffffu;
+      pv[u] = static_cast<float>((pw2[u >> 2] >> ((u & 3) * 8)) & 0xffu);
+      tv[u] = tt[u];
+    }
+  } else {
 #pragma unroll
   for (int u = 0; u < kPer; ++u) {
-    const int64_t e = c0 + u * kSortThreads + threadIdx.x;
+    const int64_t e = event_of(u);
     yv[u] = xv[u] = -1;
     pv[u] = 0.f;
     tv[u] = 0.0;
@@ -173,11 +198,12 @@ __global__ void __launch_bounds__(kSortThreads, 2) sort_chunks_kernel(const Sort
     pv[u] = d.ps_dtype == V2V_U8 ? static_cast<float>(static_cast<const uint8_t*>(d.ps)[e]) : load_f32(d.ps, d.ps_dtype, e);
     tv[u] = d.ts_dtype == V2V_F64 ? static_cast<const double*>(d.ts)[e] : static_cast<double>(static_cast<const float*>(d.ts)[e]);
   }
+  }
   {
     int w = w0;
 #pragma unroll
     for (int u = 0; u < kPer; ++u) {
-      const int64_t e = c0 + u * kSortThreads + threadIdx.x;
+      const int64_t e = event_of(u);
       wv[u] = -1;
       if (e >= c1 || e < first || e >= last) continue;
       if (w0 != w1)                                   // (most chunks lie inside one window)
