@@ -2,26 +2,25 @@
 // data/testh5.py:60-69,74-80), one visit per event and no ordering precondition.
 //
 // The contiguous-range kernel in scatter.cu visits an event once per (tap, strip) item whose bin range contains it —
-// 16 times for 5 bins of 260 rows — because a bin's events are not ordered by row.  Here a counting sort by
-// (window, strip of rows) comes first:
-//   1. window constants (one thread per window: tau_last, the denominator of :76-77);
-//   2. count   : every event -> its window (contiguous chunks, a step search from the chunk's first window) and its strip
-//                y / R (only the row coordinate is read); chunk-local counters in shared memory, then one global
-//                reduction per touched (window, strip) and CTA;
-//   3. scan    : exclusive prefix sum of the counts (one CTA; windows x strips is a few thousand entries);
-//   4. fill    : the same traversal builds an 8-byte record per event {cell in the strip, floor(t_norm)+1, polarity sign,
-//                frac(t_norm) as 2^-30 fixed point}, reserves one range per touched (window, strip) and CTA in the
-//                segment cursors and writes the records there;
-//   5. scatter : one work item per (window, strip) holds ALL bins of its rows in shared memory as exact fixed-point
-//                pairs, reads only its own records (coalesced 8-byte loads), adds both temporal taps of an event in
-//                the same visit (max(0, 1-|t_norm-b|) is 1-frac for b = floor and frac for b = floor+1) and streams
-//                the finished planes out once with 128-bit stores.
+// 16 times for 5 bins of 260 rows — because a bin's events are not ordered by row.  Here every event is read ONCE:
+//   1. window constants (one thread per window: tau_last, the folded factor of :76-77, and — without a search — the
+//      window of the first event of every chunk that starts inside this window);
+//   2. sort    : one CTA per chunk of kChunk consecutive events builds an 8-byte record per kept event {cell in its strip,
+//                floor(t_norm)+1, polarity sign, frac(t_norm) as 2^-30 fixed point}, counts per (window, strip) in shared
+//                memory, turns the counters into offsets, stages the records in (window, strip) order and writes them back
+//                over the chunk's own slice of the record array with coalesced stores, next to a 16-bit table of run
+//                offsets (no global counters, no second traversal);
+//   3. scatter : one work item per (window, strip) holds ALL bins of its rows in shared memory as fixed-point words, reads
+//                only its own runs (one per chunk that overlaps the window; coalesced 8-byte loads), adds both temporal
+//                taps of an event in the same visit (max(0, 1-|t_norm-b|) is 1-frac for b = floor and frac for
+//                b = floor+1) and streams the finished planes out once with 128-bit stores.
 // Accumulation is integer, so the result does not depend on the (atomic) record order: deterministic; exact to
 // n * 2^-31 per cell like the contiguous-range kernel for items of more than 255 records, n * 2^-24 for the others
-// (one 32-bit word per cell, half the shared atomics).  Timestamps need not be sorted: every event's bin comes from its
-// own t_norm, as in the reference (events whose taps fall outside [0, bins) are dropped and counted).
-// Extra HBM traffic: three reads of the 13-byte events (the 2nd and 3rd mostly from L2) + 8 bytes written and read per
-// event, against 4 bytes per voxel cell written once.
+// (one 32-bit word per cell, half the shared atomics); items beyond 65535 records take one 64-bit word per cell.
+// Timestamps need not be sorted: every event's bin comes from its own t_norm, as in the reference (events whose taps
+// fall outside [0, bins) are dropped and counted).
+// Extra HBM traffic: 8 bytes written and read per event, against 13 bytes of event read once and 4 bytes per voxel cell
+// written once.
 #include "scatter_common.cuh"
 
 #include <type_traits>
