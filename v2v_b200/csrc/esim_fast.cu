@@ -546,7 +546,7 @@ bool esim_fast_eligible(const EsimArgs& a) {
   return true;
 }
 
-// Geometry (threads per CTA, CTAs per SM) per variant from same-box sweeps on B200 (profiles/r02_esim_geom_sweep.txt);
+// Geometry (threads per CTA, CTAs per SM) per variant from same-box sweeps on B200 (profiles/r02_esim_experiments.md section 5);
 // bits 8..11 of v2v_esim_desc.kernel_flags select another one for tuning.
 int launch_esim_fast(const EsimArgs& a, cudaStream_t s) {
   const int geom = (a.d.kernel_flags >> 8) & 0xf;
